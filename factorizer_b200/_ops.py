@@ -1,0 +1,262 @@
+"""torch.autograd.Function wrappers over the C ABI.  PyTorch provides device memory, streams and
+autograd bookkeeping; every byte of arithmetic happens in libfactorizer_b200.so."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+class Geometry:
+    """Window geometry of a (SW)Matricize for a given input (hashable, batch-independent)."""
+
+    def __init__(self, channels: int, size: Sequence[int], patch: Sequence[int], head_dim: int,
+                 shifts: Sequence[Sequence[int]]):
+        self.channels = int(channels)
+        self.size = tuple(int(s) for s in size)
+        self.patch = tuple(int(p) for p in patch)
+        self.head_dim = int(head_dim)
+        self.shifts = tuple(tuple(int(v) for v in s) for s in shifts)
+        self.heads = self.channels // self.head_dim
+        self.grid = tuple(s // p for s, p in zip(self.size, self.patch))
+        self.num_windows = 1
+        self.num_cols = 1
+        for g, p in zip(self.grid, self.patch):
+            self.num_windows *= g
+            self.num_cols *= p
+
+    def c_geom(self, batch: int) -> L.FzGeom:
+        return L.make_geom(batch, self.channels, self.size, self.patch, self.head_dim, self.shifts)
+
+    def mat_shape(self, batch: int) -> Tuple[int, int, int, int]:
+        return (len(self.shifts) * batch * self.heads, self.num_windows, self.head_dim, self.num_cols)
+
+    def vol_shape(self, batch: int) -> Tuple[int, ...]:
+        return (batch, self.channels, *self.size)
+
+
+class SolverSpec:
+    def __init__(self, kind: int, rank: int, num_iters: int, num_grad_steps: int, eps: float = 1e-16):
+        self.kind, self.rank, self.num_iters = int(kind), int(rank), int(num_iters)
+        self.num_grad_steps, self.eps = int(num_grad_steps), float(eps)
+
+    def c_solver(self) -> L.FzSolver:
+        return L.make_solver(self.kind, self.rank, self.num_iters, self.num_grad_steps, self.eps)
+
+
+def _check_vol(x: torch.Tensor, geom: Geometry, name: str) -> torch.Tensor:
+    x = L.require_cuda_f32(x, name)
+    if tuple(x.shape[1:]) != (geom.channels, *geom.size):
+        raise ValueError(f"{name}: expected (B, {geom.channels}, {', '.join(map(str, geom.size))}), "
+                         f"got {tuple(x.shape)}")
+    return x
+
+
+def _check_mat(y: torch.Tensor, geom: Geometry, name: str) -> Tuple[torch.Tensor, int]:
+    y = L.require_cuda_f32(y, name)
+    S = len(geom.shifts)
+    if y.dim() != 4 or tuple(y.shape[1:]) != (geom.num_windows, geom.head_dim, geom.num_cols) \
+            or y.shape[0] % (S * geom.heads):
+        raise ValueError(f"{name}: expected (S*B*{geom.heads}, {geom.num_windows}, {geom.head_dim}, "
+                         f"{geom.num_cols}), got {tuple(y.shape)}")
+    return y, y.shape[0] // (S * geom.heads)
+
+
+def _call(fn, *args) -> None:
+    L.check(fn(*args))
+
+
+# ---- standalone matricize ------------------------------------------------------------------------
+def _gather(x, geom: Geometry, divide: bool):
+    lib = L.lib()
+    B = x.shape[0]
+    y = torch.empty(geom.mat_shape(B), device=x.device, dtype=torch.float32)
+    g = geom.c_geom(B)
+    with torch.cuda.device(x.device):
+        fn = lib.fz_swmat_inverse_adjoint if divide else lib.fz_swmat_forward
+        _call(fn, L.ptr(x), L.ptr(y), ctypes.byref(g), L.stream_ptr(x.device))
+    return y
+
+
+def _scatter(y, batch: int, geom: Geometry, reference_inverse: bool):
+    lib = L.lib()
+    out = torch.empty(geom.vol_shape(batch), device=y.device, dtype=torch.float32)
+    g = geom.c_geom(batch)
+    with torch.cuda.device(y.device):
+        fn = lib.fz_swmat_inverse if reference_inverse else lib.fz_swmat_forward_adjoint
+        _call(fn, L.ptr(y), L.ptr(out), ctypes.byref(g), L.stream_ptr(y.device))
+    return out
+
+
+class SWMatForward(torch.autograd.Function):
+    """SWMatricize.forward / Matricize.forward (reference operations.py:266-272, 417-421)."""
+
+    @staticmethod
+    def forward(ctx, x, geom: Geometry):
+        x = _check_vol(x, geom, "x")
+        ctx.geom = geom
+        ctx.batch = x.shape[0]
+        return _gather(x, geom, divide=False)
+
+    @staticmethod
+    def backward(ctx, gy):
+        gy, _ = _check_mat(gy, ctx.geom, "grad")
+        return _scatter(gy, ctx.batch, ctx.geom, reference_inverse=False), None
+
+
+class SWMatInverse(torch.autograd.Function):
+    """SWMatricize.inverse_forward (operations.py:423-434) when ``averaged``; the plain
+    Reshape.inverse_forward (operations.py:274-280) otherwise."""
+
+    @staticmethod
+    def forward(ctx, y, geom: Geometry, averaged: bool):
+        y, batch = _check_mat(y, geom, "y")
+        ctx.geom, ctx.averaged = geom, averaged
+        return _scatter(y, batch, geom, reference_inverse=averaged)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _check_vol(g, ctx.geom, "grad")
+        return _gather(g, ctx.geom, divide=ctx.averaged), None, None
+
+
+# ---- NMF on matricised tensors -------------------------------------------------------------------
+def _nmf_forward(x3, u0, v0, spec: SolverSpec, want_uv: bool, want_y: bool):
+    lib = L.lib()
+    n, M, N = x3.shape
+    R = spec.rank
+    u = torch.empty((n, M, R), device=x3.device, dtype=torch.float32) if want_uv else None
+    v = torch.empty((n, N, R), device=x3.device, dtype=torch.float32) if want_uv else None
+    y = torch.empty((n, M, N), device=x3.device, dtype=torch.float32) if want_y else None
+    s = spec.c_solver()
+    with torch.cuda.device(x3.device):
+        _call(lib.fz_nmf_forward, L.ptr(x3), L.ptr(u0), L.ptr(v0), L.ptr(u), L.ptr(v), L.ptr(y), n, M, N,
+              ctypes.byref(s), L.stream_ptr(x3.device))
+    return u, v, y
+
+
+def _nmf_backward(x3, u0, v0, gy, gu, gv, spec: SolverSpec):
+    lib = L.lib()
+    n, M, N = x3.shape
+    gx = torch.empty_like(x3)
+    s = spec.c_solver()
+    with torch.cuda.device(x3.device):
+        _call(lib.fz_nmf_backward, L.ptr(x3), L.ptr(u0), L.ptr(v0), L.ptr(gy), L.ptr(gu), L.ptr(gv),
+              L.ptr(gx), n, M, N, ctypes.byref(s), L.stream_ptr(x3.device))
+    return gx
+
+
+def _flatten_batch(x: torch.Tensor, size) -> torch.Tensor:
+    M, N = size
+    if x.dim() < 2 or tuple(x.shape[-2:]) != (M, N):
+        raise ValueError(f"NMF built for matrices of size {(M, N)}, got input of shape {tuple(x.shape)}")
+    return x.reshape(-1, M, N)
+
+
+class NMFReconstruct(torch.autograd.Function):
+    """MatrixFactorization.forward = reconstruct(decompose(x))
+    (reference matrix_factorization.py:514-533, 544-546) as one kernel per direction."""
+
+    @staticmethod
+    def forward(ctx, x, u0, v0, spec: SolverSpec, size):
+        x = L.require_cuda_f32(x, "x")
+        x3 = _flatten_batch(x, size)
+        u0 = L.require_cuda_f32(u0, "u0")
+        v0 = L.require_cuda_f32(v0, "v0")
+        _, _, y = _nmf_forward(x3, u0, v0, spec, want_uv=False, want_y=True)
+        ctx.save_for_backward(x3, u0, v0)
+        ctx.spec, ctx.shape = spec, x.shape
+        return y.reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x3, u0, v0 = ctx.saved_tensors
+        gy = L.require_cuda_f32(gy, "grad").reshape(x3.shape)
+        gx = _nmf_backward(x3, u0, v0, gy, None, None, ctx.spec)
+        return gx.reshape(ctx.shape), None, None, None, None
+
+
+class NMFDecompose(torch.autograd.Function):
+    """MatrixFactorization.decompose (matrix_factorization.py:514-530): returns (u, v)."""
+
+    @staticmethod
+    def forward(ctx, x, u0, v0, spec: SolverSpec, size):
+        x = L.require_cuda_f32(x, "x")
+        x3 = _flatten_batch(x, size)
+        u0 = L.require_cuda_f32(u0, "u0")
+        v0 = L.require_cuda_f32(v0, "v0")
+        u, v, _ = _nmf_forward(x3, u0, v0, spec, want_uv=True, want_y=False)
+        ctx.save_for_backward(x3, u0, v0)
+        ctx.spec, ctx.shape = spec, x.shape
+        batch = x.shape[:-2]
+        return u.reshape(*batch, size[0], spec.rank), v.reshape(*batch, size[1], spec.rank)
+
+    @staticmethod
+    def backward(ctx, gu, gv):
+        x3, u0, v0 = ctx.saved_tensors
+        n, M, N = x3.shape
+        R = ctx.spec.rank
+        gu = None if gu is None else L.require_cuda_f32(gu, "grad_u").reshape(n, M, R)
+        gv = None if gv is None else L.require_cuda_f32(gv, "grad_v").reshape(n, N, R)
+        gx = _nmf_backward(x3, u0, v0, None, gu, gv, ctx.spec)
+        return gx.reshape(ctx.shape), None, None, None, None
+
+
+# ---- fused FactMixer core ------------------------------------------------------------------------
+_workspaces = {}
+
+
+def _workspace(device, nbytes: int) -> Optional[torch.Tensor]:
+    """Per-(device, stream) scratch for the tile-order counters; grown on demand, never shrunk."""
+    if nbytes == 0:
+        return None
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(nbytes, device=device, dtype=torch.uint8)
+        _workspaces[key] = ws
+    return ws
+
+
+class SWNMF(torch.autograd.Function):
+    """reshape -> act -> factorize -> reshape.inverse_forward of FactMixer.forward
+    (reference factorizer/factorizer.py:41-50): X is read once and Y written once."""
+
+    @staticmethod
+    def forward(ctx, x, u0, v0, geom: Geometry, spec: SolverSpec, relu: bool):
+        lib = L.lib()
+        x = _check_vol(x, geom, "x")
+        u0 = L.require_cuda_f32(u0, "u0")
+        v0 = L.require_cuda_f32(v0, "v0")
+        B = x.shape[0]
+        g, s = geom.c_geom(B), spec.c_solver()
+        y = torch.empty_like(x)
+        need_grad = x.requires_grad and torch.is_grad_enabled()
+        saved = None
+        with torch.cuda.device(x.device):
+            nsaved = lib.fz_swnmf_saved_bytes(ctypes.byref(g), ctypes.byref(s)) if need_grad else 0
+            if nsaved:
+                saved = torch.empty(nsaved, device=x.device, dtype=torch.uint8)
+            ws = _workspace(x.device, lib.fz_swnmf_workspace_bytes(ctypes.byref(g), ctypes.byref(s)))
+            _call(lib.fz_swnmf_forward, L.ptr(x), L.ptr(u0), L.ptr(v0), L.ptr(y), L.ptr(saved), L.ptr(ws),
+                  ctypes.byref(g), ctypes.byref(s), int(relu), L.stream_ptr(x.device))
+        ctx.save_for_backward(x, u0, v0, saved)
+        ctx.geom, ctx.spec, ctx.relu = geom, spec, relu
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = L.lib()
+        x, u0, v0, saved = ctx.saved_tensors
+        geom, spec = ctx.geom, ctx.spec
+        gy = _check_vol(gy, geom, "grad")
+        g, s = geom.c_geom(x.shape[0]), spec.c_solver()
+        gx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            ws = _workspace(x.device, lib.fz_swnmf_workspace_bytes(ctypes.byref(g), ctypes.byref(s)))
+            _call(lib.fz_swnmf_backward, L.ptr(x), L.ptr(gy), L.ptr(u0), L.ptr(v0), L.ptr(saved), L.ptr(gx),
+                  L.ptr(ws), ctypes.byref(g), ctypes.byref(s), int(ctx.relu), L.stream_ptr(x.device))
+        return gx, None, None, None, None, None

@@ -1,0 +1,159 @@
+// extern "C" entry points: argument validation, error strings, kernel selection.
+#include <string.h>
+
+#include "fz_common.cuh"
+#include "fz_internal.cuh"
+
+namespace fz {
+
+TlsState& tls() {
+    static thread_local TlsState s = {{0}, 0, 0};
+    return s;
+}
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tls().msg, sizeof(tls().msg), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+static thread_local int g_forced_path = -1;
+
+int make_dev_geom(const fz_geom* g, DevGeom* o) {
+    if (!g) return fail(FZ_ERR_INVALID, "null geometry");
+    if (g->batch < 0 || g->channels < 1 || g->head_dim < 1)
+        return fail(FZ_ERR_INVALID, "bad geometry: batch=%d channels=%d head_dim=%d", g->batch,
+                    g->channels, g->head_dim);
+    if (g->channels % g->head_dim)
+        return fail(FZ_ERR_INVALID, "channels=%d not divisible by head_dim=%d", g->channels, g->head_dim);
+    if (g->num_shifts < 1 || g->num_shifts > FZ_MAX_SHIFTS)
+        return fail(FZ_ERR_UNSUPPORTED, "num_shifts=%d outside 1..%d", g->num_shifts, FZ_MAX_SHIFTS);
+    o->B = g->batch;
+    o->C = g->channels;
+    o->d = g->head_dim;
+    o->heads = g->channels / g->head_dim;
+    o->S = g->num_shifts;
+    o->vox = 1;
+    o->G = 1;
+    o->P = 1;
+    for (int k = 0; k < 3; ++k) {
+        if (g->size[k] < 1 || g->patch[k] < 1 || g->size[k] % g->patch[k])
+            return fail(FZ_ERR_INVALID, "size[%d]=%d not divisible by patch[%d]=%d", k, g->size[k], k,
+                        g->patch[k]);
+        o->n[k] = g->size[k];
+        o->p[k] = g->patch[k];
+        o->g[k] = g->size[k] / g->patch[k];
+        o->vox *= g->size[k];
+        o->G *= o->g[k];
+        o->P *= o->p[k];
+    }
+    if (o->vox >= (1LL << 31)) return fail(FZ_ERR_UNSUPPORTED, "volume of %lld voxels too large", o->vox);
+    for (int s = 0; s < FZ_MAX_SHIFTS; ++s)
+        for (int k = 0; k < 3; ++k) o->sh[s][k] = s < g->num_shifts ? g->shifts[s][k] : 0;
+    o->mats_per_shift = (long long)o->B * o->heads * o->G;
+    return FZ_OK;
+}
+
+}  // namespace fz
+
+using namespace fz;
+
+extern "C" {
+
+int fz_version(void) { return FZ_VERSION; }
+const char* fz_last_error(void) { return tls().msg; }
+int fz_last_path(void) { return tls().path; }
+int fz_last_launches(void) { return tls().launches; }
+void fz_set_path(int path) { g_forced_path = path; }
+
+int fz_nmf_forward(const float* x, const float* u0, const float* v0, float* u, float* v, float* y,
+                   int64_t n, int32_t M, int32_t N, const fz_solver* s, void* stream) {
+    tls().launches = 0;
+    tls().path = 0;
+    int K;
+    if (int e = check_solver(s, M, N, &K)) return e;
+    if (n < 0) return fail(FZ_ERR_INVALID, "n=%lld < 0", (long long)n);
+    if (!x || !u0 || !v0) return fail(FZ_ERR_INVALID, "null input buffer");
+    NmfArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = x; a.u0 = u0; a.v0 = v0; a.u = u; a.v = v; a.y = y;
+    a.n = n; a.M = M; a.N = N; a.T = s->num_iters; a.K = K; a.kind = s->kind; a.eps = s->eps;
+    return generic_direct(a, s->rank, false, (cudaStream_t)stream);
+}
+
+int fz_nmf_backward(const float* x, const float* u0, const float* v0, const float* gy,
+                    const float* gu, const float* gv, float* gx, int64_t n, int32_t M, int32_t N,
+                    const fz_solver* s, void* stream) {
+    tls().launches = 0;
+    tls().path = 0;
+    int K;
+    if (int e = check_solver(s, M, N, &K)) return e;
+    if (n < 0) return fail(FZ_ERR_INVALID, "n=%lld < 0", (long long)n);
+    if (!x || !u0 || !v0 || !gx) return fail(FZ_ERR_INVALID, "null buffer");
+    NmfArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = x; a.u0 = u0; a.v0 = v0; a.gy = gy; a.gu = gu; a.gv = gv; a.gx = gx;
+    a.n = n; a.M = M; a.N = N; a.T = s->num_iters; a.K = K; a.kind = s->kind; a.eps = s->eps;
+    return generic_direct(a, s->rank, true, (cudaStream_t)stream);
+}
+
+size_t fz_swnmf_saved_bytes(const fz_geom* g, const fz_solver* s) {
+    DevGeom G;
+    if (make_dev_geom(g, &G) || !s) return 0;
+    return fast_saved_bytes(G, *s);
+}
+
+size_t fz_swnmf_workspace_bytes(const fz_geom* g, const fz_solver* s) {
+    DevGeom G;
+    if (make_dev_geom(g, &G) || !s) return 0;
+    return fast_workspace_bytes(G, *s);
+}
+
+int fz_swnmf_forward(const float* x, const float* u0, const float* v0, float* y, void* saved,
+                     void* workspace, const fz_geom* g, const fz_solver* s, int32_t relu_input,
+                     void* stream) {
+    tls().launches = 0;
+    DevGeom G;
+    if (int e = make_dev_geom(g, &G)) return e;
+    int K;
+    if (int e = check_solver(s, G.d, G.P, &K)) return e;
+    if (!x || !u0 || !v0 || !y) return fail(FZ_ERR_INVALID, "null buffer");
+    if (g_forced_path != 0 && fast_supported(G, *s)) {
+        tls().path = 1;
+        return fast_forward(x, u0, v0, y, saved, workspace, G, *s, relu_input, (cudaStream_t)stream);
+    }
+    tls().path = 0;
+    NmfArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = x; a.u0 = u0; a.v0 = v0; a.y = y;
+    a.n = G.mats_per_shift; a.M = G.d; a.N = G.P; a.T = s->num_iters; a.K = K; a.kind = s->kind;
+    a.eps = s->eps; a.G = G; a.relu = relu_input;
+    return generic_window(a, s->rank, false, (cudaStream_t)stream);
+}
+
+int fz_swnmf_backward(const float* x, const float* gy, const float* u0, const float* v0,
+                      const void* saved, float* gx, void* workspace, const fz_geom* g,
+                      const fz_solver* s, int32_t relu_input, void* stream) {
+    tls().launches = 0;
+    DevGeom G;
+    if (int e = make_dev_geom(g, &G)) return e;
+    int K;
+    if (int e = check_solver(s, G.d, G.P, &K)) return e;
+    if (!x || !gy || !u0 || !v0 || !gx) return fail(FZ_ERR_INVALID, "null buffer");
+    if (g_forced_path != 0 && fast_supported(G, *s)) {
+        tls().path = 1;
+        return fast_backward(x, gy, u0, v0, saved, gx, workspace, G, *s, K, relu_input,
+                             (cudaStream_t)stream);
+    }
+    tls().path = 0;
+    NmfArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = x; a.gy = gy; a.u0 = u0; a.v0 = v0; a.gx = gx;
+    a.n = G.mats_per_shift; a.M = G.d; a.N = G.P; a.T = s->num_iters; a.K = K; a.kind = s->kind;
+    a.eps = s->eps; a.G = G; a.relu = relu_input;
+    return generic_window(a, s->rank, true, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,44 @@
+// Cross-translation-unit declarations (not part of the C ABI).
+#pragma once
+#include "fz_common.cuh"
+
+namespace fz {
+
+struct NmfArgs {
+    // forward
+    const float* x;   // direct: (n,M,N); window: volume (B,C,D,H,W)
+    const float* u0;  // (M,R)
+    const float* v0;  // (N,R)
+    float* u;         // (n,M,R) or null
+    float* v;         // (n,N,R) or null
+    float* y;         // direct: (n,M,N) or null; window: volume
+    // backward
+    const float* gy;  // direct (n,M,N) / window: volume
+    const float* gu;  // (n,M,R) or null
+    const float* gv;  // (n,N,R) or null
+    float* gx;        // direct (n,M,N) / window: volume
+    long long n;      // matrices handled by this launch
+    int M, N, T, K, kind;
+    float eps;
+    // window mode
+    DevGeom G;
+    int shift;  // which window set this launch handles
+    int relu;
+};
+
+// fz_nmf_generic.cu
+int check_solver(const fz_solver* s, int M, int N, int* K);
+int generic_direct(const NmfArgs& a, int R, bool bwd, cudaStream_t st);
+int generic_window(NmfArgs a, int R, bool bwd, cudaStream_t st);
+
+// fz_swnmf_fast.cu
+bool fast_supported(const DevGeom& G, const fz_solver& s);
+size_t fast_saved_bytes(const DevGeom& G, const fz_solver& s);
+size_t fast_workspace_bytes(const DevGeom& G, const fz_solver& s);
+int fast_forward(const float* x, const float* u0, const float* v0, float* y, void* saved,
+                 void* workspace, const DevGeom& G, const fz_solver& s, int relu, cudaStream_t st);
+int fast_backward(const float* x, const float* gy, const float* u0, const float* v0,
+                  const void* saved, float* gx, void* workspace, const DevGeom& G,
+                  const fz_solver& s, int K, int relu, cudaStream_t st);
+
+}  // namespace fz

@@ -1,0 +1,98 @@
+"""FactMixer / FactorizerBlock / FactorizerStage: the block glue around the hot path, with the
+reference's constructor signatures and parameter names (factorizer/factorizer.py:9-122).
+
+``FactMixer.forward`` is where the fused kernel plugs in: when the configured
+``reshape -> act -> factorize -> reshape.inverse_forward`` chain is
+(Matricize | SWMatricize) -> (ReLU | Identity) -> NMF('mu' | 'hals'), the four steps run as one CUDA
+kernel per direction (X read once, Y written once); any other combination runs the same steps through
+the standalone kernels.  Linear / LayerNorm / MLP stay PyTorch library calls.
+"""
+from __future__ import annotations
+
+from torch import nn
+
+from . import _ops
+from .helpers import partialize
+from .layers import MLP, LayerNorm, Linear, PositionalEmbedding
+from .matrix_factorization import NMF, MatrixFactorization
+from .operations import Matricize, SWMatricize
+
+__all__ = ["FactMixer", "FactorizerBlock", "FactorizerStage"]
+
+
+class FactMixer(nn.Module):
+    """in_proj -> reshape -> act -> factorize -> inverse reshape -> out_proj -> dropout."""
+
+    def __init__(self, in_channels, out_channels, spatial_size,
+                 reshape=(Matricize, {"num_heads": 1, "grid_size": 1}), act=nn.ReLU, factorize=NMF,
+                 dropout=0.0, **kwargs):
+        super().__init__()
+        self.in_proj = Linear(in_channels, out_channels, bias=False)
+        self.reshape = partialize(reshape)((None, out_channels, *spatial_size))
+        self.act = partialize(act)()
+        self.reshaped_size = self.reshape.output_size[2:]
+        self.factorize = partialize(factorize)(self.reshaped_size, **kwargs)
+        # the reference passes `out_channels` as the (truthy) bias flag, factorizer.py:31
+        self.out_proj = Linear(in_channels, out_channels, out_channels)
+        self.dropout = nn.Dropout(dropout)
+
+    def _fusable(self) -> bool:
+        return (isinstance(self.reshape, (Matricize, SWMatricize))
+                and type(self.act) in (nn.ReLU, nn.Identity)
+                and isinstance(self.factorize, MatrixFactorization)
+                and not self.factorize.verbose)
+
+    def forward(self, x):
+        out = self.in_proj(x)
+        if self._fusable():
+            f = self.factorize
+            out = _ops.SWNMF.apply(out, f.init.u0, f.init.v0, self.reshape._geom, f.solver_spec(),
+                                   isinstance(self.act, nn.ReLU))
+        else:
+            out = self.reshape(out)
+            out = self.act(out)
+            out = self.factorize(out)
+            out = self.reshape.inverse_forward(out)
+        out = self.out_proj(out)
+        return self.dropout(out)
+
+
+class FactorizerBlock(nn.Module):
+    """x + fact(norm1(x)); x + mlp(norm2(x))  (reference factorizer.py:60-77)."""
+
+    def __init__(self, channels, spatial_size, norm=LayerNorm, dropout=0.0, mlp_ratio=2, **kwargs):
+        super().__init__()
+        self.norm1 = partialize(norm)(channels)
+        self.fact = FactMixer(channels, channels, spatial_size, dropout=dropout, **kwargs)
+        self.norm2 = partialize(norm)(channels)
+        self.mlp = MLP(channels, ratio=mlp_ratio, dropout=dropout)
+
+    def forward(self, x):
+        x = x + self.fact(self.norm1(x))
+        x = x + self.mlp(self.norm2(x))
+        return x
+
+
+class FactorizerStage(nn.Module):
+    """adapter -> positional embedding -> depth x FactorizerBlock (reference factorizer.py:80-122).
+    As in the reference, ``dropout`` only feeds the positional-embedding dropout (:91, :101-111)."""
+
+    def __init__(self, in_channels, out_channels, spatial_size, depth=1,
+                 adapter=(Linear, {"bias": False}), pos_embed=nn.Identity, dropout=0.0, **subblocks):
+        super().__init__()
+        if in_channels != out_channels:
+            self.adapter = partialize(adapter)(in_channels, out_channels)
+        self.pos_embed = partialize(pos_embed)(out_channels, spatial_size)
+        if len(list(self.pos_embed.parameters())) > 0:
+            self.pos_drop = nn.Dropout(dropout)
+        self.blocks = nn.ModuleList(
+            FactorizerBlock(out_channels, spatial_size, **subblocks) for _ in range(depth))
+
+    def forward(self, x):
+        out = self.adapter(x) if hasattr(self, "adapter") else x
+        out = self.pos_embed(out)
+        if hasattr(self, "pos_drop"):
+            out = self.pos_drop(out)
+        for blk in self.blocks:
+            out = blk(out)
+        return out

@@ -1,0 +1,77 @@
+"""Channels-first glue layers around the hot path.  These stay plain PyTorch (cuBLAS / cuDNN / ATen
+library kernels): SURVEY.md section 8(f) row 1 lists their fusion as the next step after the
+matricize+NMF core.  Module and parameter names match the reference so its checkpoints load:
+``Linear.linear`` (factorizer/layers/linear.py:43-58), ``LayerNorm.norm`` (layers/norm.py:25-34),
+``MLP.block.{0,3}`` (layers/mlp.py:40-63), ``PositionalEmbedding.pos`` (layers/pos_embed.py:70-89).
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+from torch import nn
+
+__all__ = ["Linear", "LayerNorm", "MLP", "PositionalEmbedding", "PosEmbed"]
+
+
+class Linear(nn.Module):
+    """Pointwise linear map over channels of a (B, C, *spatial) tensor (a k=1 Conv1d)."""
+
+    def __init__(self, in_channels: int, out_channels: int, bias: bool = True, device=None, dtype=None):
+        super().__init__()
+        self.flatten = nn.Flatten(start_dim=2)
+        self.linear = nn.Conv1d(in_channels, out_channels, kernel_size=1, bias=bias, device=device,
+                                dtype=dtype)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        shape = x.shape
+        y = self.linear(self.flatten(x))
+        return y.view(shape[0], -1, *shape[2:])
+
+
+class LayerNorm(nn.Module):
+    """LayerNorm over the channel axis of a channels-first tensor."""
+
+    def __init__(self, dim: int, **kwargs):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim, **kwargs)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        y = self.norm(x.movedim(1, -1))
+        return y.movedim(-1, 1)
+
+
+class MLP(nn.Module):
+    """Linear -> GELU -> Dropout -> Linear -> Dropout (reference default ratio 3.0, mlp.py:45)."""
+
+    def __init__(self, in_channels: int, out_channels: Optional[int] = None,
+                 hidden_channels: Optional[int] = None, ratio: float = 3.0, dropout=0.0, **kwargs):
+        super().__init__()
+        out_channels = out_channels or in_channels
+        hidden_channels = hidden_channels or int(ratio * in_channels)
+        p = tuple(dropout) if isinstance(dropout, (tuple, list)) else (dropout, dropout)
+        self.block = nn.Sequential(
+            Linear(in_channels, hidden_channels, **kwargs),
+            nn.GELU(),
+            nn.Dropout(p[0]),
+            Linear(hidden_channels, out_channels, **kwargs),
+            nn.Dropout(p[1]),
+        )
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.block(x)
+
+
+class PositionalEmbedding(nn.Module):
+    """Learnable additive positional embedding (1, C, *spatial)."""
+
+    def __init__(self, channels: int, spatial_size: Sequence[int]) -> None:
+        super().__init__()
+        self.pos = nn.Parameter(torch.empty(1, channels, *spatial_size))
+        nn.init.normal_(self.pos, std=1.0)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return x + self.pos
+
+
+PosEmbed = PositionalEmbedding

@@ -1,0 +1,131 @@
+/*
+ * factorizer_b200 -- C ABI of the B200-native (sm_100a) Factorizer hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every entry point
+ * replaces a piece of the reference's (pashtari/factorizer) PyTorch eager path; the reference
+ * interface it stands in for is cited as file:line relative to the reference checkout.
+ *
+ * Conventions
+ *   - all data pointers are DEVICE pointers to C-contiguous float32 buffers on the current device;
+ *     the caller owns every buffer, the library never allocates user-visible memory;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); every call is
+ *     asynchronous on that stream, performs no host synchronisation and is CUDA-graph capturable;
+ *   - return value 0 = success, otherwise one of FZ_ERR_*; a thread-local message is available from
+ *     fz_last_error().  No C++ exception crosses this boundary;
+ *   - volumes are (B, C, D, H, W) = NCDHW; inputs with fewer than three spatial dims pad
+ *     size/patch/shifts on the LEFT with 1/1/0;
+ *   - matricised tensors are (S*B*heads, G, d, P) with row index s*(B*heads) + b*heads + h,
+ *     window index (g0*G1+g1)*G2+g2, row dd (channel h*d+dd), column (q0*P1+q1)*P2+q2
+ *     (factorizer/factorization/operations.py:321-325, 417-421).
+ */
+#ifndef FACTORIZER_B200_H_
+#define FACTORIZER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FZ_VERSION 100          /* 0.1.0 */
+#define FZ_MAX_SHIFTS 8
+#define FZ_MAX_RANK 4
+
+enum {
+    FZ_OK = 0,
+    FZ_ERR_INVALID = 1,         /* malformed argument (null pointer, non-divisible geometry, ...) */
+    FZ_ERR_UNSUPPORTED = 2,     /* valid but outside what the kernels implement                    */
+    FZ_ERR_CUDA = 3             /* CUDA runtime / driver error (message carries cudaGetErrorString) */
+};
+
+enum { FZ_SOLVER_MU = 0, FZ_SOLVER_HALS = 1 };
+
+/* Window geometry of Matricize / SWMatricize
+ * (factorizer/factorization/operations.py:299-355 and :381-415). */
+typedef struct fz_geom {
+    int32_t batch;                      /* B                                                   */
+    int32_t channels;                   /* C = heads * head_dim                                */
+    int32_t size[3];                    /* D, H, W                                             */
+    int32_t patch[3];                   /* p0, p1, p2 (each must divide size)                  */
+    int32_t head_dim;                   /* d = rows M of every matrix                          */
+    int32_t num_shifts;                 /* S (1 for a plain Matricize)                         */
+    int32_t shifts[FZ_MAX_SHIFTS][3];   /* torch.roll shifts per window set; 0 = unshifted     */
+} fz_geom;
+
+/* The unrolled solver of MatrixFactorization.decompose
+ * (factorizer/factorization/matrix_factorization.py:461-530). */
+typedef struct fz_solver {
+    int32_t kind;                       /* FZ_SOLVER_MU (:241-247) or FZ_SOLVER_HALS (:210-229) */
+    int32_t rank;                       /* R, 1..FZ_MAX_RANK                                    */
+    int32_t num_iters;                  /* T                                                    */
+    int32_t num_grad_steps;             /* k: backward differentiates the last k iterations
+                                           (context(), :506-512); <0 or >T means T             */
+    float eps;                          /* 1e-16 (:200, :236)                                   */
+} fz_solver;
+
+int fz_version(void);
+const char* fz_last_error(void);
+
+/* ---- SWMatricize / Matricize, standalone and bit-exact ------------------------------------- */
+
+/* SWMatricize.forward (operations.py:417-421; Reshape.forward :266-272):
+ * x (B,C,D,H,W) -> y (S*B*heads, G, d, P).  Pure data movement. */
+int fz_swmat_forward(const float* x, float* y, const fz_geom* g, void* stream);
+
+/* SWMatricize.inverse_forward (operations.py:423-434; Reshape.inverse_forward :274-280):
+ * out = ((0.0 + inv_0) + inv_1 + ...) / S, summed in shift order, then one true division. */
+int fz_swmat_inverse(const float* y, float* x_out, const fz_geom* g, void* stream);
+
+/* Adjoint of fz_swmat_forward: gx = sum_s unmatricize_s(gy_s) (what autograd's CatBackward /
+ * RollBackward / permute chain computes for operations.py:417-421). */
+int fz_swmat_forward_adjoint(const float* gy, float* gx, const fz_geom* g, void* stream);
+
+/* Adjoint of fz_swmat_inverse: gy_s = matricize_s(g_out / S). */
+int fz_swmat_inverse_adjoint(const float* g_out, float* gy, const fz_geom* g, void* stream);
+
+/* ---- NMF on already-matricised tensors ------------------------------------------------------ */
+
+/* MatrixFactorization.decompose + reconstruct (matrix_factorization.py:514-533, 544-546) with
+ * RandomInit buffers (:28-58) broadcast to all `n` matrices.
+ * x (n,M,N); u0 (M,R); v0 (N,R); outputs u (n,M,R), v (n,N,R), y (n,M,N) -- each may be NULL. */
+int fz_nmf_forward(const float* x, const float* u0, const float* v0, float* u, float* v, float* y,
+                   int64_t n, int32_t M, int32_t N, const fz_solver* s, void* stream);
+
+/* dL/dx through the unrolled solver (replaces autograd's replay of the bmm/add/div/relu graph).
+ * gy = dL/d(u v^T) (n,M,N), gu = dL/du (n,M,R), gv = dL/dv (n,N,R): any subset may be NULL. */
+int fz_nmf_backward(const float* x, const float* u0, const float* v0, const float* gy,
+                    const float* gu, const float* gv, float* gx, int64_t n, int32_t M, int32_t N,
+                    const fz_solver* s, void* stream);
+
+/* ---- fused FactMixer core: reshape -> act -> factorize -> inverse (factorizer.py:41-50) ----- */
+
+/* Bytes of the `saved` buffer fz_swnmf_forward fills for fz_swnmf_backward (per-window iterate
+ * summaries), and of the scratch `workspace` both directions need (tile-order counters). */
+size_t fz_swnmf_saved_bytes(const fz_geom* g, const fz_solver* s);
+size_t fz_swnmf_workspace_bytes(const fz_geom* g, const fz_solver* s);
+
+/* y_vol = SWMatricize.inverse_forward(NMF(act(SWMatricize(x_vol)))), act = ReLU if relu_input.
+ * x, y: (B,C,D,H,W).  `saved` may be NULL when no backward will follow. */
+int fz_swnmf_forward(const float* x, const float* u0, const float* v0, float* y, void* saved,
+                     void* workspace, const fz_geom* g, const fz_solver* s, int32_t relu_input,
+                     void* stream);
+
+/* gx_vol = d<gy_vol, y_vol>/dx_vol.  `saved` is the buffer written by the matching forward (NULL
+ * forces a full recompute of the iterates). */
+int fz_swnmf_backward(const float* x, const float* gy, const float* u0, const float* v0,
+                      const void* saved, float* gx, void* workspace, const fz_geom* g,
+                      const fz_solver* s, int32_t relu_input, void* stream);
+
+/* Which implementation the last fz_swnmf_* call on this thread used: 0 = generic shared-memory
+ * kernels, 1 = the specialised TMA/register kernel.  For tests and the benchmark's bookkeeping. */
+int fz_last_path(void);
+/* Number of kernel launches issued by the last fz_* call on this thread. */
+int fz_last_launches(void);
+/* Force a path for fz_swnmf_*: -1 = automatic, 0 = generic only. */
+void fz_set_path(int path);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FACTORIZER_B200_H_ */

@@ -1,0 +1,238 @@
+"""GPU parity tests proper: every call goes through the C ABI (ctypes) and is compared with the
+committed golden vectors produced by the reference, and with the numpy oracle on the same inputs.
+Tolerances: bit-exact for matricize / inverse; rtol 1e-4 / atol 1e-5 (fp32) for NMF outputs and
+input gradients, as BASELINE.json's north_star states."""
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+import cases
+from conftest import assert_close, tol_ratio
+from oracle import factorizer_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ft():
+    import factorizer_b200
+    return factorizer_b200
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("name", list(cases.SW_CASES))
+def test_swmatricize_bit_exact(ft, dev, golden, name):
+    c = cases.SW_CASES[name]
+    g = golden["sw"]
+    mod = getattr(ft, c["cls"])((None, *c["x_shape"][1:]), **c["kw"])
+    x = torch.from_numpy(cases.make_array(name, c["x_shape"], "randn")).to(dev)
+    y = mod(x)
+    assert tuple(y.shape) == tuple(g[f"{name}/y_shape"])
+    assert cases.digest(_np(y)) == str(g[f"{name}/y_digest"])
+    w = torch.from_numpy(cases.make_array(name, tuple(y.shape), "randn", tag="w")).to(dev)
+    z = mod.inverse_forward(w)
+    assert cases.digest(_np(z)) == str(g[f"{name}/z_digest"])
+    rt = mod.inverse_forward(y)
+    assert cases.digest(_np(rt)) == str(g[f"{name}/rt_digest"])
+    assert bool(g[f"{name}/roundtrip_equal"]) == bool(torch.equal(rt, x))   # README.md:49-51
+
+
+@pytest.mark.parametrize("name", list(cases.SW_CASES))
+def test_swmatricize_autograd(ft, dev, name):
+    """forward/inverse adjoints against the oracle (gradients of <w, f(x)>)."""
+    c = cases.SW_CASES[name]
+    mod = getattr(ft, c["cls"])((None, *c["x_shape"][1:]), **c["kw"])
+    x_np = cases.make_array(name, c["x_shape"], "randn")
+    x = torch.from_numpy(x_np).to(dev).requires_grad_(True)
+    y = mod(x)
+    w_np = cases.make_array(name, tuple(y.shape), "randn", tag="w")
+    w = torch.from_numpy(w_np).to(dev).requires_grad_(True)
+    (gx,) = torch.autograd.grad((y * w).sum(), x)
+    z = mod.inverse_forward(w)
+    (gw,) = torch.autograd.grad((z * x.detach()).sum(), w)
+    kw = dict(c["kw"])
+    shifts = kw.pop("shifts", None)
+    H, d, grid, patch = O.resolve_geometry((None, *c["x_shape"][1:]), **kw)
+    n = len(c["x_shape"]) - 2
+    if c["cls"] == "SWMatricize":
+        shifts = O.normalise_shifts(O.default_shifts(patch) if shifts is None else shifts, n)
+        S = len(shifts)
+        parts = np.split(w_np, S, axis=0)
+        gx_ref = sum(O.unmatricize(p, x_np.shape[0], H, d, grid, patch, s) for p, s in zip(parts, shifts))
+        gw_ref = O.swmat_forward(x_np / np.float32(S), H, d, grid, patch, shifts)
+    else:
+        shifts = O.normalise_shifts([shifts], n)
+        gx_ref = O.unmatricize(w_np, x_np.shape[0], H, d, grid, patch, shifts[0])
+        gw_ref = O.swmat_forward(x_np, H, d, grid, patch, shifts)
+    assert_close(_np(gx), gx_ref, rtol=1e-6, atol=1e-6, what="gx")
+    np.testing.assert_array_equal(_np(gw), gw_ref)
+
+
+WELL_CONDITIONED = {n for n, c in cases.NMF_CASES.items() if c["solver"] == "mu" or c["rank"] == 1}
+
+
+@pytest.mark.parametrize("name", list(cases.NMF_CASES))
+def test_nmf_matches_reference(ft, dev, golden, name):
+    c = cases.NMF_CASES[name]
+    g = golden["nmf"]
+    M, N = c["shape"][-2:]
+    nmf = ft.NMF(size=(M, N), rank=c["rank"], num_iters=c["num_iters"], num_grad_steps=c["num_grad_steps"],
+                 init="uniform", solver=c["solver"])
+    nmf.load_state_dict({"init.u0": torch.from_numpy(g[f"{name}/u0"]), "init.v0": torch.from_numpy(g[f"{name}/v0"])})
+    nmf = nmf.to(dev)
+    x = torch.from_numpy(cases.make_array(name, c["shape"], c["dist"])).to(dev).requires_grad_(True)
+    gy = torch.from_numpy(cases.make_array(name, c["shape"], "randn", tag="gy")).to(dev)
+    y = nmf(x)                                               # fused decompose + reconstruct
+    (gx,) = torch.autograd.grad((y * gy).sum(), x)
+    u, v = nmf.decompose(x)                                  # factor outputs + their own backward
+    y2 = nmf.reconstruct(u, v)
+    (gx2,) = torch.autograd.grad((y2 * gy).sum(), x)
+    assert u.shape == (*c["shape"][:-2], M, c["rank"]) and v.shape == (*c["shape"][:-2], N, c["rank"])
+    assert (u >= 0).all() and (v >= 0).all()                 # reference tests/test_nmf.py:19-20
+    assert y.shape == x.shape
+    if name in WELL_CONDITIONED:
+        assert_close(_np(u), g[f"{name}/u"], what="u")
+        assert_close(_np(v), g[f"{name}/v"], what="v")
+        assert_close(_np(y), g[f"{name}/y"], what="y")
+        assert_close(_np(y2), g[f"{name}/y"], what="y via decompose")
+        assert_close(_np(gx), g[f"{name}/gx"], what="gx")
+        assert_close(_np(gx2), g[f"{name}/gx"], what="gx via decompose")
+    else:
+        ref_gap = max(tol_ratio(g[f"{name}/y"], g[f"{name}/y64"]), tol_ratio(g[f"{name}/gx"], g[f"{name}/gx64"]))
+        for yy, gg in ((y, gx), (y2, gx2)):
+            ours = max(tol_ratio(_np(yy), g[f"{name}/y64"]), tol_ratio(_np(gg), g[f"{name}/gx64"]))
+            assert ours <= max(1.0, 10 * ref_gap), (ours, ref_gap)
+
+
+def _fused_module(ft, c, g, name, dev):
+    xs = c["x_shape"]
+    reshape = getattr(ft, c["cls"])((None, *xs[1:]), **c["kw"])
+    nmf = ft.NMF(reshape.output_size[2:], init="uniform", **c["nmf"])
+    nmf.load_state_dict({"init.u0": torch.from_numpy(g[f"{name}/u0"]), "init.v0": torch.from_numpy(g[f"{name}/v0"])})
+    return reshape, nmf.to(dev)
+
+
+@pytest.mark.parametrize("path", ["auto", "generic"])
+@pytest.mark.parametrize("name", list(cases.FUSED_CASES))
+def test_fused_core_matches_reference(ft, dev, golden, name, path):
+    from factorizer_b200 import _lib, _ops
+    c = cases.FUSED_CASES[name]
+    g = golden["fused"]
+    reshape, nmf = _fused_module(ft, c, g, name, dev)
+    x = torch.from_numpy(cases.make_array(name, c["x_shape"], c["dist"])).to(dev).requires_grad_(True)
+    gy = torch.from_numpy(cases.make_array(name, c["x_shape"], "randn", tag="gy")).to(dev)
+    _lib.lib().fz_set_path(-1 if path == "auto" else 0)
+    try:
+        y = _ops.SWNMF.apply(x, nmf.init.u0, nmf.init.v0, reshape._geom, nmf.solver_spec(), c["relu"])
+        (gx,) = torch.autograd.grad((y * gy).sum(), x)
+    finally:
+        _lib.lib().fz_set_path(-1)
+    assert_close(_np(y), g[f"{name}/y"], what="y")
+    assert_close(_np(gx), g[f"{name}/gx"], what="gx")
+
+
+@pytest.mark.parametrize("name", ["fused_cfg2_16", "fused_mu_r2"])
+def test_unfused_chain_equals_fused(ft, dev, golden, name):
+    """reshape -> act -> factorize -> inverse through the standalone kernels agrees with the fused op."""
+    from factorizer_b200 import _ops
+    c = cases.FUSED_CASES[name]
+    g = golden["fused"]
+    reshape, nmf = _fused_module(ft, c, g, name, dev)
+    x = torch.from_numpy(cases.make_array(name, c["x_shape"], c["dist"])).to(dev).requires_grad_(True)
+    gy = torch.from_numpy(cases.make_array(name, c["x_shape"], "randn", tag="gy")).to(dev)
+    m = reshape(x)
+    if c["relu"]:
+        m = torch.relu(m)
+    y = reshape.inverse_forward(nmf(m))
+    (gx,) = torch.autograd.grad((y * gy).sum(), x)
+    assert_close(_np(y), g[f"{name}/y"], what="y")
+    assert_close(_np(gx), g[f"{name}/gx"], what="gx")
+
+
+def test_factorizer_block_matches_reference(ft, dev, golden):
+    name = "block_c16_16"
+    c = cases.BLOCK_CASES[name]
+    g = golden["block"]
+    blk = ft.FactorizerBlock(channels=c["channels"], spatial_size=c["spatial"], norm=ft.LayerNorm,
+                             reshape=(ft.SWMatricize, c["kw"]), act=nn.ReLU, factorize=ft.NMF,
+                             mlp_ratio=c["mlp_ratio"], dropout=0.0, **c["nmf"])
+    sd = {k.split("/sd/")[1]: torch.from_numpy(g[k]) for k in g.files if "/sd/" in k}
+    blk.load_state_dict(sd)
+    blk = blk.to(dev)
+    xs = (c["batch"], c["channels"], *c["spatial"])
+    x = torch.from_numpy(cases.make_array(name, xs, "randn")).to(dev).requires_grad_(True)
+    gy = torch.from_numpy(cases.make_array(name, xs, "randn", tag="gy")).to(dev)
+    y = blk(x)
+    params = dict(blk.named_parameters())
+    grads = torch.autograd.grad((y * gy).sum(), [x] + list(params.values()))
+    assert_close(_np(y), g[f"{name}/y"], what="y")
+    assert_close(_np(grads[0]), g[f"{name}/gx"], what="gx")
+    for (k, _), gp in zip(params.items(), grads[1:]):
+        ref = g[f"{name}/gp/{k}"]
+        # parameter gradients are sums over 8192 voxels of fp32 products: scale the bound accordingly
+        scale = max(1.0, float(np.abs(ref).max()))
+        assert_close(_np(gp) / scale, ref / scale, rtol=1e-4, atol=1e-4, what=f"grad {k}")
+
+
+def test_reference_test_nmf_port(ft, dev):
+    """Port of the reference's tests/test_nmf.py:7-39 onto CUDA tensors."""
+    size = (2, 4, 8, 16)
+    nmf = ft.NMF(size=(8, 16), rank=3, init="uniform", solver="hals").to(dev)
+    x = torch.rand(size, device=dev, requires_grad=True)
+    u, v = nmf.decompose(x)
+    assert u.shape == (2, 4, 8, 3) and v.shape == (2, 4, 16, 3)
+    assert (u >= 0).all() and (v >= 0).all()
+    assert nmf(x).shape == x.shape
+    u = torch.rand((2, 4, 8, 3), device=dev, requires_grad=True)
+    v = torch.rand((2, 4, 16, 3), device=dev, requires_grad=True)
+    assert nmf.reconstruct(u, v).shape == size
+    loss = nmf.loss(x, u, v)
+    assert loss.shape == size[:1] and (loss >= 0).all()
+
+
+def test_empty_batch(ft, dev):
+    nmf = ft.NMF(size=(8, 16), rank=1).to(dev)
+    y = nmf(torch.empty(0, 8, 16, device=dev))
+    assert y.shape == (0, 8, 16)
+
+
+def test_full_size_properties(ft, dev):
+    """BASELINE config 2 at its real size (1,32,128^3): size-independent properties.
+    (a) exact round trip of SWMatricize (README.md:49-51); (b) every window is independent and the
+    same u0/v0 serve all of them, so a volume tiled from one 8^3 window pattern per head gives an
+    output that is the same tiling; (c) HALS rank-1 of a rank-1 non-negative window reproduces it."""
+    from factorizer_b200 import _ops
+    C, n = 32, 128
+    sw = ft.SWMatricize((None, C, n, n, n), head_dim=8, patch_size=8)
+    torch.manual_seed(0)
+    x = torch.rand(1, C, n, n, n, device=dev)
+    y = sw(x)
+    assert y.shape == (8, 4096, 8, 512)
+    assert torch.equal(sw.inverse_forward(y), x)
+    del y
+    nmf = ft.NMF((8, 512), rank=1, num_iters=5, init="uniform", solver="hals").to(dev)
+    # (b) periodic volume with period 8 along every axis: shifted and unshifted windows all see a
+    # cyclic shift of the same matrix set, outputs must be periodic too
+    tile = torch.rand(1, C, 8, 8, 8, device=dev)
+    xp = tile.repeat(1, 1, 16, 16, 16).contiguous()
+    yp = _ops.SWNMF.apply(xp, nmf.init.u0, nmf.init.v0, sw._geom, nmf.solver_spec(), True)
+    ref = yp[:, :, :8, :8, :8].repeat(1, 1, 16, 16, 16)
+    assert torch.allclose(yp, ref, rtol=1e-5, atol=1e-6)
+    small = ft.SWMatricize((None, C, 8, 8, 8), head_dim=8, patch_size=8)
+    ys = _ops.SWNMF.apply(tile.contiguous(), nmf.init.u0, nmf.init.v0, small._geom, nmf.solver_spec(), True)
+    assert torch.allclose(yp[:, :, :8, :8, :8], ys, rtol=1e-4, atol=1e-5)
+    # (c) rank-1 windows are fixed points: a (channel) x b (voxel) with constant b over space
+    a = torch.rand(1, C, 1, 1, 1, device=dev) + 0.5
+    x1 = a.expand(1, C, n, n, n).contiguous()
+    y1 = _ops.SWNMF.apply(x1, nmf.init.u0, nmf.init.v0, sw._geom, nmf.solver_spec(), True)
+    assert torch.allclose(y1, x1, rtol=1e-4, atol=1e-5)
