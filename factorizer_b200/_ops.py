@@ -132,6 +132,8 @@ def _nmf_forward(x3, u0, v0, spec: SolverSpec, want_uv: bool, want_y: bool):
     v = torch.empty((n, N, R), device=x3.device, dtype=torch.float32) if want_uv else None
     y = torch.empty((n, M, N), device=x3.device, dtype=torch.float32) if want_y else None
     s = spec.c_solver()
+    if n == 0:
+        return u, v, y
     with torch.cuda.device(x3.device):
         _call(lib.fz_nmf_forward, L.ptr(x3), L.ptr(u0), L.ptr(v0), L.ptr(u), L.ptr(v), L.ptr(y), n, M, N,
               ctypes.byref(s), L.stream_ptr(x3.device))
@@ -143,6 +145,8 @@ def _nmf_backward(x3, u0, v0, gy, gu, gv, spec: SolverSpec):
     n, M, N = x3.shape
     gx = torch.empty_like(x3)
     s = spec.c_solver()
+    if n == 0:
+        return gx
     with torch.cuda.device(x3.device):
         _call(lib.fz_nmf_backward, L.ptr(x3), L.ptr(u0), L.ptr(v0), L.ptr(gy), L.ptr(gu), L.ptr(gv),
               L.ptr(gx), n, M, N, ctypes.byref(s), L.stream_ptr(x3.device))

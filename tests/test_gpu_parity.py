@@ -163,6 +163,10 @@ def test_factorizer_block_matches_reference(ft, dev, golden):
     name = "block_c16_16"
     c = cases.BLOCK_CASES[name]
     g = golden["block"]
+    # the glue Linear layers are cuDNN convolutions, which default to TF32 on CUDA; parity against
+    # the reference's fp32 CPU run needs true fp32 there (the NMF kernels never use TF32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     blk = ft.FactorizerBlock(channels=c["channels"], spatial_size=c["spatial"], norm=ft.LayerNorm,
                              reshape=(ft.SWMatricize, c["kw"]), act=nn.ReLU, factorize=ft.NMF,
                              mlp_ratio=c["mlp_ratio"], dropout=0.0, **c["nmf"])
