@@ -238,7 +238,7 @@ class SWNMF(torch.autograd.Function):
         B = x.shape[0]
         g, s = geom.c_geom(B), spec.c_solver()
         y = torch.empty_like(x)
-        need_grad = x.requires_grad and torch.is_grad_enabled()
+        need_grad = ctx.needs_input_grad[0]
         saved = None
         with torch.cuda.device(x.device):
             nsaved = lib.fz_swnmf_saved_bytes(ctypes.byref(g), ctypes.byref(s)) if need_grad else 0

@@ -19,7 +19,7 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
-static thread_local int g_forced_path = -1;
+static volatile int g_forced_path = -1;  // process-wide: autograd runs backward on its own thread
 
 int make_dev_geom(const fz_geom* g, DevGeom* o) {
     if (!g) return fail(FZ_ERR_INVALID, "null geometry");
