@@ -817,12 +817,15 @@ static long long latest_needed(const DevGeom& G, const FastParams& P, int s, int
 // Processing order: `when[set][row]` is a virtual time; chain heads run at time = row, dependants
 // `lag` rows after the last row they need.  forward: all early sets are heads, the final set depends
 // on all of them.  backward: set j depends on set j-1.
-static void build_order(const DevGeom& G, FastParams& P, bool forward) {
+static void build_order(const DevGeom& G, FastParams& P, bool forward, int pairs_in_flight) {
     const int NR = G.g[0] * G.g[1];
     static thread_local long long when[FZ_MAX_SHIFTS][kMaxOrder];
     struct Key { long long key; unsigned entry; };
     static thread_local Key keys[kMaxOrder];
-    int lag = 6;
+    // a dependant must trail by about two generations of in-flight windows (one to finish computing,
+    // one for its completion signal), measured in rows of its own set
+    const long long per_row_all_sets = (long long)G.heads * G.g[2] * G.S;
+    int lag = (int)((2LL * pairs_in_flight + per_row_all_sets - 1) / per_row_all_sets) + 2;
     if (const char* env = getenv("FZ_LAG_ROWS")) lag = atoi(env);
     if (forward) {
         for (int s = 0; s < G.S; ++s)
@@ -859,6 +862,7 @@ static void build_order(const DevGeom& G, FastParams& P, bool forward) {
     P.entries = n;
 }
 
+static int num_sms();
 static int fill_params(FastParams& P, const DevGeom& G, const fz_solver& s, int K, int relu, bool forward) {
     memset(&P, 0, sizeof(P));
     P.n0 = G.n[0]; P.n1 = G.n[1]; P.n2 = G.n[2];
@@ -882,7 +886,7 @@ static int fill_params(FastParams& P, const DevGeom& G, const fz_solver& s, int 
         P.dep_of[q] = (q > 0 && q < G.S) ? q - 1 : -1;
         P.signals[q] = forward ? (q < G.S && q != P.final_set) : (q + 1 < G.S);
     }
-    build_order(G, P, forward);
+    build_order(G, P, forward, num_sms() * (forward ? kFwdPairs : kBwdPairs));
     P.total_items = (long long)G.B * P.entries * P.TPR;
     P.T = s.num_iters; P.K = K; P.relu = relu; P.rec_floats = rec_floats_for(s.num_iters);
     P.eps = s.eps; P.inv_S = 1.0f / (float)G.S;

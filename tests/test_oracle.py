@@ -99,3 +99,24 @@ def test_fused_core(golden, name):
                           num_iters=nm["num_iters"], num_grad_steps=nm.get("num_grad_steps"))
     assert_close(y, g[f"{name}/y"], what="y")
     assert_close(gx, g[f"{name}/gx"], what="gx")
+
+
+C_CASES = [n for n, c in cases.FUSED_CASES.items()
+           if c["nmf"]["solver"] == "hals" and c["nmf"]["rank"] == 1 and len(c["x_shape"]) == 5]
+
+
+@pytest.mark.parametrize("name", C_CASES)
+def test_c_oracle_matches_golden(golden, name):
+    """oracle/nmf_oracle.c (the OpenMP CPU baseline) against the reference's outputs."""
+    from oracle import c_oracle
+    c = cases.FUSED_CASES[name]
+    g = golden["fused"]
+    H, d, grid, patch, shifts = _geom(c)
+    x = cases.make_array(name, c["x_shape"], c["dist"])
+    gy = cases.make_array(name, c["x_shape"], "randn", tag="gy")
+    nm = c["nmf"]
+    y = c_oracle.swnmf_forward(x, g[f"{name}/v0"], d, patch, shifts, relu=c["relu"], num_iters=nm["num_iters"])
+    gx = c_oracle.swnmf_backward(x, gy, g[f"{name}/v0"], d, patch, shifts, relu=c["relu"],
+                                 num_iters=nm["num_iters"], num_grad_steps=nm.get("num_grad_steps"))
+    assert_close(y, g[f"{name}/y"], what="y")
+    assert_close(gx, g[f"{name}/gx"], what="gx")
