@@ -51,11 +51,12 @@ constexpr int kMaxT = 8;
 constexpr int kFwdPairs = 8;          // 16 warps / CTA, 1 CTA / SM
 constexpr int kBwdPairs = 4;          // 8 warps / CTA, 1 CTA / SM
 constexpr int kFacFloats = 520;       // u (8) + v (512) per early-set window
-constexpr int kRecStride = 80;        // shared-memory floats reserved per window record (9 T rounded up, T <= 8)
+constexpr int kRecStride = 144;       // shared-memory floats reserved per window record (T <= 8: 72 + 72)
 
 struct alignas(64) FastParams {
     CUtensorMap tm_x;     // X volume
     CUtensorMap tm_g;     // dY volume (backward)
+    CUtensorMap tm_out;   // output volume: dX (backward: partial-sum load, tile store) / Y (forward: half-tile store, box (8,8,4,8,1))
     const float* x;
     const float* gy;
     float* out;
@@ -71,9 +72,11 @@ struct alignas(64) FastParams {
     int final_set;
     long long vox;
     int NR, TPR, tpr_shift, entries, per_sample, total_items;
-    int T, K, relu, rec_floats;
+    int T, K, relu;
+    int rec_floats;       // floats per saved window record: [u_t (8T) | b_t (T) | pad to 4 | Gam (64) | r (8)]
+    int rec_head;         // offset of Gam = 9T rounded up to 4
     float eps, inv_S;
-    int debug;            // FZ_DEBUG_FLAGS: 1 = skip dependency waits, 2 = skip output (timing experiments only)
+    int debug;            // FZ_DEBUG_FLAGS (timing experiments only): 1 = skip dependency waits, 2 = skip output
     unsigned order[kMaxOrder];  // (set << 29) | (head << 20) | (g0 << 10) | g1, in processing order
 };
 
@@ -116,9 +119,24 @@ __device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* m, u
     asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(cw), "r"(ch), "r"(cd), "r"(cc), "r"(cb) : "memory");
 }
+__device__ __forceinline__ void tma_store_tile(const CUtensorMap* m, const void* src, int cw, int ch, int cd, int cc, int cb) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                 ::"l"(m), "r"(smem_u32(src)), "r"(cw), "r"(ch), "r"(cd), "r"(cc), "r"(cb) : "memory");
+}
+// contiguous shared -> global bulk copy (bytes: multiple of 16), completion through the bulk async-group
+__device__ __forceinline__ void bulk_store_1d(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
@@ -285,6 +303,14 @@ __device__ __forceinline__ void wait_rows(const FastParams& P, const Info& it, i
     for (int q = 0; q < 4; ++q)
         while (ld_poll(d.p[q]) < P.TPR) __nanosleep(64);
 }
+// Completion of a window whose output left through TMA / bulk stores that the caller has already waited
+// for with cp.async.bulk.wait_group 0.  That wait alone is NOT enough to publish with a relaxed
+// reduction: measured on B200, a dependent window then occasionally reads the previous contents of
+// the tile (the bulk writes are complete for the issuing thread, not yet performed at gpu scope), so
+// the counter is bumped with release semantics.
+__device__ __forceinline__ void signal_row_done(const FastParams& P, int set, int b, int rowid) {
+    red_release_add(P.ctr + 2 + ((long long)set * P.B + b) * P.heads * P.NR + rowid, 1);
+}
 __device__ __forceinline__ void signal_row(const FastParams& P, int set, int b, int rowid) {
     red_release_add(P.ctr + 2 + ((long long)set * P.B + b) * P.heads * P.NR + rowid, 1);
 }
@@ -412,9 +438,16 @@ struct alignas(16) PairShared {       // static shared memory, one per pair
     int oready;
 };
 
-__device__ __forceinline__ int claim(const FastParams& P) { return atomicAdd(P.ctr, 1); }
+// Next item of the global work queue.  Inline PTX on purpose: nvcc turns atomicAdd() under a lane
+// predicate into its warp-aggregated form, which shuffles the RESULT around immediately and so stalls
+// the warp for the full round trip; here the result is not looked at until the next window.
+__device__ __forceinline__ int claim(const FastParams& P) {
+    int v;
+    asm volatile("atom.relaxed.gpu.global.add.s32 %0, [%1], 1;" : "=r"(v) : "l"(P.ctr) : "memory");
+    return v;
+}
 
-struct Pending { int set, b, rowid; };   // leader: finished window whose completion is not yet published
+struct Pending { int set, b, rowid, bulk; };   // bulk: the output left through a bulk async store   // leader: finished window whose completion is not yet published
 
 // =====================================================================================================
 // forward
@@ -597,7 +630,7 @@ __global__ void __launch_bounds__(kBwdPairs * 64, 1) swnmf_bwd_fast(const __grid
     float* gin = xin + 4096;         // dY tile
     float* oin = gin + 4096;         // partial dX of the previous window set of the chain
     PairShared& ps = ps_all[c.pair];
-    const int rec_lanes = P.rec_floats >> 2;
+    const int rec_lanes = P.rec_head >> 2;
 
     for (int j = threadIdx.x; j < 512; j += blockDim.x) v0s[j] = P.v0[j];
     int claimed = 0;
@@ -818,6 +851,8 @@ __global__ void __launch_bounds__(kBwdPairs * 64, 1) swnmf_bwd_fast(const __grid
     if (c.second && pend.set >= 0) signal_row(P, pend.set, pend.b, pend.rowid);
 }
 
+#include "fz_swnmf_gram.cuh"
+
 // =====================================================================================================
 // host side
 // =====================================================================================================
@@ -837,14 +872,14 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-static int make_map(CUtensorMap* m, const void* ptr, const DevGeom& G) {
+static int make_map(CUtensorMap* m, const void* ptr, const DevGeom& G, int box_d = 8) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return fail(FZ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     if (reinterpret_cast<uintptr_t>(ptr) & 15) return fail(FZ_ERR_INVALID, "volume pointer %p is not 16-byte aligned", ptr);
     cuuint64_t dims[5] = {(cuuint64_t)G.n[2], (cuuint64_t)G.n[1], (cuuint64_t)G.n[0], (cuuint64_t)G.C, (cuuint64_t)G.B};
     cuuint64_t strides[4] = {(cuuint64_t)G.n[2] * 4, (cuuint64_t)G.n[2] * G.n[1] * 4, (cuuint64_t)G.vox * 4,
                              (cuuint64_t)G.vox * G.C * 4};
-    cuuint32_t box[5] = {8, 8, 8, 8, 1};
+    cuuint32_t box[5] = {8, 8, (cuuint32_t)box_d, 8, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(ptr), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -853,7 +888,8 @@ static int make_map(CUtensorMap* m, const void* ptr, const DevGeom& G) {
     return FZ_OK;
 }
 
-static int rec_floats_for(int T) { return ((9 * T + 3) / 4) * 4; }
+static int rec_head_for(int T) { return ((9 * T + 3) / 4) * 4; }
+static int rec_floats_for(int T) { return rec_head_for(T) + 72; }
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 bool fast_supported(const DevGeom& G, const fz_solver& s) {
@@ -917,14 +953,15 @@ static long long latest_needed(const DevGeom& G, const FastParams& P, int s, int
 // its own end) when the dependency is finishing.
 // forward: all early sets are heads, the final set depends on all of them.  backward: set j depends
 // on set j-1.
-static void build_order(const DevGeom& G, FastParams& P, bool forward, int pairs_in_flight) {
+static void build_order(const DevGeom& G, FastParams& P, bool forward, int windows_in_flight) {
     const int NR = G.g[0] * G.g[1];
     static thread_local long long when[FZ_MAX_SHIFTS][kMaxOrder];
     struct Key { long long key; unsigned entry; };
     static thread_local Key keys[kMaxOrder];
     const long long per_unit = (long long)G.g[2] * G.S;
-    int lag = (int)((pairs_in_flight + per_unit - 1) / per_unit) + 2;
-    if (const char* env = getenv("FZ_LAG_ROWS")) lag = atoi(env);
+    // `windows_in_flight`: how many windows are claimed but not finished at any time
+    int lag = (int)((windows_in_flight + per_unit - 1) / per_unit) + 2;
+    if (const char* env = getenv(forward ? "FZ_LAG_FWD" : "FZ_LAG_BWD")) lag = atoi(env);
     int n = 0;
     for (int h = 0; h < G.heads; ++h) {
         const long long base = (long long)h * NR;
@@ -963,11 +1000,12 @@ struct PlanKey {
 };
 
 static int fill_params(FastParams& P, PlanKey& cached, const DevGeom& G, const fz_solver& s, int K, int relu, bool forward) {
+    const bool gram = relu != 0;
     PlanKey key;
     memset(&key, 0, sizeof(key));
     key.B = G.B; key.C = G.C; key.S = G.S; key.T = s.num_iters; key.K = K; key.relu = relu; key.forward = forward;
     key.sms = num_sms();
-    { const char* env = getenv("FZ_LAG_ROWS"); key.lag_env = env ? atoi(env) + 1 : 0; }
+    { const char* env = getenv(forward ? "FZ_LAG_FWD" : "FZ_LAG_BWD"); key.lag_env = env ? atoi(env) + 1 : 0; }
     for (int k = 0; k < 3; ++k) key.n[k] = G.n[k];
     for (int q = 0; q < G.S; ++q)
         for (int k = 0; k < 3; ++k) key.sh[q][k] = G.sh[q][k];
@@ -1002,10 +1040,15 @@ static int fill_params(FastParams& P, PlanKey& cached, const DevGeom& G, const f
         P.dep_of[q] = (q > 0 && q < G.S) ? q - 1 : -1;
         P.signals[q] = forward ? (q < G.S && q != P.final_set) : (q + 1 < G.S);
     }
-    build_order(G, P, forward, num_sms() * (forward ? kFwdPairs : kBwdPairs));
+    // direct kernels: a pair holds three claimed windows (current, next, next-but-one); Gram forward:
+    // a warp holds two; Gram backward: a pair holds three
+    int in_flight;
+    if (gram) in_flight = forward ? 2 * num_sms() * kGFwdWarps : 2 * num_sms() * kGBwdPairs;
+    else in_flight = 2 * num_sms() * (forward ? kFwdPairs : kBwdPairs);
+    build_order(G, P, forward, in_flight);
     P.per_sample = P.entries * P.TPR;
     P.total_items = G.B * P.per_sample;
-    P.T = s.num_iters; P.K = K; P.relu = relu; P.rec_floats = rec_floats_for(s.num_iters);
+    P.T = s.num_iters; P.K = K; P.relu = relu; P.rec_floats = rec_floats_for(s.num_iters); P.rec_head = rec_head_for(s.num_iters);
     P.eps = s.eps; P.inv_S = 1.0f / (float)G.S;
     cached = key;
     return FZ_OK;
@@ -1020,6 +1063,7 @@ int fast_forward(const float* x, const float* u0, const float* v0, float* y, voi
     if (int e = fill_params(P, cached, G, s, 0, relu, true)) return e;
     if (int e = make_map(&P.tm_x, x, G)) return e;
     P.tm_g = P.tm_x;
+    if (int e = make_map(&P.tm_out, y, G, relu ? 4 : 8)) return e;
     if (reinterpret_cast<uintptr_t>(y) & 15) return fail(FZ_ERR_INVALID, "output pointer %p is not 16-byte aligned", (void*)y);
     P.x = x; P.gy = nullptr; P.out = y; P.v0 = v0; P.saved = static_cast<float*>(saved);
     P.ctr = static_cast<int*>(workspace);
@@ -1028,15 +1072,26 @@ int fast_forward(const float* x, const float* u0, const float* v0, float* y, voi
     const size_t smem = (size_t)kFwdPairs * kTileBytes;
     static bool attr_set = false;
     if (!attr_set) {
-        FZ_CUDA_CHECK(cudaFuncSetAttribute(swnmf_fwd_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         FZ_CUDA_CHECK(cudaFuncSetAttribute(swnmf_fwd_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    int ctas_needed = (P.total_items + kFwdPairs - 1) / kFwdPairs;
-    int grid = num_sms();
-    if (ctas_needed < grid) grid = ctas_needed;
-    if (relu) swnmf_fwd_fast<true><<<grid, kFwdPairs * 64, smem, st>>>(P);
-    else swnmf_fwd_fast<false><<<grid, kFwdPairs * 64, smem, st>>>(P);
+    if (relu) {
+        const size_t gsmem = (size_t)kGFwdWarps * (kTileBytes + kTileBytes / 2);
+        static bool gattr = false;
+        if (!gattr) {
+            FZ_CUDA_CHECK(cudaFuncSetAttribute(swnmf_fwd_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+            gattr = true;
+        }
+        int ctas_needed = (P.total_items + kGFwdWarps - 1) / kGFwdWarps;
+        int grid = num_sms();
+        if (ctas_needed < grid) grid = ctas_needed;
+        swnmf_fwd_gram<<<grid, kGFwdWarps * 32, gsmem, st>>>(P);
+    } else {
+        int ctas_needed = (P.total_items + kFwdPairs - 1) / kFwdPairs;
+        int grid = num_sms();
+        if (ctas_needed < grid) grid = ctas_needed;
+        swnmf_fwd_fast<false><<<grid, kFwdPairs * 64, smem, st>>>(P);
+    }
     FZ_LAUNCH_CHECK();
     return FZ_OK;
 }
@@ -1052,6 +1107,7 @@ int fast_backward(const float* x, const float* gy, const float* u0, const float*
     if (int e = fill_params(P, cached, G, s, K, relu, false)) return e;
     if (int e = make_map(&P.tm_x, x, G)) return e;
     if (int e = make_map(&P.tm_g, gy, G)) return e;
+    if (int e = make_map(&P.tm_out, gx, G)) return e;
     P.x = x; P.gy = gy; P.out = gx; P.v0 = v0;
     P.saved = const_cast<float*>(static_cast<const float*>(saved));
     P.ctr = static_cast<int*>(workspace);
@@ -1059,15 +1115,26 @@ int fast_backward(const float* x, const float* gy, const float* u0, const float*
     const size_t smem = (size_t)kBwdPairs * 3 * kTileBytes;
     static bool attr_set = false;
     if (!attr_set) {
-        FZ_CUDA_CHECK(cudaFuncSetAttribute(swnmf_bwd_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         FZ_CUDA_CHECK(cudaFuncSetAttribute(swnmf_bwd_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    int ctas_needed = (P.total_items + kBwdPairs - 1) / kBwdPairs;
-    int grid = num_sms();
-    if (ctas_needed < grid) grid = ctas_needed;
-    if (relu) swnmf_bwd_fast<true><<<grid, kBwdPairs * 64, smem, st>>>(P);
-    else swnmf_bwd_fast<false><<<grid, kBwdPairs * 64, smem, st>>>(P);
+    if (relu) {
+        const size_t gsmem = (size_t)kGBwdPairs * 3 * kTileBytes;
+        static bool gattr = false;
+        if (!gattr) {
+            FZ_CUDA_CHECK(cudaFuncSetAttribute(swnmf_bwd_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+            gattr = true;
+        }
+        int ctas_needed = (P.total_items + kGBwdPairs - 1) / kGBwdPairs;
+        int grid = num_sms();
+        if (ctas_needed < grid) grid = ctas_needed;
+        swnmf_bwd_gram<<<grid, kGBwdPairs * 64, gsmem, st>>>(P);
+    } else {
+        int ctas_needed = (P.total_items + kBwdPairs - 1) / kBwdPairs;
+        int grid = num_sms();
+        if (ctas_needed < grid) grid = ctas_needed;
+        swnmf_bwd_fast<false><<<grid, kBwdPairs * 64, smem, st>>>(P);
+    }
     FZ_LAUNCH_CHECK();
     return FZ_OK;
 }

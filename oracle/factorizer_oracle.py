@@ -300,3 +300,81 @@ def swnmf_backward(x, gy_vol, u0, v0, H, d, grid, patch, shifts, relu=True, solv
     for j, s in enumerate(shifts):
         out = out + unmatricize(gm[j * n:(j + 1) * n], B, H, d, grid, patch, s)
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# Gram-matrix form of rank-1 HALS on non-negative windows (what the CUDA kernels evaluate when
+# act = ReLU).  Algebraically identical to nmf_forward / nmf_backward above whenever no ReLU of the
+# solver clips after the first half-step, which X >= 0 guarantees
+# (factorizer/factorization/matrix_factorization.py:224-227: a = x @ v >= 0).  Kept here so the
+# conditioning of the reformulation is pinned against the reference's golden vectors on CPU.
+# ----------------------------------------------------------------------------------------------
+def hals_r1_gram(x, v0, gy, num_iters=5, num_grad_steps=None, eps=EPS):
+    """x (n, M, N) >= 0, v0 (N,), gy (n, M, N) -> (y, dx), every op in x.dtype.
+
+    Forward: Gam = X X^T, r = X 1, a_1 = X v0; u_{t+1} = relu((rd_t (Gam u_t + eps r) + eps) /
+    (rd_t^2 (u_t Gam u_t + 2 eps u_t.r + N eps^2) + eps)), v_T = rd_T (X^T u_T + eps), y = u_T v_T^T.
+    Backward: SURVEY App. A.3 with vbar_t = X^T z_t + kappa_t 1 (t < T):
+    dX = rd_T u_T gv^T + M X + m 1^T + abar_L v_{L-1}^T."""
+    dt = x.dtype.type
+    x = np.ascontiguousarray(x)
+    n, M, N = x.shape
+    T = num_iters
+    K = T if num_grad_steps is None else max(1, min(T, num_grad_steps))
+    eps = dt(eps)
+    v0 = v0.astype(x.dtype)
+    Gm = np.einsum("nik,njk->nij", x, x).astype(x.dtype)
+    r = x.sum(-1).astype(x.dtype)
+    a = np.einsum("nik,k->ni", x, v0).astype(x.dtype)
+    b = np.full(n, (v0 * v0).sum(), dtype=x.dtype)
+    us, bs, rds = [], [], []
+    for t in range(T):
+        u = np.maximum((a + eps) / (b + eps)[:, None], 0).astype(x.dtype)
+        rd = (dt(1) / ((u * u).sum(-1) + eps)).astype(x.dtype)
+        us.append(u); bs.append(b.copy()); rds.append(rd)
+        if t < T - 1:
+            Gu = np.einsum("nij,nj->ni", Gm, u).astype(x.dtype)
+            a = ((Gu + eps * r) * rd[:, None]).astype(x.dtype)
+            b = (((u * Gu).sum(-1) + 2 * eps * (u * r).sum(-1) + dt(N) * eps * eps) * rd * rd).astype(x.dtype)
+    uT, rdT = us[-1], rds[-1]
+    vT = np.maximum((np.einsum("nik,ni->nk", x, uT) + eps) * rdT[:, None], 0).astype(x.dtype)
+    y = (uT[:, :, None] * vT[:, None, :]).astype(x.dtype)
+    if gy is None:
+        return y, None
+    gy = gy.astype(x.dtype)
+    gu = np.einsum("nik,nk->ni", gy, vT)
+    gv = np.einsum("nik,ni->nk", gy, uT).astype(x.dtype)
+    w = (gu + np.einsum("nik,nk->ni", x, gv * rdT[:, None])).astype(x.dtype)
+    e = (gv * vT).sum(-1).astype(x.dtype)
+    Mm = np.zeros((n, M, M), x.dtype)
+    m = np.zeros((n, M), x.dtype)
+
+    def close_step(w_, db_, u_, b_, first):
+        ub = w_ + 2 * db_[:, None] * u_
+        if first:
+            ub = np.where(u_ > 0, ub, 0)       # only u_1 can be clipped (v0 may be anything)
+        rb = dt(1) / (b_ + eps)
+        return (ub * rb[:, None]).astype(x.dtype), (-(ub * u_).sum(-1) * rb).astype(x.dtype)
+
+    ab, bbar = close_step(w, -e * rdT, uT, bs[-1], T == 1)
+    for t in range(T - 2, T - K - 1, -1):
+        u, rd = us[t], rds[t]
+        brd = 2 * bbar * rd
+        kappa = brd * eps
+        z = (ab + brd[:, None] * u).astype(x.dtype)
+        Mm += rd[:, None, None] * (u[:, :, None] * z[:, None, :] + ab[:, :, None] * u[:, None, :])
+        m += rd[:, None] * (kappa[:, None] * u + eps * ab)
+        Gz = np.einsum("nij,nj->ni", Gm, z)
+        Gu = np.einsum("nij,nj->ni", Gm, u)
+        w = (rd[:, None] * (Gz + kappa[:, None] * r)).astype(x.dtype)
+        qv = rd * ((z * Gu).sum(-1) + eps * (z * r).sum(-1) + kappa * (u * r).sum(-1) + dt(N) * kappa * eps)
+        ab, bbar = close_step(w, (-qv * rd).astype(x.dtype), u, bs[t], t == 0)
+    dx = rdT[:, None, None] * uT[:, :, None] * gv[:, None, :]
+    if K >= T:
+        dx = dx + ab[:, :, None] * v0[None, None, :]
+    else:   # truncated unroll: v_{L-1} = rd (X^T u_{L-1} + eps) is a constant, a_L = X v_{L-1} still reads X
+        u, rd = us[T - K - 1], rds[T - K - 1]
+        Mm += rd[:, None, None] * ab[:, :, None] * u[:, None, :]
+        m += rd[:, None] * eps * ab
+    dx = dx + np.einsum("nij,njk->nik", Mm, x) + m[:, :, None]
+    return y, dx.astype(x.dtype)

@@ -120,3 +120,27 @@ def test_c_oracle_matches_golden(golden, name):
                                  num_iters=nm["num_iters"], num_grad_steps=nm.get("num_grad_steps"))
     assert_close(y, g[f"{name}/y"], what="y")
     assert_close(gx, g[f"{name}/gx"], what="gx")
+
+
+@pytest.mark.parametrize("name", ["hals_r1_8x512", "hals_r1_relu_randn", "hals_r1_zero_window", "hals_r1_8x64_T3_k1",
+                                  "hals_r1_32x64"])
+def test_gram_form_is_well_conditioned(golden, name):
+    """The Gram-matrix form the CUDA kernels evaluate for act = ReLU (csrc/fz_swnmf_gram.cuh) equals the
+    reference's unrolled solver: exactly in fp64, and in fp32 no further from the fp64 reference than
+    the reference's own fp32 run is (plus a small slack)."""
+    c = cases.NMF_CASES[name]
+    g = golden["nmf"]
+    M, N = c["shape"][-2:]
+    x = cases.make_array(name, c["shape"], c["dist"]).reshape(-1, M, N)
+    gy = cases.make_array(name, c["shape"], "randn", tag="gy").reshape(-1, M, N)
+    v0 = g[f"{name}/v0"][:, 0]
+    kw = dict(num_iters=c["num_iters"], num_grad_steps=c["num_grad_steps"])
+    y64, gx64 = g[f"{name}/y64"].reshape(x.shape), g[f"{name}/gx64"].reshape(x.shape)
+    yr, gr = g[f"{name}/y"].reshape(x.shape), g[f"{name}/gx"].reshape(x.shape)
+    y, dx = O.hals_r1_gram(x.astype(np.float64), v0.astype(np.float64), gy.astype(np.float64), **kw)
+    assert tol_ratio(y, y64) < 1e-6 and tol_ratio(dx, gx64) < 1e-6
+    y, dx = O.hals_r1_gram(x, v0, gy, **kw)
+    assert_close(y, yr, what="y")
+    assert_close(dx, gr, what="gx")
+    assert tol_ratio(y, y64) <= tol_ratio(yr, y64) + 0.02
+    assert tol_ratio(dx, gx64) <= tol_ratio(gr, gx64) + 0.05
