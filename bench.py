@@ -282,7 +282,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "volumes_per_gpu": 1, "parallelism": f"batch-sharded x{world}, no data-path collective",
                        "l2": "inputs (3 x 256 MiB per step) are larger than the 126 MB L2; no explicit flush",
-                       "path": "fast (TMA/register kernels)" if fast_path == 1 else "generic",
+                       "path": {0: "generic", 1: "window-at-a-time TMA/register kernels", 2: "three-pass octant kernels"}[fast_path],
                        "fwd_us": fwd_us, "bwd_us": bwd_us,
                        "fused_op_hbm_frac": (fwd_bytes + bwd_bytes) / ((fwd_us + bwd_us) * 1e-6) / 1e9 / peak},
             "roofline": {"bound": "hbm", "kernel": "swnmf_bwd_fast", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -108,7 +108,12 @@ size_t fz_swnmf_saved_bytes(const fz_geom* g, const fz_solver* s) {
 size_t fz_swnmf_workspace_bytes(const fz_geom* g, const fz_solver* s) {
     DevGeom G;
     if (make_dev_geom(g, &G) || !s) return 0;
-    return fast_workspace_bytes(G, *s);
+    size_t a = fast_workspace_bytes(G, *s);
+    if (phase_supported(G, *s, 1)) {
+        const size_t b = phase_workspace_bytes(G, *s);
+        if (b > a) a = b;
+    }
+    return a;
 }
 
 int fz_swnmf_forward(const float* x, const float* u0, const float* v0, float* y, void* saved,
@@ -120,6 +125,10 @@ int fz_swnmf_forward(const float* x, const float* u0, const float* v0, float* y,
     int K;
     if (int e = check_solver(s, G.d, G.P, &K)) return e;
     if (!x || !u0 || !v0 || !y) return fail(FZ_ERR_INVALID, "null buffer");
+    if ((g_forced_path == -1 || g_forced_path == 2) && phase_supported(G, *s, relu_input)) {
+        tls().path = 2;
+        return phase_forward(x, v0, y, saved, workspace, G, *s, (cudaStream_t)stream);
+    }
     if (g_forced_path != 0 && fast_supported(G, *s)) {
         tls().path = 1;
         return fast_forward(x, u0, v0, y, saved, workspace, G, *s, relu_input, (cudaStream_t)stream);
@@ -142,6 +151,10 @@ int fz_swnmf_backward(const float* x, const float* gy, const float* u0, const fl
     int K;
     if (int e = check_solver(s, G.d, G.P, &K)) return e;
     if (!x || !gy || !u0 || !v0 || !gx) return fail(FZ_ERR_INVALID, "null buffer");
+    if ((g_forced_path == -1 || g_forced_path == 2) && phase_supported(G, *s, relu_input)) {
+        tls().path = 2;
+        return phase_backward(x, gy, v0, saved, gx, workspace, G, *s, K, (cudaStream_t)stream);
+    }
     if (g_forced_path != 0 && fast_supported(G, *s)) {
         tls().path = 1;
         return fast_backward(x, gy, u0, v0, saved, gx, workspace, G, *s, K, relu_input,

@@ -41,4 +41,12 @@ int fast_backward(const float* x, const float* gy, const float* u0, const float*
                   const void* saved, float* gx, void* workspace, const DevGeom& G,
                   const fz_solver& s, int K, int relu, cudaStream_t st);
 
+// fz_swnmf_phase.cu: three-pass "octant" formulation for [unshifted, shifted by patch/2], act = ReLU
+bool phase_supported(const DevGeom& G, const fz_solver& s, int relu);
+size_t phase_workspace_bytes(const DevGeom& G, const fz_solver& s);
+int phase_forward(const float* x, const float* v0, float* y, void* saved, void* workspace,
+                  const DevGeom& G, const fz_solver& s, cudaStream_t st);
+int phase_backward(const float* x, const float* gy, const float* v0, const void* saved, float* gx,
+                   void* workspace, const DevGeom& G, const fz_solver& s, int K, cudaStream_t st);
+
 }  // namespace fz

@@ -118,11 +118,13 @@ int fz_swnmf_backward(const float* x, const float* gy, const float* u0, const fl
                       const fz_solver* s, int32_t relu_input, void* stream);
 
 /* Which implementation the last fz_swnmf_* call on this thread used: 0 = generic shared-memory
- * kernels, 1 = the specialised TMA/register kernel.  For tests and the benchmark's bookkeeping. */
+ * kernels, 1 = the window-at-a-time TMA/register kernels (8x512 windows, rank-1 HALS, any shifts),
+ * 2 = the three-pass octant kernels (the same with shifts [0, patch/2] and ReLU: the default
+ * Swin-Factorizer block).  For tests and the benchmark's bookkeeping. */
 int fz_last_path(void);
 /* Number of kernel launches issued by the last fz_* call on this thread. */
 int fz_last_launches(void);
-/* Force a path for fz_swnmf_*: -1 = automatic, 0 = generic only. */
+/* Force a path for fz_swnmf_*: -1 = automatic, 0 = generic only, 1 = never the octant kernels. */
 void fz_set_path(int path);
 
 #ifdef __cplusplus

@@ -122,7 +122,7 @@ def _fused_module(ft, c, g, name, dev):
     return reshape, nmf.to(dev)
 
 
-@pytest.mark.parametrize("path", ["auto", "generic"])
+@pytest.mark.parametrize("path", ["auto", "window", "generic"])
 @pytest.mark.parametrize("name", list(cases.FUSED_CASES))
 def test_fused_core_matches_reference(ft, dev, golden, name, path):
     from factorizer_b200 import _lib, _ops
@@ -131,7 +131,7 @@ def test_fused_core_matches_reference(ft, dev, golden, name, path):
     reshape, nmf = _fused_module(ft, c, g, name, dev)
     x = torch.from_numpy(cases.make_array(name, c["x_shape"], c["dist"])).to(dev).requires_grad_(True)
     gy = torch.from_numpy(cases.make_array(name, c["x_shape"], "randn", tag="gy")).to(dev)
-    _lib.lib().fz_set_path(-1 if path == "auto" else 0)
+    _lib.lib().fz_set_path({"auto": -1, "window": 1, "generic": 0}[path])   # auto: octant kernels where they apply
     try:
         y = _ops.SWNMF.apply(x, nmf.init.u0, nmf.init.v0, reshape._geom, nmf.solver_spec(), c["relu"])
         (gx,) = torch.autograd.grad((y * gy).sum(), x)
