@@ -80,7 +80,9 @@ struct alignas(64) PhaseParams {
     float* oct;           // pass 1 -> pass 2 records
     float* fac;           // forward pass 2 -> pass 3
     float* mb;            // backward pass 2 -> pass 3
+    float* b1;            // v_0 . v_0, written by forward pass 1
     int n0, n1, n2, G0, G1, G2, heads, B, C;
+    int pow2, s2, s1, s0, sh;   // all of G2, G1, G0, heads are powers of two: their log2 (tile_coord without divisions)
     int tiles;            // B * heads * G0 * G1 * G2 = windows per set
     long long vox;
     int T, K, rec_floats, rec_head;
@@ -91,6 +93,13 @@ struct alignas(64) PhaseParams {
 struct TileCoord { int b, h, t0, t1, t2; };
 __device__ __forceinline__ TileCoord tile_coord(const PhaseParams& P, int tid) {
     TileCoord c;
+    if (P.pow2) {
+        c.t2 = tid & (P.G2 - 1); tid >>= P.s2;
+        c.t1 = tid & (P.G1 - 1); tid >>= P.s1;
+        c.t0 = tid & (P.G0 - 1); tid >>= P.s0;
+        c.h = tid & (P.heads - 1); c.b = tid >> P.sh;
+        return c;
+    }
     c.t2 = tid % P.G2; tid /= P.G2;
     c.t1 = tid % P.G1; tid /= P.G1;
     c.t0 = tid % P.G0; tid /= P.G0;
@@ -193,6 +202,13 @@ __global__ void __launch_bounds__(kW1 * 32, 1) phase_fwd_gram(const __grid_const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (blockIdx.x == 0 && warp == 0) {
+        // b_1 = v_0 . v_0 is the same for every window: computed once, here
+        float sq = 0.f;
+        for (int j = lane; j < 512; j += 32) sq = fmaf(v0s[j], v0s[j], sq);
+        sq = warp_sum_f(sq);
+        if (lane == 0) *P.b1 = sq;
+    }
     Stream S; S.gw = blockIdx.x * kW1 + warp; S.nw = gridDim.x * kW1; S.lane = lane;
 
     // where this lane's 15 reduced values go inside its octant's record
@@ -292,45 +308,60 @@ __device__ __forceinline__ int tri_index(int i, int j) {   // position of Gam(i,
 }
 
 __global__ void __launch_bounds__(kSolveThreads) phase_fwd_solve(const __grid_constant__ PhaseParams P) {
-    __shared__ float red[kSolveThreads / 32];
-    // b_1 = v_0 . v_0
-    float s = 0.f;
-    for (int j = threadIdx.x; j < 512; j += blockDim.x) { const float v = P.v0[j]; s = fmaf(v, v, s); }
-    s = warp_sum_f(s);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-    __syncthreads();
-    float b1 = 0.f;
-#pragma unroll
-    for (int q = 0; q < kSolveThreads / 32; ++q) b1 += red[q];
-
-    const int lane = threadIdx.x & 31, row = lane & 7;
+    __shared__ __align__(16) float stage[kSolveThreads / 8][8][kOctFloats];   // 16 windows x 8 octant records
+    __shared__ __align__(16) float sums[kSolveThreads / 8][64];               // their sums: Gam (36) | r (8) | a1 set 0 | a1 set 1
+    const int lane = threadIdx.x & 31, row = lane & 7, grp = threadIdx.x >> 3;
     const long long gwin = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    if (gwin >= 2LL * P.tiles) return;       // whole 8-lane groups leave together
+    if (gwin >= 2LL * P.tiles) return;       // whole 8-lane groups leave together; nothing below crosses groups
     const unsigned gmask = 0xffu << (lane & 24);
     const int set = gwin >= P.tiles ? 1 : 0;
-    const int local = (int)(gwin - (long long)set * P.tiles);
-    const TileCoord c = tile_coord(P, local);
     const float eps = P.eps;
+    {
+        // the 8 lanes of a window fetch its 8 octant records together: each record is 15 consecutive
+        // float4, lane i takes float4 i and 8 + i; all 16 loads of a lane are independent
+        const int local = (int)(gwin - (long long)set * P.tiles);
+        const TileCoord c = tile_coord(P, local);
+        float4 va[8], vb[8];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            const int src = set ? source_tile_of(P, c, o) : local;
+            const float4* g4 = reinterpret_cast<const float4*>(P.oct + ((size_t)src * 8 + o) * kOctFloats);
+            va[o] = __ldcg(g4 + row);
+            vb[o] = row < 7 ? __ldcg(g4 + 8 + row) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            float4* s4 = reinterpret_cast<float4*>(&stage[grp][o][0]);
+            s4[row] = va[o];
+            if (row < 7) s4[8 + row] = vb[o];
+        }
+    }
+    const float b1 = __ldcg(P.b1);
+    __syncwarp(gmask);
+    // lane i adds floats 8i .. 8i+7 of the 8 records
+    {
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            const float4* s4 = reinterpret_cast<const float4*>(&stage[grp][o][0]);
+            const float4 p = s4[2 * row];
+            a0.x += p.x; a0.y += p.y; a0.z += p.z; a0.w += p.w;
+            if (row < 7) { const float4 q = s4[2 * row + 1]; a1.x += q.x; a1.y += q.y; a1.z += q.z; a1.w += q.w; }
+        }
+        float4* d4 = reinterpret_cast<float4*>(&sums[grp][0]);
+        d4[2 * row] = a0; d4[2 * row + 1] = a1;
+    }
+    __syncwarp(gmask);
 
     float grow[8], r[8], a[8];
+    {
+        const float* sm = &sums[grp][0];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { grow[j] = 0.f; r[j] = 0.f; a[j] = 0.f; }
-    int tri[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) tri[j] = row <= j ? tri_index(row, j) : tri_index(j, row);
-#pragma unroll 1
-    for (int o = 0; o < 8; ++o) {
-        const int src = set ? source_tile_of(P, c, o) : local;
-        const float* rec = P.oct + ((size_t)src * 8 + o) * kOctFloats;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) grow[j] += __ldcg(rec + tri[j]);
-        float t8[8];
-        ld8(rec + 36, t8);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] += t8[j];
-        ld8(rec + 44 + 8 * set, t8);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] += t8[j];
+        for (int j = 0; j < 8; ++j) {
+            grow[j] = sm[row <= j ? tri_index(row, j) : tri_index(j, row)];
+            r[j] = sm[36 + j];
+            a[j] = sm[44 + 8 * set + j];
+        }
     }
     float* rec = P.saved ? P.saved + gwin * P.rec_floats : nullptr;
     if (rec) {
@@ -591,41 +622,48 @@ __global__ void __launch_bounds__(kWB * 32, 1) phase_bwd_reduce(const __grid_con
 // backward pass 2: per window, 8 lanes: the 8-vector recursion t = T .. 1 (fz_swnmf_gram.cuh header)
 // =====================================================================================================
 __global__ void __launch_bounds__(kSolveThreads) phase_bwd_solve(const __grid_constant__ PhaseParams P) {
-    const int lane = threadIdx.x & 31, row = lane & 7;
+    __shared__ __align__(16) float stage[kSolveThreads / 8][8][kBwdOct];
+    const int lane = threadIdx.x & 31, row = lane & 7, grp = threadIdx.x >> 3;
     const long long gwin = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     if (gwin >= 2LL * P.tiles) return;
     const unsigned gmask = 0xffu << (lane & 24);
     const int set = gwin >= P.tiles ? 1 : 0;
-    const int local = (int)(gwin - (long long)set * P.tiles);
-    const TileCoord c = tile_coord(P, local);
     const float eps = P.eps;
     const int T = P.T;
-
+    const float* rec = P.saved + gwin * P.rec_floats;
+    float grow[8], r[8], u[8], unext[8], bcur, bnext = 0.f;
+    {
+        // lane i fetches octant i's (w, e) record; the saved record's pieces are fetched alongside
+        const int local = (int)(gwin - (long long)set * P.tiles);
+        const int src = set ? source_tile_of(P, tile_coord(P, local), row) : local;
+        const float4* g4 = reinterpret_cast<const float4*>(P.oct + (((size_t)src * 8 + row) * 2 + set) * kBwdOct);
+        const float4 p0 = __ldcg(g4), p1 = __ldcg(g4 + 1), p2 = __ldcg(g4 + 2);
+        ld8(rec + P.rec_head + 8 * row, grow);
+        ld8(rec + P.rec_head + 64, r);
+        ld8(rec + 8 * (T - 1), u);
+        bcur = __ldcg(rec + 8 * T + (T - 1));
+        if (T >= 2) { ld8(rec + 8 * (T - 2), unext); bnext = __ldcg(rec + 8 * T + (T - 2)); }
+        float4* s4 = reinterpret_cast<float4*>(&stage[grp][row][0]);
+        s4[0] = p0; s4[1] = p1; s4[2] = p2;
+    }
+    __syncwarp(gmask);
     float w[8], e = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) w[j] = 0.f;
-#pragma unroll 1
-    for (int o = 0; o < 8; ++o) {
-        const int src = set ? source_tile_of(P, c, o) : local;
-        const float* rec = P.oct + (((size_t)src * 8 + o) * 2 + set) * kBwdOct;
-        float t8[8];
-        ld8(rec, t8);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) w[j] += t8[j];
-        e += __ldcg(rec + 8);
+    for (int o = 0; o < 8; ++o) {
+        const float4* oc = reinterpret_cast<const float4*>(&stage[grp][o][0]);
+        const float4 a = oc[0], b = oc[1];
+        w[0] += a.x; w[1] += a.y; w[2] += a.z; w[3] += a.w; w[4] += b.x; w[5] += b.y; w[6] += b.z; w[7] += b.w;
+        e += stage[grp][o][8];
     }
-    const float* rec = P.saved + gwin * P.rec_floats;
-    float grow[8], r[8], u[8];
-    ld8(rec + P.rec_head + 8 * row, grow);
-    ld8(rec + P.rec_head + 64, r);
-    ld8(rec + 8 * (T - 1), u);
     const float rdT = rcp_nr(dot8(u, u) + eps);     // same instruction sequence as the forward's rd_T
     float mrow[8], mi = 0.f, ab[8], bbar;
 #pragma unroll
     for (int j = 0; j < 8; ++j) mrow[j] = 0.f;
     {
         const float db = -e * rdT;
-        const float rb = rcp_nr(__ldcg(rec + 8 * T + (T - 1)) + eps);
+        const float rb = rcp_nr(bcur + eps);
         float bacc = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -640,7 +678,10 @@ __global__ void __launch_bounds__(kSolveThreads) phase_bwd_solve(const __grid_co
 #pragma unroll
     for (int j = 0; j < 8; ++j) { uT[j] = u[j]; ruT[j] = u[j] * rdT; }
     for (int t = T - 2; t >= T - P.K; --t) {
-        ld8(rec + 8 * t, u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) u[j] = unext[j];
+        bcur = bnext;
+        if (t >= 1) { ld8(rec + 8 * (t - 1), unext); bnext = __ldcg(rec + 8 * T + (t - 1)); }   // one step ahead
         const float rd = rcp_nr(dot8(u, u) + eps);
         const float brd = 2.f * bbar * rd, kappa = brd * eps;
         float z[8];
@@ -661,7 +702,7 @@ __global__ void __launch_bounds__(kSolveThreads) phase_bwd_solve(const __grid_co
         }
         const float qv = rd * (dot8(z, gu) + eps * dot8(z, r) + kappa * dot8(u, r) + 512.f * kappa * eps);
         const float db = -qv * rd;
-        const float rb = rcp_nr(__ldcg(rec + 8 * T + t) + eps);
+        const float rb = rcp_nr(bcur + eps);
         float bacc = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -675,7 +716,9 @@ __global__ void __launch_bounds__(kSolveThreads) phase_bwd_solve(const __grid_co
     }
     if (P.K < T) {
         // truncated unroll: a_L = X v_{L-1} still reads X, v_{L-1} = rd (X^T u_{L-1} + eps 1) is a constant
-        ld8(rec + 8 * (T - P.K - 1), u);
+        // u_{L-1} is the iterate prefetched by the last step of the sweep (or by the prologue when K == 1)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) u[j] = unext[j];
         const float ar = pick8(ab, row) * rcp_nr(dot8(u, u) + eps);
 #pragma unroll
         for (int j = 0; j < 8; ++j) mrow[j] = fmaf(ar, u[j], mrow[j]);
@@ -846,13 +889,14 @@ int num_sms() {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 int rec_head_for(int T) { return ((9 * T + 3) / 4) * 4; }
 
-struct Layout { size_t oct, fac, mb, total; };
+struct Layout { size_t oct, b1, fac, mb, total; };
 Layout layout(const DevGeom& G) {
     const size_t tiles = (size_t)G.mats_per_shift;
     Layout L;
     L.oct = 0;
     const size_t oct_bytes = tiles * kTileRec * sizeof(float);     // forward records (the backward's are smaller)
-    L.fac = align_up(oct_bytes, 256);
+    L.b1 = align_up(oct_bytes, 256);
+    L.fac = L.b1 + 256;
     L.mb = L.fac + align_up(2 * tiles * kFacF * sizeof(float), 256);
     L.total = L.mb + align_up(2 * tiles * kMbF * sizeof(float), 256);
     return L;
@@ -864,11 +908,17 @@ void fill(PhaseParams& P, const DevGeom& G, const fz_solver& s, int K, void* wor
     P.G0 = G.g[0]; P.G1 = G.g[1]; P.G2 = G.g[2];
     P.heads = G.heads; P.B = G.B; P.C = G.C; P.vox = G.vox;
     P.tiles = (int)G.mats_per_shift;
+    {
+        auto lg = [](int v) { int q = 0; while ((1 << q) < v) ++q; return (1 << q) == v ? q : -1; };
+        P.s2 = lg(P.G2); P.s1 = lg(P.G1); P.s0 = lg(P.G0); P.sh = lg(P.heads);
+        P.pow2 = P.s2 >= 0 && P.s1 >= 0 && P.s0 >= 0 && P.sh >= 0;
+    }
     P.T = s.num_iters; P.K = K; P.rec_head = rec_head_for(s.num_iters); P.rec_floats = P.rec_head + 72;
     P.eps = s.eps;
     const Layout L = layout(G);
     char* ws = static_cast<char*>(workspace);
     P.oct = reinterpret_cast<float*>(ws + L.oct);
+    P.b1 = reinterpret_cast<float*>(ws + L.b1);
     P.fac = reinterpret_cast<float*>(ws + L.fac);
     P.mb = reinterpret_cast<float*>(ws + L.mb);
 }
