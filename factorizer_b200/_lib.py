@@ -46,6 +46,7 @@ _SIGNATURES = {
     "fz_last_path": (c_int, []),
     "fz_last_launches": (c_int, []),
     "fz_set_path": (None, [c_int]),
+    "fz_set_pass_mask": (None, [c_int]),
     "fz_swmat_forward": (c_int, [c_void_p, c_void_p, POINTER(FzGeom), c_void_p]),
     "fz_swmat_inverse": (c_int, [c_void_p, c_void_p, POINTER(FzGeom), c_void_p]),
     "fz_swmat_forward_adjoint": (c_int, [c_void_p, c_void_p, POINTER(FzGeom), c_void_p]),

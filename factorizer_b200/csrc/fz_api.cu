@@ -67,6 +67,7 @@ const char* fz_last_error(void) { return tls().msg; }
 int fz_last_path(void) { return tls().path; }
 int fz_last_launches(void) { return tls().launches; }
 void fz_set_path(int path) { g_forced_path = path; }
+void fz_set_pass_mask(int mask) { phase_set_pass_mask(mask); }
 
 int fz_nmf_forward(const float* x, const float* u0, const float* v0, float* u, float* v, float* y,
                    int64_t n, int32_t M, int32_t N, const fz_solver* s, void* stream) {

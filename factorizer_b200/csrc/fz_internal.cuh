@@ -43,6 +43,7 @@ int fast_backward(const float* x, const float* gy, const float* u0, const float*
 
 // fz_swnmf_phase.cu: three-pass "octant" formulation for [unshifted, shifted by patch/2], act = ReLU
 bool phase_supported(const DevGeom& G, const fz_solver& s, int relu);
+void phase_set_pass_mask(int mask);
 size_t phase_workspace_bytes(const DevGeom& G, const fz_solver& s);
 int phase_forward(const float* x, const float* v0, float* y, void* saved, void* workspace,
                   const DevGeom& G, const fz_solver& s, cudaStream_t st);

@@ -25,8 +25,6 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include <algorithm>
-
 #include "fz_internal.cuh"
 
 namespace fz {
@@ -38,8 +36,8 @@ constexpr int kTileRec = 8 * kOctFloats;   // 480 floats per tile
 constexpr int kFacF = 12;             // per window: u_T (8), rd_T, pad
 constexpr int kBwdOct = 12;           // per (octant, set): w (8), e, pad
 constexpr int kMbF = 100;             // per window: M (64) | m (8) | abar_1 (8) | rd_T u_T (8) | u_T (8) | pad (4); 400 B keeps 8 records in distinct banks
-constexpr int kW1 = 6;                // warps per CTA, pass 1 forward (2 x 16 KiB each)
-constexpr int kW3 = 6;                // pass 3 forward (2 x 16 KiB each)
+constexpr int kW1 = 7;                // warps per CTA, pass 1 forward (2 x 16 KiB each)
+constexpr int kW3 = 6;                // pass 3 forward (2 x 16 KiB each; 7 warps measured slower: 111 vs 97 us)
 constexpr int kWB = 3;                // passes 1 and 3 backward (2 x 32 KiB each)
 constexpr int kSolveThreads = 128;
 
@@ -84,7 +82,6 @@ struct alignas(64) PhaseParams {
     float* fac;           // forward pass 2 -> pass 3
     float* mb;            // backward pass 2 -> pass 3
     float* b1;            // v_0 . v_0, written by forward pass 1
-    int* cnt;             // fused kernels: per-row completion counters (zeroed before every launch)
     int n0, n1, n2, G0, G1, G2, heads, B, C;
     int pow2, s2, s1, s0, sh;   // all of G2, G1, G0, heads are powers of two: their log2 (tile_coord without divisions)
     int tiles;            // B * heads * G0 * G1 * G2 = windows per set
@@ -195,8 +192,10 @@ struct Stream {
 };
 
 // pass 1 of one tile: per-octant Gram partials (Gam, r, a_1 for both window sets) -> P.oct[tid]
-__device__ __forceinline__ void fwd_tile_gram(const PhaseParams& P, const float* tile, const float* v0s, float* scratch,
+// The tile buffer itself is the scratch area for the 480-float record once X sits in registers.
+__device__ __forceinline__ void fwd_tile_gram(const PhaseParams& P, float* tile, const float* v0s,
                                               const int (&dst)[15], int lane, int tid) {
+    float* scratch = tile;
         f2 x[8][8];
         {
             const float4* t4 = reinterpret_cast<const float4*>(tile);
@@ -256,6 +255,7 @@ __device__ __forceinline__ void fwd_tile_gram(const PhaseParams& P, const float*
             float4* o4 = reinterpret_cast<float4*>(P.oct + (size_t)tid * kTileRec);
             for (int q = lane; q < kTileRec / 4; q += 32) o4[q] = s4[q];
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer goes back to TMA
 }
 
 // =====================================================================================================
@@ -264,12 +264,10 @@ __device__ __forceinline__ void fwd_tile_gram(const PhaseParams& P, const float*
 __global__ void __launch_bounds__(kW1 * 32, 1) phase_fwd_gram(const __grid_constant__ PhaseParams P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(16) float v0s[512];
-    __shared__ __align__(16) float scratch_all[kW1][kTileRec];
     __shared__ uint64_t bars[kW1][2];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* buf = reinterpret_cast<float*>(smem_raw) + (size_t)warp * 2 * 4096;
-    float* scratch = scratch_all[warp];
     for (int j = threadIdx.x; j < 512; j += blockDim.x) v0s[j] = P.v0[j];
     if (lane == 0) {
         mbar_init(&bars[warp][0], 1);
@@ -313,7 +311,7 @@ __global__ void __launch_bounds__(kW1 * 32, 1) phase_fwd_gram(const __grid_const
         const int tid = S.tile(k), st = k & 1;
         mbar_wait(&bars[warp][st], parity[st]);
         parity[st] ^= 1;
-        fwd_tile_gram(P, buf + st * 4096, v0s, scratch, dst, lane, tid);
+        fwd_tile_gram(P, buf + st * 4096, v0s, dst, lane, tid);
     }
 }
 
@@ -325,53 +323,31 @@ __device__ __forceinline__ int tri_index(int i, int j) {   // position of Gam(i,
 }
 
 // pass 2 for one window (8 lanes, `gmask`): add its 8 octant records, run the T sweeps, write the saved
-// record and the factors pass 3 needs.  stage: 8 x 60 floats, sums: 64 floats of shared memory.
-constexpr unsigned kUnwritten = 0xffffffffu;   // fused kernels: records are pre-filled with this pattern (no arithmetic produces it)
-__device__ __forceinline__ bool unwritten(float v) { return __float_as_uint(v) == kUnwritten; }
-
-template <bool VALIDATE>
-__device__ __forceinline__ void fwd_solve_window(const PhaseParams& P, float* stage, float* sums, long long gwin, int set,
+// record and the factors pass 3 needs.  sums: 64 floats of shared memory.
+__device__ __forceinline__ void fwd_solve_window(const PhaseParams& P, float* sums, long long gwin, int set,
                                                  int lane, unsigned gmask, float b1) {
     const int row = lane & 7;
     const float eps = P.eps;
     {
-        // the 8 lanes of a window fetch its 8 octant records together: each record is 15 consecutive
-        // float4, lane i takes float4 i and 8 + i; all 16 loads of a lane are independent
+        // The 8 lanes of a window read its 8 octant records together (each record is 15 consecutive
+        // float4, lane i takes float4 2i and 2i+1) and add them up on the fly: all 16 loads of a lane
+        // are independent, and the sums (floats 8i .. 8i+7 in lane i) go to shared memory for the
+        // row / full-vector views below.
         const int local = (int)(gwin - (long long)set * P.tiles);
         const TileCoord c = tile_coord(P, local);
         float4 va[8], vb[8];
-        for (;;) {
-            bool stale = false;
-#pragma unroll
-            for (int o = 0; o < 8; ++o) {
-                const int src = set ? source_tile_of(P, c, o) : local;
-                const float4* g4 = reinterpret_cast<const float4*>(P.oct + ((size_t)src * 8 + o) * kOctFloats);
-                va[o] = __ldcg(g4 + row);
-                vb[o] = row < 7 ? __ldcg(g4 + 8 + row) : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (VALIDATE) stale = stale || unwritten(va[o].x) || unwritten(vb[o].x);
-            }
-            // every 16-byte piece is written by one store instruction: a piece is either still the
-            // fill pattern or complete
-            if (!VALIDATE || !__any_sync(gmask, stale)) break;
-            __nanosleep(256);
-        }
 #pragma unroll
         for (int o = 0; o < 8; ++o) {
-            float4* s4 = reinterpret_cast<float4*>(stage + o * kOctFloats);
-            s4[row] = va[o];
-            if (row < 7) s4[8 + row] = vb[o];
+            const int src = set ? source_tile_of(P, c, o) : local;
+            const float4* g4 = reinterpret_cast<const float4*>(P.oct + ((size_t)src * 8 + o) * kOctFloats);
+            va[o] = __ldcg(g4 + 2 * row);
+            vb[o] = row < 7 ? __ldcg(g4 + 2 * row + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-    }
-        __syncwarp(gmask);
-    // lane i adds floats 8i .. 8i+7 of the 8 records
-    {
-        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+        float4 a0 = va[0], a1 = vb[0];
 #pragma unroll
-        for (int o = 0; o < 8; ++o) {
-            const float4* s4 = reinterpret_cast<const float4*>(stage + o * kOctFloats);
-            const float4 p = s4[2 * row];
-            a0.x += p.x; a0.y += p.y; a0.z += p.z; a0.w += p.w;
-            if (row < 7) { const float4 q = s4[2 * row + 1]; a1.x += q.x; a1.y += q.y; a1.z += q.z; a1.w += q.w; }
+        for (int o = 1; o < 8; ++o) {
+            a0.x += va[o].x; a0.y += va[o].y; a0.z += va[o].z; a0.w += va[o].w;
+            a1.x += vb[o].x; a1.y += vb[o].y; a1.z += vb[o].z; a1.w += vb[o].w;
         }
         float4* d4 = reinterpret_cast<float4*>(sums);
         d4[2 * row] = a0; d4[2 * row + 1] = a1;
@@ -429,15 +405,14 @@ __device__ __forceinline__ void fwd_solve_window(const PhaseParams& P, float* st
 }
 
 __global__ void __launch_bounds__(kSolveThreads) phase_fwd_solve(const __grid_constant__ PhaseParams P) {
-    __shared__ __align__(16) float stage[kSolveThreads / 8][8][kOctFloats];   // 16 windows x 8 octant records
-    __shared__ __align__(16) float sums[kSolveThreads / 8][64];               // their sums: Gam (36) | r (8) | a1 set 0 | a1 set 1
+    __shared__ __align__(16) float sums[kSolveThreads / 8][64];               // per window: Gam (36) | r (8) | a1 set 0 | a1 set 1
     const int lane = threadIdx.x & 31, row = lane & 7, grp = threadIdx.x >> 3;
     const long long gidx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     if (gidx >= 2LL * P.t_count) return;     // whole 8-lane groups leave together; nothing below crosses groups
     const unsigned gmask = 0xffu << (lane & 24);
     const int set = gidx >= P.t_count ? 1 : 0;
     const long long gwin = (long long)set * P.tiles + P.t_begin + (gidx - (long long)set * P.t_count);
-    fwd_solve_window<false>(P, &stage[grp][0][0], &sums[grp][0], gwin, set, lane, gmask, __ldcg(P.b1));
+    fwd_solve_window(P, &sums[grp][0], gwin, set, lane, gmask, __ldcg(P.b1));
 }
 
 // =====================================================================================================
@@ -541,134 +516,6 @@ __global__ void __launch_bounds__(kW3 * 32, 1) phase_fwd_apply(const __grid_cons
     }
 }
 
-
-// =====================================================================================================
-// forward, the three passes in ONE persistent kernel.
-// Separate launches make pass 3 re-read X from HBM (the volume does not fit in L2).  Here the passes
-// are interleaved row of tiles by row of tiles inside each (sample, head) sub-volume: pass 2 of a row
-// of windows runs `lag` rows after the last pass-1 row it needs, pass 3 of a row of tiles `lag` rows
-// after the last pass-2 row it needs, so pass 3 finds its X tiles in L2 (live footprint: a few dozen
-// rows of tiles).  Work is assigned statically (item i -> warp i mod #warps, every warp walks its items
-// in order), dependencies are per-row completion counters; an item only ever waits for items that come
-// earlier in the sequence, so there is no deadlock as long as all warps are resident (1 CTA / SM).
-// =====================================================================================================
-constexpr int kMaxSeg = 2048;
-struct alignas(16) FusedPlan {
-    int nseg, seglen, periods, n_sv, NR, gpr;   // segments per period, items per segment (= G2, pass-2 segments are padded), ...
-    unsigned desc[kMaxSeg];                     // type << 30 | set << 29 | periods_back << 24 | row
-};
-struct Item { int type, set, sv, row, idx; };   // type: 0 pass 1 (tile), 1 pass 2 (4 windows), 2 pass 3 (tile), 3 nothing
-
-__device__ __forceinline__ Item decode_item(const FusedPlan& F, int item, int total) {
-    Item it;
-    it.type = 3; it.set = 0; it.sv = 0; it.row = 0; it.idx = 0;
-    if (item >= total) return it;
-    const int seg_global = item / F.seglen, idx = item - seg_global * F.seglen;
-    const int period = seg_global / F.nseg, seg = seg_global - period * F.nseg;
-    const unsigned d = F.desc[seg];
-    const int sv = period - (int)((d >> 24) & 31u);
-    const int type = (int)(d >> 30);
-    if (sv < 0 || sv >= F.n_sv || (type == 1 && idx >= F.gpr)) return it;
-    it.type = type; it.set = (int)((d >> 29) & 1u); it.sv = sv; it.row = (int)(d & 0xffffffu); it.idx = idx;
-    return it;
-}
-
-// Synchronisation: none.  Every record a later pass reads (octant records, window factors) lives in a
-// buffer that the host fills with 0xff bytes before the launch; a reader that still sees that pattern in
-// a 16-byte piece simply reloads.  This needs no release / acquire fences (measured: a MEMBAR after a
-// tile's worth of stores costs the warp ~1 us, 10-20 % of the kernel), only that a piece is written by
-// one store instruction and read by one load instruction.
-__device__ __forceinline__ Fac load_fac_valid(const float* fac, long long wid) {
-    Fac f;
-    const float4* p = reinterpret_cast<const float4*>(fac + wid * kFacF);
-    float4 a, b, c;
-    for (;;) {
-        a = __ldcg(p); b = __ldcg(p + 1); c = __ldcg(p + 2);
-        if (!(unwritten(a.x) || unwritten(b.x) || unwritten(c.x))) break;
-        __nanosleep(256);
-    }
-    f.u[0] = a.x; f.u[1] = a.y; f.u[2] = a.z; f.u[3] = a.w; f.u[4] = b.x; f.u[5] = b.y; f.u[6] = b.z; f.u[7] = b.w;
-    f.rd = c.x;
-    return f;
-}
-
-__global__ void __launch_bounds__(kW1 * 32, 1) phase_fwd_fused(const __grid_constant__ PhaseParams P, const __grid_constant__ FusedPlan F) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ __align__(16) float v0s[512];
-    __shared__ __align__(16) float scratch_all[kW1][kTileRec];
-    __shared__ uint64_t bars[kW1][2];
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* buf = reinterpret_cast<float*>(smem_raw) + (size_t)warp * 2 * 4096;
-    float* scratch = scratch_all[warp];
-    for (int j = threadIdx.x; j < 512; j += blockDim.x) v0s[j] = P.v0[j];
-    if (lane == 0) {
-        mbar_init(&bars[warp][0], 1);
-        mbar_init(&bars[warp][1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    float b1;
-    {
-        float sq = 0.f;
-        for (int j = lane; j < 512; j += 32) sq = fmaf(v0s[j], v0s[j], sq);
-        b1 = warp_sum_f(sq);
-    }
-    int dst[15];
-    {
-        int id[kOctFloats];
-#pragma unroll
-        for (int q = 0; q < kOctFloats; ++q) id[q] = q;
-        halve_idx<60, kOctFloats>(id, lane & 1);
-        halve_idx<30, kOctFloats>(id, lane & 2);
-#pragma unroll
-        for (int q = 0; q < 15; ++q) dst[q] = (lane >> 2) * kOctFloats + id[q];
-    }
-    const int gw = blockIdx.x * kW1 + warp, nw = gridDim.x * kW1;
-    const int total = F.periods * F.nseg * F.seglen;
-    const int per_sv = F.NR * P.G2;
-
-    auto tile_of = [&](const Item& it) { return it.sv * per_sv + it.row * P.G2 + it.idx; };
-    auto issue = [&](const Item& it, int k) {
-        if ((it.type == 0 || it.type == 2) && lane == 0) {
-            const TileCoord c = tile_coord(P, tile_of(it));
-            mbar_arrive_expect_tx(&bars[warp][k & 1], kTileBytes);
-            tma_load_tile(buf + (k & 1) * 4096, &P.tm_x, &bars[warp][k & 1], c.t2 * 8, c.t1 * 8, c.t0 * 8, c.h * 8, c.b);
-        }
-    };
-    Item cur = decode_item(F, gw, total);
-    issue(cur, 0);
-    uint32_t par0 = 0, par1 = 0;
-    for (int k = 0; gw + k * nw < total; ++k) {
-        const Item nxt = decode_item(F, gw + (k + 1) * nw, total);
-        __syncwarp();
-        issue(nxt, k + 1);
-        const int st = k & 1;
-        float* tile = buf + st * 4096;
-        if (cur.type == 0) {
-            const int tid = tile_of(cur);
-            if (st) { mbar_wait(&bars[warp][1], par1); par1 ^= 1; } else { mbar_wait(&bars[warp][0], par0); par0 ^= 1; }
-            fwd_tile_gram(P, tile, v0s, scratch, dst, lane, tid);
-        } else if (cur.type == 1) {
-            // pass 2: up to 4 windows of this row, 8 lanes each; the idle tile buffer is the staging area
-            const int wl = 4 * cur.idx + (lane >> 3);
-            if (wl < P.G2) {
-                const long long gwin = (long long)cur.set * P.tiles + (long long)cur.sv * per_sv + cur.row * P.G2 + wl;
-                float* stg = tile + (lane >> 3) * (8 * kOctFloats + 64);
-                fwd_solve_window<true>(P, stg, stg + 8 * kOctFloats, gwin, cur.set, lane, 0xffu << (lane & 24), b1);
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer goes back to TMA
-        } else if (cur.type == 2) {
-            const int tid = tile_of(cur);
-            const TileCoord tc = tile_coord(P, tid);
-            const Fac f0 = load_fac_valid(P.fac, tid);
-            const Fac f1 = load_fac_valid(P.fac, (long long)P.tiles + shifted_window_of(P, tc, lane >> 2));
-            if (st) { mbar_wait(&bars[warp][1], par1); par1 ^= 1; } else { mbar_wait(&bars[warp][0], par0); par0 ^= 1; }
-            fwd_tile_apply(P, tile, f0, f1, tc, lane);
-        }
-        cur = nxt;
-    }
-}
 
 // =====================================================================================================
 // backward pass 1: per octant and window set, lane-partials of  w = G v_T / 2 + X cbar_T  and  e = qbar_T . v_T
@@ -794,7 +641,7 @@ __global__ void __launch_bounds__(kWB * 32, 1) phase_bwd_reduce(const __grid_con
 // =====================================================================================================
 // backward pass 2: per window, 8 lanes: the 8-vector recursion t = T .. 1 (fz_swnmf_gram.cuh header)
 // =====================================================================================================
-__global__ void __launch_bounds__(kSolveThreads) phase_bwd_solve(const __grid_constant__ PhaseParams P) {
+__global__ void __launch_bounds__(kSolveThreads, 5) phase_bwd_solve(const __grid_constant__ PhaseParams P) {
     __shared__ __align__(16) float stage[kSolveThreads / 8][8][kBwdOct];
     const int lane = threadIdx.x & 31, row = lane & 7, grp = threadIdx.x >> 3;
     const long long gidx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
@@ -1063,7 +910,7 @@ int num_sms() {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 int rec_head_for(int T) { return ((9 * T + 3) / 4) * 4; }
 
-struct Layout { size_t oct, b1, fac, mb, cnt, cnt_bytes, total; };
+struct Layout { size_t oct, b1, fac, mb, total; };
 Layout layout(const DevGeom& G) {
     const size_t tiles = (size_t)G.mats_per_shift;
     Layout L;
@@ -1072,9 +919,7 @@ Layout layout(const DevGeom& G) {
     L.b1 = align_up(oct_bytes, 256);
     L.fac = L.b1 + 256;
     L.mb = L.fac + align_up(2 * tiles * kFacF * sizeof(float), 256);
-    L.cnt = L.mb + align_up(2 * tiles * kMbF * sizeof(float), 256);
-    L.cnt_bytes = align_up((size_t)3 * G.B * G.heads * G.g[0] * G.g[1] * sizeof(int), 256);
-    L.total = L.cnt + L.cnt_bytes;
+    L.total = L.mb + align_up(2 * tiles * kMbF * sizeof(float), 256);
     return L;
 }
 
@@ -1097,70 +942,19 @@ void fill(PhaseParams& P, const DevGeom& G, const fz_solver& s, int K, void* wor
     P.b1 = reinterpret_cast<float*>(ws + L.b1);
     P.fac = reinterpret_cast<float*>(ws + L.fac);
     P.mb = reinterpret_cast<float*>(ws + L.mb);
-    P.cnt = reinterpret_cast<int*>(ws + L.cnt);
 }
 
-// How many (sample, head) sub-volumes one chunk of launches covers: as many as keep the volumes pass 3
-// re-reads (`vols` of them: X forward, X and dY backward) within about half of the 126 MB L2.
+// How many (sample, head) sub-volumes one chunk of launches covers.  Sub-volumes are independent, so the
+// three passes could run chunk by chunk to keep pass 3's re-reads in L2; measured on B200 the shorter
+// launches lose more (tails, ramps, launch gaps: 232 / 329 us per-head vs 186 / 259 us whole-volume at
+// config 2) than the L2 hits win, so the default is one chunk.  FZ_PHASE_SVS=n overrides (experiments).
 int svs_per_chunk(const DevGeom& G, int vols) {
+    (void)vols;
     const int svs = G.B * G.heads;
-    if (const char* env = getenv("FZ_PHASE_SVS")) { const int v = atoi(env); return v < 1 ? svs : v; }
-    const double sv_bytes = 8.0 * (double)G.vox * 4.0 * vols;
-    int n = (int)(72e6 / sv_bytes);
-    if (n < 1) n = 1;
-    return n > svs ? svs : n;
+    if (const char* env = getenv("FZ_PHASE_SVS")) { const int v = atoi(env); if (v >= 1 && v < svs) return v; }
+    return svs;
 }
 
-
-// ---- schedule of the fused kernels ------------------------------------------------------------------------
-// One period = the NR rows of tiles of one (sample, head) sub-volume.  Slot of an item = the row of pass 1
-// it runs alongside; pass 2 / pass 3 rows run `lag` slots after the last row they need, items whose
-// slot falls beyond the period run in a later period (periods_back).
-static bool build_fused_plan(FusedPlan& F, const DevGeom& G, int total_warps) {
-    const int G0 = G.g[0], G1 = G.g[1], G2 = G.g[2], NR = G0 * G1;
-    if (4 * NR > kMaxSeg || NR >= (1 << 24)) return false;
-    const int gpr = (G2 + 3) / 4;
-    const int per_slot = 2 * G2 + 2 * gpr;      // real items per row of tiles
-    int lag = (2 * total_warps + per_slot - 1) / per_slot + 2;
-    if (const char* env = getenv("FZ_FUSED_LAG")) lag = atoi(env);
-    static thread_local int slotB1[kMaxSeg / 4], slotC[kMaxSeg / 4];
-    auto rowat = [&](int r0, int r1) { return ((r0 % G0 + G0) % G0) * G1 + ((r1 % G1 + G1) % G1); };
-    for (int r0 = 0; r0 < G0; ++r0)
-        for (int r1 = 0; r1 < G1; ++r1) {
-            int m = 0;
-            for (int a = 0; a < 2; ++a)
-                for (int b = 0; b < 2; ++b) { const int q = rowat(r0 - a, r1 - b); if (q > m) m = q; }
-            slotB1[r0 * G1 + r1] = m + lag;
-        }
-    for (int r0 = 0; r0 < G0; ++r0)
-        for (int r1 = 0; r1 < G1; ++r1) {
-            int m = r0 * G1 + r1 + lag;      // pass 2 of the unshifted window of the same row
-            for (int a = 0; a < 2; ++a)
-                for (int b = 0; b < 2; ++b) { const int q = slotB1[rowat(r0 + a, r1 + b)]; if (q > m) m = q; }
-            slotC[r0 * G1 + r1] = m + lag;
-        }
-    struct Ent { long long key; unsigned desc; };
-    static thread_local Ent ent[kMaxSeg];
-    int n = 0, max_back = 0;
-    auto add = [&](int slot, int type, int set, int row) {
-        const int back = slot / NR, pos = slot % NR;
-        if (back > max_back) max_back = back;
-        ent[n].key = ((((long long)pos * 4 + (3 - type)) * 2 + set) * 64) + back;   // later passes first within a slot
-        ent[n].desc = ((unsigned)type << 30) | ((unsigned)set << 29) | ((unsigned)back << 24) | (unsigned)row;
-        ++n;
-    };
-    for (int row = 0; row < NR; ++row) {
-        add(row, 0, 0, row);
-        add(row + lag, 1, 0, row);
-        add(slotB1[row], 1, 1, row);
-        add(slotC[row], 2, 0, row);
-    }
-    if (max_back >= 32) return false;
-    std::sort(ent, ent + n, [](const Ent& a, const Ent& b) { return a.key < b.key; });
-    for (int i = 0; i < n; ++i) F.desc[i] = ent[i].desc;
-    F.nseg = n; F.seglen = G2; F.n_sv = G.B * G.heads; F.periods = F.n_sv + max_back; F.NR = NR; F.gpr = gpr;
-    return (long long)F.periods * F.nseg * F.seglen < (1LL << 30);
-}
 
 int grid_for(int tiles, int warps) {
     int ctas = (tiles + warps - 1) / warps;
@@ -1168,6 +962,9 @@ int grid_for(int tiles, int warps) {
 }
 
 }  // namespace
+
+static volatile int g_pass_mask = 7;
+void phase_set_pass_mask(int mask) { g_pass_mask = mask & 7; }
 
 bool phase_supported(const DevGeom& G, const fz_solver& s, int relu) {
     if (!relu || s.kind != FZ_SOLVER_HALS || s.rank != 1) return false;
@@ -1202,25 +999,6 @@ int phase_forward(const float* x, const float* v0, float* y, void* saved, void* 
         FZ_CUDA_CHECK(cudaFuncSetAttribute(phase_fwd_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, kW3 * 2 * kTileBytes));
         attr = true;
     }
-    {
-        const char* env = getenv("FZ_PHASE_FUSED");
-        static thread_local FusedPlan F;
-        const int grid = num_sms();
-        if (env && atoi(env) && build_fused_plan(F, G, grid * kW1)) {
-            static bool fattr = false;
-            if (!fattr) {
-                FZ_CUDA_CHECK(cudaFuncSetAttribute(phase_fwd_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, kW1 * 2 * kTileBytes));
-                fattr = true;
-            }
-            // octant records and window factors double as their own "written" flags
-            FZ_CUDA_CHECK(cudaMemsetAsync(P.oct, 0xff, (size_t)P.tiles * kTileRec * sizeof(float), st));
-            FZ_CUDA_CHECK(cudaMemsetAsync(P.fac, 0xff, (size_t)2 * P.tiles * kFacF * sizeof(float), st));
-            P.t_begin = 0; P.t_count = P.tiles; P.reverse = 0;
-            phase_fwd_fused<<<grid, kW1 * 32, kW1 * 2 * kTileBytes, st>>>(P, F);
-            FZ_LAUNCH_CHECK();
-            return FZ_OK;
-        }
-    }
     // (sample, head) sub-volumes are independent problems: pass 1-3 can run chunk by chunk, so that
     // pass 3 finds what pass 1 read still in L2
     const int per_sv = G.G, svs = G.B * G.heads, svc = svs_per_chunk(G, 1);
@@ -1228,13 +1006,20 @@ int phase_forward(const float* x, const float* v0, float* y, void* saved, void* 
         P.t_begin = sv * per_sv;
         P.t_count = (sv + svc <= svs ? svc : svs - sv) * per_sv;
         P.reverse = 1;
-        phase_fwd_gram<<<grid_for(P.t_count, kW1), kW1 * 32, kW1 * 2 * kTileBytes, st>>>(P);
-        FZ_LAUNCH_CHECK();
+        const int mask = g_pass_mask;
+        if (mask & 1) {
+            phase_fwd_gram<<<grid_for(P.t_count, kW1), kW1 * 32, kW1 * 2 * kTileBytes, st>>>(P);
+            FZ_LAUNCH_CHECK();
+        }
         const long long groups = 2LL * P.t_count;
-        phase_fwd_solve<<<(unsigned)((groups * 8 + kSolveThreads - 1) / kSolveThreads), kSolveThreads, 0, st>>>(P);
-        FZ_LAUNCH_CHECK();
-        phase_fwd_apply<<<grid_for(P.t_count, kW3), kW3 * 32, kW3 * 2 * kTileBytes, st>>>(P);
-        FZ_LAUNCH_CHECK();
+        if (mask & 2) {
+            phase_fwd_solve<<<(unsigned)((groups * 8 + kSolveThreads - 1) / kSolveThreads), kSolveThreads, 0, st>>>(P);
+            FZ_LAUNCH_CHECK();
+        }
+        if (mask & 4) {
+            phase_fwd_apply<<<grid_for(P.t_count, kW3), kW3 * 32, kW3 * 2 * kTileBytes, st>>>(P);
+            FZ_LAUNCH_CHECK();
+        }
     }
     return FZ_OK;
 }
@@ -1261,13 +1046,20 @@ int phase_backward(const float* x, const float* gy, const float* v0, const void*
         P.t_begin = sv * per_sv;
         P.t_count = (sv + svc <= svs ? svc : svs - sv) * per_sv;
         P.reverse = 1;
-        phase_bwd_reduce<<<grid_for(P.t_count, kWB), kWB * 32, kWB * 4 * kTileBytes, st>>>(P);
-        FZ_LAUNCH_CHECK();
+        const int mask = g_pass_mask;
+        if (mask & 1) {
+            phase_bwd_reduce<<<grid_for(P.t_count, kWB), kWB * 32, kWB * 4 * kTileBytes, st>>>(P);
+            FZ_LAUNCH_CHECK();
+        }
         const long long groups = 2LL * P.t_count;
-        phase_bwd_solve<<<(unsigned)((groups * 8 + kSolveThreads - 1) / kSolveThreads), kSolveThreads, 0, st>>>(P);
-        FZ_LAUNCH_CHECK();
-        phase_bwd_apply<<<grid_for(P.t_count, kWB), kWB * 32, kWB * 4 * kTileBytes, st>>>(P);
-        FZ_LAUNCH_CHECK();
+        if (mask & 2) {
+            phase_bwd_solve<<<(unsigned)((groups * 8 + kSolveThreads - 1) / kSolveThreads), kSolveThreads, 0, st>>>(P);
+            FZ_LAUNCH_CHECK();
+        }
+        if (mask & 4) {
+            phase_bwd_apply<<<grid_for(P.t_count, kWB), kWB * 32, kWB * 4 * kTileBytes, st>>>(P);
+            FZ_LAUNCH_CHECK();
+        }
     }
     return FZ_OK;
 }

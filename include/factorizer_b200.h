@@ -127,6 +127,12 @@ int fz_last_launches(void);
 /* Force a path for fz_swnmf_*: -1 = automatic, 0 = generic only, 1 = never the octant kernels. */
 void fz_set_path(int path);
 
+/* Measurement hook for the octant kernels (path 2): run only the passes whose bit is set (bit 0 = pass 1,
+ * per-octant partial sums; bit 1 = pass 2, per-window recursion; bit 2 = pass 3, per-voxel output).
+ * With a mask other than 7 the RESULTS ARE NOT VALID; bench.py uses it to time one kernel of a call with
+ * CUDA events after a complete call has filled the intermediate buffers.  Default 7. */
+void fz_set_pass_mask(int mask);
+
 #ifdef __cplusplus
 }
 #endif
