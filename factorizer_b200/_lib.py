@@ -55,6 +55,10 @@ _SIGNATURES = {
                                c_int32, c_int32, POINTER(FzSolver), c_void_p]),
     "fz_nmf_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int64, c_int32, c_int32, POINTER(FzSolver), c_void_p]),
+    "fz_layernorm_cf_supported": (c_int, [c_int32, c_int64]),
+    "fz_layernorm_cf_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_float, c_void_p]),
+    "fz_layernorm_cf_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
+                                         c_int64, c_float, c_void_p]),
     "fz_swnmf_saved_bytes": (c_size_t, [POINTER(FzGeom), POINTER(FzSolver)]),
     "fz_swnmf_workspace_bytes": (c_size_t, [POINTER(FzGeom), POINTER(FzSolver)]),
     "fz_swnmf_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

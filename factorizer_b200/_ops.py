@@ -264,3 +264,49 @@ class SWNMF(torch.autograd.Function):
             _call(lib.fz_swnmf_backward, L.ptr(x), L.ptr(gy), L.ptr(u0), L.ptr(v0), L.ptr(saved), L.ptr(gx),
                   L.ptr(ws), ctypes.byref(g), ctypes.byref(s), int(ctx.relu), L.stream_ptr(x.device))
         return gx, None, None, None, None, None
+
+
+# ---- channels-first LayerNorm (glue around the mixer) --------------------------------------------
+def layernorm_cf_supported(x: torch.Tensor) -> bool:
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() >= 3):
+        return False
+    vox = 1
+    for s in x.shape[2:]:
+        vox *= s
+    return bool(L.lib().fz_layernorm_cf_supported(x.shape[1], vox))
+
+
+class LayerNormCF(torch.autograd.Function):
+    """LayerNorm over dim 1 of a (B, C, *spatial) tensor without leaving the channels-first layout
+    (reference factorizer/layers/norm.py:25-34)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps: float):
+        lib = L.lib()
+        x = L.require_cuda_f32(x, "x")
+        B, C = x.shape[0], x.shape[1]
+        vox = x.numel() // max(B * C, 1)
+        y = torch.empty_like(x)
+        w = None if weight is None else L.require_cuda_f32(weight, "weight")
+        b = None if bias is None else L.require_cuda_f32(bias, "bias")
+        with torch.cuda.device(x.device):
+            _call(lib.fz_layernorm_cf_forward, L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), B, C, vox, float(eps),
+                  L.stream_ptr(x.device))
+        ctx.save_for_backward(x, w)
+        ctx.eps, ctx.has_bias = float(eps), bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = L.lib()
+        x, w = ctx.saved_tensors
+        gy = L.require_cuda_f32(gy, "grad")
+        B, C = x.shape[0], x.shape[1]
+        vox = x.numel() // max(B * C, 1)
+        gx = torch.empty_like(x)
+        gw = torch.empty(C, device=x.device, dtype=torch.float32) if w is not None else None
+        gb = torch.empty(C, device=x.device, dtype=torch.float32) if ctx.has_bias else None
+        with torch.cuda.device(x.device):
+            _call(lib.fz_layernorm_cf_backward, L.ptr(x), L.ptr(w), L.ptr(gy), L.ptr(gx), L.ptr(gw), L.ptr(gb), B, C, vox,
+                  ctx.eps, L.stream_ptr(x.device))
+        return gx, gw, gb, None

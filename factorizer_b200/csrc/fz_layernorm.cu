@@ -1,0 +1,212 @@
+// LayerNorm over the channel axis of a channels-first (B, C, voxels) fp32 tensor, forward and backward,
+// without the movedim + contiguous round trips the reference's wrapper makes
+// (factorizer/layers/norm.py:25-34 permutes to channels-last, calls nn.LayerNorm, permutes back: on a
+// (1,32,128^3) activation that is 6 full-tensor copies and two 3 ms LayerNorm kernels per block step).
+//
+// One thread owns two neighbouring voxels (float2 per channel, so a warp reads 256 contiguous bytes per
+// channel), keeps all C values in registers, and loops over voxel pairs grid-stride; the backward
+// accumulates d(gamma), d(beta) per thread across its voxels, reduces them per CTA in shared memory and
+// issues one atomicAdd per channel and CTA.  HBM-bound: forward reads x and writes y once, backward reads
+// x and dy once and writes dx once.
+#include "fz_common.cuh"
+
+namespace fz {
+namespace {
+
+constexpr int kLnThreads = 256;
+
+template <int C>
+__global__ void __launch_bounds__(kLnThreads) layernorm_cf_fwd(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, float* __restrict__ y,
+                                                               long long pairs_per_sample, long long total_pairs, float eps) {
+    __shared__ float gs[C], bs[C];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { gs[c] = gamma ? gamma[c] : 1.f; bs[c] = beta ? beta[c] : 0.f; }
+    __syncthreads();
+    const long long vox = 2 * pairs_per_sample;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total_pairs; p += (long long)gridDim.x * blockDim.x) {
+        const long long b = p / pairs_per_sample, v = p - b * pairs_per_sample;
+        const float2* xp = reinterpret_cast<const float2*>(x + b * C * vox) + v;
+        float2 val[C];
+        float2 sum = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < C; ++c) { val[c] = __ldcs(xp + (long long)c * pairs_per_sample); sum.x += val[c].x; sum.y += val[c].y; }
+        const float2 mean = make_float2(sum.x * (1.f / C), sum.y * (1.f / C));
+        float2 var = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float dx = val[c].x - mean.x, dy = val[c].y - mean.y;
+            var.x = fmaf(dx, dx, var.x); var.y = fmaf(dy, dy, var.y);
+        }
+        const float2 rstd = make_float2(rsqrtf(var.x * (1.f / C) + eps), rsqrtf(var.y * (1.f / C) + eps));
+        float2* yp = reinterpret_cast<float2*>(y + b * C * vox) + v;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float2 o;
+            o.x = fmaf((val[c].x - mean.x) * rstd.x, gs[c], bs[c]);
+            o.y = fmaf((val[c].y - mean.y) * rstd.y, gs[c], bs[c]);
+            yp[(long long)c * pairs_per_sample] = o;
+        }
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kLnThreads) layernorm_cf_bwd(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                               const float* __restrict__ dy, float* __restrict__ dx,
+                                                               float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                               long long pairs_per_sample, long long total_pairs, float eps) {
+    __shared__ float gs[C];
+    __shared__ float red[2][C][kLnThreads / 32];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) gs[c] = gamma ? gamma[c] : 1.f;
+    __syncthreads();
+    const long long vox = 2 * pairs_per_sample;
+    float dg[C], db[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { dg[c] = 0.f; db[c] = 0.f; }
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total_pairs; p += (long long)gridDim.x * blockDim.x) {
+        const long long b = p / pairs_per_sample, v = p - b * pairs_per_sample;
+        const float2* xp = reinterpret_cast<const float2*>(x + b * C * vox) + v;
+        const float2* gp = reinterpret_cast<const float2*>(dy + b * C * vox) + v;
+        float2 xh[C], g[C];
+        float2 sum = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            xh[c] = __ldcs(xp + (long long)c * pairs_per_sample);
+            g[c] = __ldcs(gp + (long long)c * pairs_per_sample);
+            sum.x += xh[c].x; sum.y += xh[c].y;
+        }
+        const float2 mean = make_float2(sum.x * (1.f / C), sum.y * (1.f / C));
+        float2 var = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            xh[c].x -= mean.x; xh[c].y -= mean.y;
+            var.x = fmaf(xh[c].x, xh[c].x, var.x); var.y = fmaf(xh[c].y, xh[c].y, var.y);
+        }
+        const float2 rstd = make_float2(rsqrtf(var.x * (1.f / C) + eps), rsqrtf(var.y * (1.f / C) + eps));
+        // xh = normalised input; parameter gradients; g <- dy * gamma
+        float2 m1 = make_float2(0.f, 0.f), m2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            xh[c].x *= rstd.x; xh[c].y *= rstd.y;
+            dg[c] = fmaf(g[c].x, xh[c].x, fmaf(g[c].y, xh[c].y, dg[c]));
+            db[c] += g[c].x + g[c].y;
+            g[c].x *= gs[c]; g[c].y *= gs[c];
+            m1.x += g[c].x; m1.y += g[c].y;
+            m2.x = fmaf(g[c].x, xh[c].x, m2.x); m2.y = fmaf(g[c].y, xh[c].y, m2.y);
+        }
+        m1.x *= (1.f / C); m1.y *= (1.f / C); m2.x *= (1.f / C); m2.y *= (1.f / C);
+        float2* op = reinterpret_cast<float2*>(dx + b * C * vox) + v;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float2 o;
+            o.x = rstd.x * (g[c].x - m1.x - xh[c].x * m2.x);
+            o.y = rstd.y * (g[c].y - m1.y - xh[c].y * m2.y);
+            op[(long long)c * pairs_per_sample] = o;
+        }
+    }
+    if (dgamma || dbeta) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float a = warp_sum(dg[c]), b = warp_sum(db[c]);
+            if (lane == 0) { red[0][c][warp] = a; red[1][c][warp] = b; }
+        }
+        __syncthreads();
+        for (int q = threadIdx.x; q < 2 * C; q += blockDim.x) {
+            const int which = q / C, c = q - which * C;
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < kLnThreads / 32; ++w) s += red[which][c][w];
+            float* dst = which ? dbeta : dgamma;
+            if (dst) atomicAdd(dst + c, s);
+        }
+    }
+}
+
+int sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+template <int C>
+int launch_fwd(const float* x, const float* gamma, const float* beta, float* y, long long batch, long long voxels, float eps, cudaStream_t st) {
+    const long long pps = voxels / 2, total = batch * pps;
+    long long blocks = (total + kLnThreads - 1) / kLnThreads;
+    const long long cap = 8LL * sm_count();
+    if (blocks > cap) blocks = cap;
+    layernorm_cf_fwd<C><<<(unsigned)blocks, kLnThreads, 0, st>>>(x, gamma, beta, y, pps, total, eps);
+    FZ_LAUNCH_CHECK();
+    return FZ_OK;
+}
+template <int C>
+int launch_bwd(const float* x, const float* gamma, const float* dy, float* dx, float* dgamma, float* dbeta, long long batch,
+               long long voxels, float eps, cudaStream_t st) {
+    const long long pps = voxels / 2, total = batch * pps;
+    long long blocks = (total + kLnThreads - 1) / kLnThreads;
+    const long long cap = 2LL * sm_count();
+    if (blocks > cap) blocks = cap;
+    if (dgamma) FZ_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, C * sizeof(float), st));
+    if (dbeta) FZ_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, C * sizeof(float), st));
+    layernorm_cf_bwd<C><<<(unsigned)blocks, kLnThreads, 0, st>>>(x, gamma, dy, dx, dgamma, dbeta, pps, total, eps);
+    FZ_LAUNCH_CHECK();
+    return FZ_OK;
+}
+
+int check_args(const void* a, const void* b, long long batch, int channels, long long voxels) {
+    if (!a || !b) return fail(FZ_ERR_INVALID, "null buffer");
+    if (batch < 0 || voxels < 0) return fail(FZ_ERR_INVALID, "negative size");
+    if (channels != 8 && channels != 16 && channels != 32)
+        return fail(FZ_ERR_UNSUPPORTED, "channels-first LayerNorm kernel handles 8, 16 or 32 channels, got %d", channels);
+    if (voxels % 2) return fail(FZ_ERR_UNSUPPORTED, "channels-first LayerNorm kernel needs an even number of voxels, got %lld", voxels);
+    if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 7) return fail(FZ_ERR_INVALID, "buffers must be 8-byte aligned");
+    return FZ_OK;
+}
+
+}  // namespace
+}  // namespace fz
+
+using namespace fz;
+
+extern "C" {
+
+int fz_layernorm_cf_supported(int32_t channels, int64_t voxels) {
+    return (channels == 8 || channels == 16 || channels == 32) && voxels % 2 == 0;
+}
+
+int fz_layernorm_cf_forward(const float* x, const float* gamma, const float* beta, float* y, int64_t batch,
+                            int32_t channels, int64_t voxels, float eps, void* stream) {
+    tls().launches = 0;
+    if (int e = check_args(x, y, batch, channels, voxels)) return e;
+    if (batch == 0 || voxels == 0) return FZ_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (channels) {
+        case 8: return launch_fwd<8>(x, gamma, beta, y, batch, voxels, eps, st);
+        case 16: return launch_fwd<16>(x, gamma, beta, y, batch, voxels, eps, st);
+        default: return launch_fwd<32>(x, gamma, beta, y, batch, voxels, eps, st);
+    }
+}
+
+int fz_layernorm_cf_backward(const float* x, const float* gamma, const float* dy, float* dx, float* dgamma,
+                             float* dbeta, int64_t batch, int32_t channels, int64_t voxels, float eps, void* stream) {
+    tls().launches = 0;
+    if (int e = check_args(x, dx, batch, channels, voxels)) return e;
+    if (!dy) return fail(FZ_ERR_INVALID, "null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (batch == 0 || voxels == 0) {
+        if (dgamma) FZ_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, channels * sizeof(float), st));
+        if (dbeta) FZ_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, channels * sizeof(float), st));
+        return FZ_OK;
+    }
+    switch (channels) {
+        case 8: return launch_bwd<8>(x, gamma, dy, dx, dgamma, dbeta, batch, voxels, eps, st);
+        case 16: return launch_bwd<16>(x, gamma, dy, dx, dgamma, dbeta, batch, voxels, eps, st);
+        default: return launch_bwd<32>(x, gamma, dy, dx, dgamma, dbeta, batch, voxels, eps, st);
+    }
+}
+
+}  // extern "C"

@@ -1,6 +1,6 @@
-"""Channels-first glue layers around the hot path.  These stay plain PyTorch (cuBLAS / cuDNN / ATen
-library kernels): SURVEY.md section 8(f) row 1 lists their fusion as the next step after the
-matricize+NMF core.  Module and parameter names match the reference so its checkpoints load:
+"""Channels-first glue layers around the hot path.  LayerNorm runs a
+hand-written channels-first kernel (csrc/fz_layernorm.cu) where it applies; Linear is a cuBLAS GEMM on the
+(C_out, C_in) x (C_in, voxels) view instead of a k=1 cuDNN convolution; GELU / residual adds are ATen.  Module and parameter names match the reference so its checkpoints load:
 ``Linear.linear`` (factorizer/layers/linear.py:43-58), ``LayerNorm.norm`` (layers/norm.py:25-34),
 ``MLP.block.{0,3}`` (layers/mlp.py:40-63), ``PositionalEmbedding.pos`` (layers/pos_embed.py:70-89).
 """
@@ -24,8 +24,15 @@ class Linear(nn.Module):
                                 dtype=dtype)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        # same arithmetic as the k=1 Conv1d of the reference (layers/linear.py:53-58), as one GEMM per
+        # sample: W (C_out, C_in) @ x (C_in, voxels); the Conv1d module only holds the parameters
         shape = x.shape
-        y = self.linear(self.flatten(x))
+        w = self.linear.weight.squeeze(-1)
+        xf = self.flatten(x)                                  # (B, C_in, voxels): a view, no copy
+        if self.linear.bias is not None:
+            y = torch.baddbmm(self.linear.bias[None, :, None], w.unsqueeze(0).expand(shape[0], -1, -1), xf)
+        else:
+            y = torch.bmm(w.unsqueeze(0).expand(shape[0], -1, -1), xf)
         return y.view(shape[0], -1, *shape[2:])
 
 
@@ -37,6 +44,9 @@ class LayerNorm(nn.Module):
         self.norm = nn.LayerNorm(dim, **kwargs)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        from . import _ops
+        if _ops.layernorm_cf_supported(x) and tuple(self.norm.normalized_shape) == (x.shape[1],):
+            return _ops.LayerNormCF.apply(x, self.norm.weight, self.norm.bias, self.norm.eps)
         y = self.norm(x.movedim(1, -1))
         return y.movedim(-1, 1)
 

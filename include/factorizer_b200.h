@@ -117,6 +117,19 @@ int fz_swnmf_backward(const float* x, const float* gy, const float* u0, const fl
                       const void* saved, float* gx, void* workspace, const fz_geom* g,
                       const fz_solver* s, int32_t relu_input, void* stream);
 
+/* ---- channels-first LayerNorm: the glue on either side of the mixer ---- */
+
+/* LayerNorm over the channel axis of a (batch, channels, voxels) tensor
+ * (factorizer/layers/norm.py:25-34: movedim -> nn.LayerNorm(channels) -> movedim; biased variance, eps
+ * inside the square root).  gamma / beta may be NULL (no affine).  Kernels exist for 8, 16 and 32
+ * channels and an even number of voxels; fz_layernorm_cf_supported() tells. */
+int fz_layernorm_cf_supported(int32_t channels, int64_t voxels);
+int fz_layernorm_cf_forward(const float* x, const float* gamma, const float* beta, float* y, int64_t batch,
+                            int32_t channels, int64_t voxels, float eps, void* stream);
+/* dx, and d(gamma), d(beta) (each `channels` floats, overwritten; either may be NULL) of <dy, y>. */
+int fz_layernorm_cf_backward(const float* x, const float* gamma, const float* dy, float* dx, float* dgamma,
+                             float* dbeta, int64_t batch, int32_t channels, int64_t voxels, float eps, void* stream);
+
 /* Which implementation the last fz_swnmf_* call on this thread used: 0 = generic shared-memory
  * kernels, 1 = the window-at-a-time TMA/register kernels (8x512 windows, rank-1 HALS, any shifts),
  * 2 = the three-pass octant kernels (the same with shifts [0, patch/2] and ReLU: the default

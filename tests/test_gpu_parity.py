@@ -240,3 +240,42 @@ def test_full_size_properties(ft, dev):
     x1 = a.expand(1, C, n, n, n).contiguous()
     y1 = _ops.SWNMF.apply(x1, nmf.init.u0, nmf.init.v0, sw._geom, nmf.solver_spec(), True)
     assert torch.allclose(y1, x1, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 8, 8, 8), (1, 16, 6, 10, 4), (3, 8, 50), (1, 32, 16, 16, 16)])
+def test_layernorm_channels_first(ft, dev, shape):
+    """ft.LayerNorm (hand-written channels-first kernel) against torch's own layer_norm on the permuted
+    tensor, which is literally what the reference does (factorizer/layers/norm.py:25-34): output, input
+    gradient and the affine parameters' gradients."""
+    from factorizer_b200 import _ops
+    torch.manual_seed(0)
+    C = shape[1]
+    ln = ft.LayerNorm(C).to(dev)
+    with torch.no_grad():
+        ln.norm.weight.copy_(torch.randn(C, device=dev))
+        ln.norm.bias.copy_(torch.randn(C, device=dev))
+    x = (3 * torch.randn(shape, device=dev) + 1).requires_grad_(True)
+    gy = torch.randn(shape, device=dev)
+    assert _ops.layernorm_cf_supported(x)
+    y = ln(x)
+    gx, gw, gb = torch.autograd.grad((y * gy).sum(), [x, ln.norm.weight, ln.norm.bias])
+    x64 = x.detach().double().requires_grad_(True)
+    w64 = ln.norm.weight.detach().double().requires_grad_(True)
+    b64 = ln.norm.bias.detach().double().requires_grad_(True)
+    y64 = torch.nn.functional.layer_norm(x64.movedim(1, -1), (C,), w64, b64, ln.norm.eps).movedim(-1, 1)
+    rx, rw, rb = torch.autograd.grad((y64 * gy.double()).sum(), [x64, w64, b64])
+    assert_close(_np(y), _np(y64), what="y")
+    assert_close(_np(gx), _np(rx), what="gx")
+    scale = max(1.0, float(rw.abs().max()), float(rb.abs().max()))
+    assert_close(_np(gw) / scale, _np(rw) / scale, what="gw")
+    assert_close(_np(gb) / scale, _np(rb) / scale, what="gb")
+
+
+def test_layernorm_fallback_shapes(ft, dev):
+    """Channel counts / voxel counts without a kernel take the reference's own permute + nn.LayerNorm route."""
+    from factorizer_b200 import _ops
+    x = torch.randn(2, 24, 5, 3, device=dev)
+    assert not _ops.layernorm_cf_supported(x)
+    ln = ft.LayerNorm(24).to(dev)
+    ref = torch.nn.functional.layer_norm(x.movedim(1, -1), (24,), ln.norm.weight, ln.norm.bias, ln.norm.eps).movedim(-1, 1)
+    assert torch.allclose(ln(x), ref)
