@@ -59,6 +59,11 @@ _SIGNATURES = {
     "fz_layernorm_cf_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_float, c_void_p]),
     "fz_layernorm_cf_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                                          c_int64, c_float, c_void_p]),
+    "fz_glue_supported": (c_int, [c_int32, c_int32, c_int64]),
+    "fz_ln_linear_forward": (c_int, [c_void_p] * 5 + [c_int64, c_int32, c_int64, c_float, c_void_p]),
+    "fz_mixer_mlp_forward": (c_int, [c_void_p] * 12 + [c_int64, c_int32, c_int32, c_int64, c_float, c_void_p]),
+    "fz_mlp_backward": (c_int, [c_void_p] * 14 + [c_int64, c_int32, c_int32, c_int64, c_float, c_void_p]),
+    "fz_linear_backward": (c_int, [c_void_p] * 11 + [c_int64, c_int32, c_int64, c_float, c_int32, c_void_p]),
     "fz_swnmf_saved_bytes": (c_size_t, [POINTER(FzGeom), POINTER(FzSolver)]),
     "fz_swnmf_workspace_bytes": (c_size_t, [POINTER(FzGeom), POINTER(FzSolver)]),
     "fz_swnmf_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -225,45 +225,124 @@ def _workspace(device, nbytes: int) -> Optional[torch.Tensor]:
     return ws
 
 
+def _swnmf_forward(x, u0, v0, geom: Geometry, spec: SolverSpec, relu: bool, need_grad: bool):
+    """One launch sequence of the fused core; returns (y, saved-for-backward buffer or None)."""
+    lib = L.lib()
+    g, s = geom.c_geom(x.shape[0]), spec.c_solver()
+    y = torch.empty_like(x)
+    saved = None
+    with torch.cuda.device(x.device):
+        nsaved = lib.fz_swnmf_saved_bytes(ctypes.byref(g), ctypes.byref(s)) if need_grad else 0
+        if nsaved:
+            saved = torch.empty(nsaved, device=x.device, dtype=torch.uint8)
+        ws = _workspace(x.device, lib.fz_swnmf_workspace_bytes(ctypes.byref(g), ctypes.byref(s)))
+        _call(lib.fz_swnmf_forward, L.ptr(x), L.ptr(u0), L.ptr(v0), L.ptr(y), L.ptr(saved), L.ptr(ws),
+              ctypes.byref(g), ctypes.byref(s), int(relu), L.stream_ptr(x.device))
+    return y, saved
+
+
+def _swnmf_backward(x, gy, u0, v0, saved, geom: Geometry, spec: SolverSpec, relu: bool):
+    lib = L.lib()
+    g, s = geom.c_geom(x.shape[0]), spec.c_solver()
+    gx = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        ws = _workspace(x.device, lib.fz_swnmf_workspace_bytes(ctypes.byref(g), ctypes.byref(s)))
+        _call(lib.fz_swnmf_backward, L.ptr(x), L.ptr(gy), L.ptr(u0), L.ptr(v0), L.ptr(saved), L.ptr(gx),
+              L.ptr(ws), ctypes.byref(g), ctypes.byref(s), int(relu), L.stream_ptr(x.device))
+    return gx
+
+
 class SWNMF(torch.autograd.Function):
     """reshape -> act -> factorize -> reshape.inverse_forward of FactMixer.forward
     (reference factorizer/factorizer.py:41-50): X is read once and Y written once."""
 
     @staticmethod
     def forward(ctx, x, u0, v0, geom: Geometry, spec: SolverSpec, relu: bool):
-        lib = L.lib()
         x = _check_vol(x, geom, "x")
         u0 = L.require_cuda_f32(u0, "u0")
         v0 = L.require_cuda_f32(v0, "v0")
-        B = x.shape[0]
-        g, s = geom.c_geom(B), spec.c_solver()
-        y = torch.empty_like(x)
-        need_grad = ctx.needs_input_grad[0]
-        saved = None
-        with torch.cuda.device(x.device):
-            nsaved = lib.fz_swnmf_saved_bytes(ctypes.byref(g), ctypes.byref(s)) if need_grad else 0
-            if nsaved:
-                saved = torch.empty(nsaved, device=x.device, dtype=torch.uint8)
-            ws = _workspace(x.device, lib.fz_swnmf_workspace_bytes(ctypes.byref(g), ctypes.byref(s)))
-            _call(lib.fz_swnmf_forward, L.ptr(x), L.ptr(u0), L.ptr(v0), L.ptr(y), L.ptr(saved), L.ptr(ws),
-                  ctypes.byref(g), ctypes.byref(s), int(relu), L.stream_ptr(x.device))
+        y, saved = _swnmf_forward(x, u0, v0, geom, spec, relu, ctx.needs_input_grad[0])
         ctx.save_for_backward(x, u0, v0, saved)
         ctx.geom, ctx.spec, ctx.relu = geom, spec, relu
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        lib = L.lib()
         x, u0, v0, saved = ctx.saved_tensors
-        geom, spec = ctx.geom, ctx.spec
-        gy = _check_vol(gy, geom, "grad")
-        g, s = geom.c_geom(x.shape[0]), spec.c_solver()
-        gx = torch.empty_like(x)
-        with torch.cuda.device(x.device):
-            ws = _workspace(x.device, lib.fz_swnmf_workspace_bytes(ctypes.byref(g), ctypes.byref(s)))
-            _call(lib.fz_swnmf_backward, L.ptr(x), L.ptr(gy), L.ptr(u0), L.ptr(v0), L.ptr(saved), L.ptr(gx),
-                  L.ptr(ws), ctypes.byref(g), ctypes.byref(s), int(ctx.relu), L.stream_ptr(x.device))
+        gy = _check_vol(gy, ctx.geom, "grad")
+        gx = _swnmf_backward(x, gy, u0, v0, saved, ctx.geom, ctx.spec, ctx.relu)
         return gx, None, None, None, None, None
+
+
+# ---- whole FactorizerBlock: fused glue kernels around the fused core --------------------------------
+def block_glue_supported(x: torch.Tensor, hidden: int) -> bool:
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() >= 3):
+        return False
+    vox = 1
+    for s in x.shape[2:]:
+        vox *= s
+    return bool(L.lib().fz_glue_supported(x.shape[1], int(hidden), vox))
+
+
+class FactorizerBlockFn(torch.autograd.Function):
+    """FactorizerBlock.forward (reference factorizer/factorizer.py:74-77 with FactMixer.forward :34-57) for
+    norm = LayerNorm, act = ReLU, no dropout: three launches forward (norm1+in_proj | fused matricize+NMF core |
+    out_proj+residual+norm2+MLP+residual), four backward.  Saves x, z (in_proj output), m (core output) and x1
+    (after the first residual); every intermediate of the MLP is recomputed in the backward kernel."""
+
+    @staticmethod
+    def forward(ctx, x, g1, b1n, w_in, w_out, b_out, g2, b2n, w1, bb1, w2, bb2, u0, v0, geom, spec, eps1, eps2):
+        lib = L.lib()
+        x = _check_vol(x, geom, "x")
+        params = [L.require_cuda_f32(t, "parameter") for t in (g1, b1n, w_in, w_out, b_out, g2, b2n, w1, bb1, w2, bb2)]
+        g1, b1n, w_in, w_out, b_out, g2, b2n, w1, bb1, w2, bb2 = params
+        u0 = L.require_cuda_f32(u0, "u0")
+        v0 = L.require_cuda_f32(v0, "v0")
+        B, C = x.shape[0], x.shape[1]
+        vox = x.numel() // max(B * C, 1)
+        hid = w1.shape[0]
+        need_grad = any(ctx.needs_input_grad[:12])
+        st = L.stream_ptr(x.device)
+        z = torch.empty_like(x)
+        out = torch.empty_like(x)
+        x1 = torch.empty_like(x) if need_grad else None
+        with torch.cuda.device(x.device):
+            _call(lib.fz_ln_linear_forward, L.ptr(x), L.ptr(g1), L.ptr(b1n), L.ptr(w_in), L.ptr(z), B, C, vox, float(eps1), st)
+            m, saved = _swnmf_forward(z, u0, v0, geom, spec, True, need_grad)
+            _call(lib.fz_mixer_mlp_forward, L.ptr(x), L.ptr(m), L.ptr(w_out), L.ptr(b_out), L.ptr(g2), L.ptr(b2n),
+                  L.ptr(w1), L.ptr(bb1), L.ptr(w2), L.ptr(bb2), L.ptr(x1), L.ptr(out), B, C, hid, vox, float(eps2), st)
+        if need_grad:
+            ctx.save_for_backward(x, z, m, x1, saved, g1, b1n, w_in, w_out, g2, b2n, w1, bb1, w2, u0, v0)
+            ctx.geom, ctx.spec, ctx.eps = geom, spec, (float(eps1), float(eps2))
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = L.lib()
+        x, z, m, x1, saved, g1, b1n, w_in, w_out, g2, b2n, w1, bb1, w2, u0, v0 = ctx.saved_tensors
+        gout = _check_vol(gout, ctx.geom, "grad")
+        B, C = x.shape[0], x.shape[1]
+        vox = x.numel() // max(B * C, 1)
+        hid = w1.shape[0]
+        eps1, eps2 = ctx.eps
+        st = L.stream_ptr(x.device)
+        new = lambda t: torch.empty_like(t)
+        dg2, db2n, dw1, dbb1, dw2, dbb2 = new(g2), new(b2n), new(w1), new(bb1), new(w2), torch.empty(C, device=x.device)
+        dw_out, db_out, dw_in, dg1, db1n = new(w_out), torch.empty(C, device=x.device), new(w_in), new(g1), new(b1n)
+        dx1 = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _call(lib.fz_mlp_backward, L.ptr(x1), L.ptr(gout), L.ptr(g2), L.ptr(b2n), L.ptr(w1), L.ptr(bb1), L.ptr(w2),
+                  L.ptr(dx1), L.ptr(dg2), L.ptr(db2n), L.ptr(dw1), L.ptr(dbb1), L.ptr(dw2), L.ptr(dbb2), B, C, hid, vox,
+                  eps2, st)
+            dm = torch.empty_like(x)
+            _call(lib.fz_linear_backward, L.ptr(dx1), L.ptr(m), None, None, L.ptr(w_out), None, L.ptr(dm),
+                  L.ptr(dw_out), L.ptr(db_out), None, None, B, C, vox, 0.0, 0, st)
+            dz = _swnmf_backward(z, dm, u0, v0, saved, ctx.geom, ctx.spec, True)
+            dx = dm                         # dm is dead once the core's backward has run: reuse its storage
+            _call(lib.fz_linear_backward, L.ptr(dz), L.ptr(x), L.ptr(g1), L.ptr(b1n), L.ptr(w_in), L.ptr(dx1), L.ptr(dx),
+                  L.ptr(dw_in), None, L.ptr(dg1), L.ptr(db1n), B, C, vox, eps1, 1, st)
+        return (dx, dg1, db1n, dw_in, dw_out, db_out, dg2, db2n, dw1, dbb1, dw2, dbb2,
+                None, None, None, None, None, None)
 
 
 # ---- channels-first LayerNorm (glue around the mixer) --------------------------------------------

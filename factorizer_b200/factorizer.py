@@ -5,7 +5,9 @@ reference's constructor signatures and parameter names (factorizer/factorizer.py
 ``reshape -> act -> factorize -> reshape.inverse_forward`` chain is
 (Matricize | SWMatricize) -> (ReLU | Identity) -> NMF('mu' | 'hals'), the four steps run as one CUDA
 kernel per direction (X read once, Y written once); any other combination runs the same steps through
-the standalone kernels.  Linear / LayerNorm / MLP stay PyTorch library calls.
+the standalone kernels.  A 32-channel FactorizerBlock with LayerNorm / ReLU / GELU and no active dropout runs
+entirely in hand-written kernels (csrc/fz_block_glue.cu around the fused core); other blocks run the glue
+layer by layer.
 """
 from __future__ import annotations
 
@@ -67,7 +69,36 @@ class FactorizerBlock(nn.Module):
         self.norm2 = partialize(norm)(channels)
         self.mlp = MLP(channels, ratio=mlp_ratio, dropout=dropout)
 
+    def _fused_args(self, x):
+        """Arguments of the fused block path, or None when this block / input is outside what it covers
+        (then the layers run one by one: fused core, hand-written LayerNorm, library GEMMs)."""
+        f, mlp = self.fact, self.mlp
+        if not (type(self.norm1) is LayerNorm and type(self.norm2) is LayerNorm and type(mlp) is MLP
+                and type(f) is FactMixer and f._fusable() and isinstance(f.act, nn.ReLU)
+                and getattr(f.reshape, "_geom", None) is not None):
+            return None
+        n1, n2 = self.norm1.norm, self.norm2.norm
+        fc1, act, dr1, fc2, dr2 = mlp.block
+        drops = (f.dropout, dr1, dr2)
+        if self.training and any(d.p > 0 for d in drops):
+            return None
+        if not (type(act) is nn.GELU and act.approximate == "none" and n1.elementwise_affine and n2.elementwise_affine
+                and n1.bias is not None and n2.bias is not None and fc1.linear.bias is not None
+                and fc2.linear.bias is not None and f.in_proj.linear.bias is None and f.out_proj.linear.bias is not None):
+            return None
+        C = x.shape[1] if x.dim() >= 3 else -1
+        if tuple(n1.normalized_shape) != (C,) or tuple(n2.normalized_shape) != (C,) \
+                or fc2.linear.out_channels != C or not _ops.block_glue_supported(x, fc1.linear.out_channels):
+            return None
+        sq = lambda lin: lin.linear.weight.squeeze(-1)
+        return (n1.weight, n1.bias, sq(f.in_proj), sq(f.out_proj), f.out_proj.linear.bias, n2.weight, n2.bias,
+                sq(fc1), fc1.linear.bias, sq(fc2), fc2.linear.bias, f.factorize.init.u0, f.factorize.init.v0,
+                f.reshape._geom, f.factorize.solver_spec(), n1.eps, n2.eps)
+
     def forward(self, x):
+        args = self._fused_args(x)
+        if args is not None:
+            return _ops.FactorizerBlockFn.apply(x, *args)
         x = x + self.fact(self.norm1(x))
         x = x + self.mlp(self.norm2(x))
         return x

@@ -130,6 +130,40 @@ int fz_layernorm_cf_forward(const float* x, const float* gamma, const float* bet
 int fz_layernorm_cf_backward(const float* x, const float* gamma, const float* dy, float* dx, float* dgamma,
                              float* dbeta, int64_t batch, int32_t channels, int64_t voxels, float eps, void* stream);
 
+/* ---- FactMixer / FactorizerBlock pointwise glue, 32-channel blocks --------
+ * All tensors are (batch, channels, voxels) fp32 = flattened NCDHW; weights are the reference's Conv1d(k=1)
+ * weights squeezed to (out, in) (factorizer/layers/linear.py:43-50).  Gradient outputs are OVERWRITTEN. */
+
+/* 1 if the four kernels below handle this block: 32 channels, an even number of voxels, MLP hidden width a
+ * multiple of 8 up to 64. */
+int fz_glue_supported(int32_t channels, int32_t hidden, int64_t voxels);
+
+/* z = W LN(x): norm1 + bias-free in_proj (factorizer/factorizer.py:26,38,75; layers/norm.py:29-34). */
+int fz_ln_linear_forward(const float* x, const float* gamma, const float* beta, const float* W, float* z, int64_t batch,
+                         int32_t channels, int64_t voxels, float eps, void* stream);
+
+/* x1 = x + W_out m + b_out ; out = x1 + W2 gelu(W1 LN(x1) + b1) + b2: out_proj + residual
+ * (factorizer.py:53,75) and norm2 + MLP + residual (factorizer.py:76, layers/mlp.py:54-60, exact-erf GELU).
+ * x1 may be NULL (inference); the backward needs it. */
+int fz_mixer_mlp_forward(const float* x, const float* m, const float* Wout, const float* bout, const float* gamma,
+                         const float* beta, const float* W1, const float* b1, const float* W2, const float* b2, float* x1,
+                         float* out, int64_t batch, int32_t channels, int32_t hidden, int64_t voxels, float eps, void* stream);
+
+/* Backward of out = x1 + MLP(LN(x1)): dx1 and the gradients of gamma/beta (LN), W1 (hidden,channels), b1, W2
+ * (channels,hidden), b2.  Replaces autograd's replay of layers/mlp.py:54-60 + layers/norm.py:29-34. */
+int fz_mlp_backward(const float* x1, const float* dout, const float* gamma, const float* beta, const float* W1,
+                    const float* b1, const float* W2, float* dx1, float* dgamma, float* dbeta, float* dW1, float* db1,
+                    float* dW2, float* db2, int64_t batch, int32_t channels, int32_t hidden, int64_t voxels, float eps,
+                    void* stream);
+
+/* Backward of y = W n(a) (+ b) with n = LayerNorm (layernorm != 0) or identity:
+ *   da = W^T dy, through the LayerNorm when there is one, plus `resid` (the gradient arriving over the residual
+ *   connection; may be NULL); dW = sum dy n(a)^T; db = sum dy (may be NULL); d(gamma), d(beta) (LayerNorm only).
+ * Serves out_proj (a = m, no LayerNorm) and in_proj + norm1 (a = x, resid = dx1). */
+int fz_linear_backward(const float* dy, const float* a, const float* gamma, const float* beta, const float* W,
+                       const float* resid, float* da, float* dW, float* db, float* dgamma, float* dbeta, int64_t batch,
+                       int32_t channels, int64_t voxels, float eps, int32_t layernorm, void* stream);
+
 /* Which implementation the last fz_swnmf_* call on this thread used: 0 = generic shared-memory
  * kernels, 1 = the window-at-a-time TMA/register kernels (8x512 windows, rank-1 HALS, any shifts),
  * 2 = the three-pass octant kernels (the same with shifts [0, patch/2] and ReLU: the default

@@ -72,6 +72,12 @@ FUSED_CASES = {
 BLOCK_CASES = {
     "block_c16_16": dict(channels=16, spatial=(16, 16, 16), batch=2, mlp_ratio=2,
                          kw=dict(head_dim=8, patch_size=8), nmf=dict(rank=1, num_iters=5, init="uniform", solver="hals")),
+    # 32 channels: the fully fused block path (csrc/fz_block_glue.cu); the second one has 384 voxels per
+    # sample (a partial 512-voxel tile) and 8x64 windows (generic core kernels)
+    "block_c32_16": dict(channels=32, spatial=(16, 16, 16), batch=1, mlp_ratio=2,
+                         kw=dict(head_dim=8, patch_size=8), nmf=dict(rank=1, num_iters=5, init="uniform", solver="hals")),
+    "block_c32_p4": dict(channels=32, spatial=(4, 8, 12), batch=2, mlp_ratio=1.5,
+                         kw=dict(head_dim=8, patch_size=4), nmf=dict(rank=1, num_iters=5, init="uniform", solver="hals")),
 }
 
 

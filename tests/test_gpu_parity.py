@@ -159,33 +159,126 @@ def test_unfused_chain_equals_fused(ft, dev, golden, name):
     assert_close(_np(gx), g[f"{name}/gx"], what="gx")
 
 
-def test_factorizer_block_matches_reference(ft, dev, golden):
-    name = "block_c16_16"
+@pytest.mark.parametrize("name", list(cases.BLOCK_CASES))
+def test_factorizer_block_matches_reference(ft, dev, golden, name):
     c = cases.BLOCK_CASES[name]
     g = golden["block"]
-    # the glue Linear layers are cuDNN convolutions, which default to TF32 on CUDA; parity against
-    # the reference's fp32 CPU run needs true fp32 there (the NMF kernels never use TF32)
+    # the layer-by-layer path (blocks that are not 32 channels wide) runs its Linear layers as library GEMMs,
+    # which may default to TF32 on CUDA; parity against the reference's fp32 CPU run needs true fp32 there
+    # (our own kernels never use TF32)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     blk = ft.FactorizerBlock(channels=c["channels"], spatial_size=c["spatial"], norm=ft.LayerNorm,
                              reshape=(ft.SWMatricize, c["kw"]), act=nn.ReLU, factorize=ft.NMF,
                              mlp_ratio=c["mlp_ratio"], dropout=0.0, **c["nmf"])
-    sd = {k.split("/sd/")[1]: torch.from_numpy(g[k]) for k in g.files if "/sd/" in k}
+    sd = {k.split("/sd/")[1]: torch.from_numpy(g[k]) for k in g.files if k.startswith(name + "/sd/")}
     blk.load_state_dict(sd)
     blk = blk.to(dev)
     xs = (c["batch"], c["channels"], *c["spatial"])
     x = torch.from_numpy(cases.make_array(name, xs, "randn")).to(dev).requires_grad_(True)
     gy = torch.from_numpy(cases.make_array(name, xs, "randn", tag="gy")).to(dev)
+    assert (blk._fused_args(x) is not None) == (c["channels"] == 32)
     y = blk(x)
+    assert (type(y.grad_fn).__name__ == "FactorizerBlockFnBackward") == (c["channels"] == 32)
     params = dict(blk.named_parameters())
     grads = torch.autograd.grad((y * gy).sum(), [x] + list(params.values()))
     assert_close(_np(y), g[f"{name}/y"], what="y")
     assert_close(_np(grads[0]), g[f"{name}/gx"], what="gx")
     for (k, _), gp in zip(params.items(), grads[1:]):
         ref = g[f"{name}/gp/{k}"]
-        # parameter gradients are sums over 8192 voxels of fp32 products: scale the bound accordingly
+        # parameter gradients are sums over thousands of voxels of fp32 products: scale the bound accordingly
         scale = max(1.0, float(np.abs(ref).max()))
         assert_close(_np(gp) / scale, ref / scale, rtol=1e-4, atol=1e-4, what=f"grad {k}")
+    # inference path (no saved tensors) gives the same output
+    with torch.no_grad():
+        assert torch.equal(blk(x.detach()), y.detach())
+
+
+def _glue_call(fn, *args):
+    from factorizer_b200 import _lib as L
+    L.check(fn(*[a.data_ptr() if isinstance(a, torch.Tensor) else a for a in args]))
+
+
+@pytest.mark.parametrize("shape", [(1, 32, 8, 8, 8), (2, 32, 6, 10, 7), (3, 32, 1030)])
+def test_glue_kernels_against_torch_fp64(ft, dev, shape):
+    """Each kernel of csrc/fz_block_glue.cu through the C ABI against fp64 torch autograd of the same
+    layers (LayerNorm over channels, k=1 Conv1d, exact GELU: the reference's factorizer/layers/*)."""
+    from factorizer_b200 import _lib as L
+    lib = L.lib()
+    torch.manual_seed(3)
+    B, C = shape[0], shape[1]
+    vox = int(np.prod(shape[2:]))
+    if vox % 2:
+        pytest.skip("odd voxel count")
+    HID = 48
+    st = torch.cuda.current_stream().cuda_stream
+    r = lambda *s: torch.randn(*s, device=dev)
+    x, m, gout = 2 * r(B, C, vox) + 0.5, r(B, C, vox), r(B, C, vox)
+    g1, b1n, g2, b2n = 1 + 0.3 * r(C), 0.3 * r(C), 1 + 0.3 * r(C), 0.3 * r(C)
+    w_in, w_out, b_out = r(C, C) / 6, r(C, C) / 6, 0.2 * r(C)
+    w1, bb1, w2, bb2 = r(HID, C) / 6, 0.2 * r(HID), r(C, HID) / 7, 0.2 * r(C)
+    eps = 1e-5
+    D = lambda t: t.detach().double().requires_grad_(True)
+    F = torch.nn.functional
+    ln = lambda t, g, b: F.layer_norm(t.movedim(1, -1), (C,), g, b, eps).movedim(-1, 1)
+    lin = lambda t, w, b=None: torch.einsum("oc,bcv->bov", w, t) + (0 if b is None else b[None, :, None])
+
+    def close(a, b, what, scale=1.0):
+        assert_close(_np(a) / scale, _np(b) / scale, rtol=1e-4, atol=2e-5, what=what)
+
+    # ---- z = W_in LN1(x) and its backward (with a residual gradient) ----
+    z = torch.empty_like(x)
+    _glue_call(lib.fz_ln_linear_forward, x, g1, b1n, w_in, z, B, C, vox, eps, st)
+    xd, g1d, b1d, wind = D(x), D(g1), D(b1n), D(w_in)
+    zd = lin(ln(xd, g1d, b1d), wind)
+    close(z, zd, "z")
+    dz, resid = r(B, C, vox), r(B, C, vox)
+    ref = torch.autograd.grad((zd * dz.double()).sum() + (xd * resid.double()).sum(), [xd, wind, g1d, b1d])
+    dx, dw, dg, dbt = torch.empty_like(x), torch.empty_like(w_in), torch.empty_like(g1), torch.empty_like(b1n)
+    _glue_call(lib.fz_linear_backward, dz, x, g1, b1n, w_in, resid, dx, dw, None, dg, dbt, B, C, vox, eps, 1, st)
+    close(dx, ref[0], "dx (in_proj + norm1)")
+    for got, want, what in ((dw, ref[1], "dW_in"), (dg, ref[2], "dgamma1"), (dbt, ref[3], "dbeta1")):
+        close(got, want, what, scale=max(1.0, float(want.abs().max())))
+
+    # ---- out_proj backward (no LayerNorm, bias) ----
+    md, woutd, boutd = D(m), D(w_out), D(b_out)
+    yd = lin(md, woutd, boutd)
+    ref = torch.autograd.grad((yd * dz.double()).sum(), [md, woutd, boutd])
+    dm, dwo, dbo = torch.empty_like(x), torch.empty_like(w_out), torch.empty_like(b_out)
+    _glue_call(lib.fz_linear_backward, dz, m, None, None, w_out, None, dm, dwo, dbo, None, None, B, C, vox, 0.0, 0, st)
+    close(dm, ref[0], "dm")
+    for got, want, what in ((dwo, ref[1], "dW_out"), (dbo, ref[2], "db_out")):
+        close(got, want, what, scale=max(1.0, float(want.abs().max())))
+
+    # ---- x1 = x + out_proj(m); out = x1 + MLP(LN2(x1)) and the MLP backward ----
+    x1, out = torch.empty_like(x), torch.empty_like(x)
+    _glue_call(lib.fz_mixer_mlp_forward, x, m, w_out, b_out, g2, b2n, w1, bb1, w2, bb2, x1, out, B, C, HID, vox, eps, st)
+    x1d = (x.double() + lin(m.double(), w_out.double(), b_out.double())).detach().requires_grad_(True)
+    g2d, b2d, w1d, bb1d, w2d, bb2d = D(g2), D(b2n), D(w1), D(bb1), D(w2), D(bb2)
+    outd = x1d + lin(F.gelu(lin(ln(x1d, g2d, b2d), w1d, bb1d)), w2d, bb2d)
+    close(x1, x1d, "x1")
+    close(out, outd, "out")
+    out2 = torch.empty_like(x)
+    _glue_call(lib.fz_mixer_mlp_forward, x, m, w_out, b_out, g2, b2n, w1, bb1, w2, bb2, None, out2, B, C, HID, vox, eps, st)
+    assert torch.equal(out, out2)
+    ref = torch.autograd.grad((outd * gout.double()).sum(), [x1d, g2d, b2d, w1d, bb1d, w2d, bb2d])
+    dx1 = torch.empty_like(x)
+    got = [dx1] + [torch.empty_like(t) for t in (g2, b2n, w1, bb1, w2, bb2)]
+    _glue_call(lib.fz_mlp_backward, x1, gout, g2, b2n, w1, bb1, w2, *got, B, C, HID, vox, eps, st)
+    close(got[0], ref[0], "dx1")
+    for a, b, what in zip(got[1:], ref[1:], ("dgamma2", "dbeta2", "dW1", "db1", "dW2", "db2")):
+        close(a, b, what, scale=max(1.0, float(b.abs().max())))
+
+
+def test_glue_rejects_unsupported(ft, dev):
+    from factorizer_b200 import _lib as L
+    lib = L.lib()
+    assert lib.fz_glue_supported(32, 64, 512) == 1
+    assert lib.fz_glue_supported(16, 32, 512) == 0 and lib.fz_glue_supported(32, 128, 512) == 0
+    assert lib.fz_glue_supported(32, 64, 511) == 0
+    x = torch.zeros(1, 16, 64, device=dev)
+    with pytest.raises(NotImplementedError):
+        L.check(lib.fz_ln_linear_forward(x.data_ptr(), None, None, x.data_ptr(), x.data_ptr(), 1, 16, 64, 1e-5, None))
 
 
 def test_reference_test_nmf_port(ft, dev):
