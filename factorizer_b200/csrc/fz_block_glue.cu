@@ -249,9 +249,10 @@ __global__ void __launch_bounds__(128, 2) mixer_mlp_fwd(const float* __restrict_
 // ------------------------------------------------------------------------------------------------
 // weight-gradient tiles
 // ------------------------------------------------------------------------------------------------
-// acc[(i*4+k)*32 + lane] += sum over the tile's voxels of SA[ro+4i][v] * SB[co+8k][v], ro = lane&3, co = lane>>2:
-// a 32x32 outer-product sum; warp w takes every 8th float4 column.
-__device__ __forceinline__ void wgrad_32x32(const float* __restrict__ SA, const float* __restrict__ SB, float* __restrict__ acc, int tid) {
+// scr[(i*4+k)*32 + lane] = this warp's share of sum_v SA[ro+4i][v] * SB[co+8k][v], ro = lane&3, co = lane>>2:
+// a 32x32 outer-product sum; warp w takes every 8th float4 column and writes to its own scratch slice (fp32
+// atomics on shared memory are compare-and-swap loops on this architecture, hence the two-step reduction).
+__device__ __forceinline__ void wgrad_32x32(const float* __restrict__ SA, const float* __restrict__ SB, float* __restrict__ scr, int tid) {
     const int lane = tid & 31, grp = tid >> 5, ro = lane & 3, co = lane >> 2;
     f2 a[8][4];
 #pragma unroll
@@ -277,12 +278,12 @@ __device__ __forceinline__ void wgrad_32x32(const float* __restrict__ SA, const 
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) atomicAdd(acc + (i * 4 + k) * 32 + lane, a[i][k].x + a[i][k].y);
+        for (int k = 0; k < 4; ++k) scr[(i * 4 + k) * 32 + lane] = a[i][k].x + a[i][k].y;
 }
 
-// acc[(i*4+k)*16 + tt] += sum_v SA[jh*4+i][v] * SB[rt+8k][v], tt = lane&15, jh = tt>>3, rt = tt&7: an 8x32
-// outer-product sum; 16 half-warps each take every 16th float4 column.
-__device__ __forceinline__ void wgrad_8x32(const float* __restrict__ SA, const float* __restrict__ SB, float* __restrict__ acc, int tid) {
+// scr[(i*4+k)*16 + tt] = this warp's share of sum_v SA[jh*4+i][v] * SB[rt+8k][v], tt = lane&15, jh = tt>>3,
+// rt = tt&7: an 8x32 outer-product sum; 16 half-warps each take every 16th float4 column.
+__device__ __forceinline__ void wgrad_8x32(const float* __restrict__ SA, const float* __restrict__ SB, float* __restrict__ scr, int tid) {
     const int lane = tid & 31, tt = lane & 15, jh = tt >> 3, rt = tt & 7, grp = (tid >> 5) * 2 + (lane >> 4);
     f2 a[4][4];
 #pragma unroll
@@ -311,9 +312,14 @@ __device__ __forceinline__ void wgrad_8x32(const float* __restrict__ SA, const f
         for (int k = 0; k < 4; ++k) {
             float s = a[i][k].x + a[i][k].y;
             s += __shfl_xor_sync(0xffffffffu, s, 16);
-            if (lane < 16) atomicAdd(acc + (i * 4 + k) * 16 + tt, s);
+            if (lane < 16) scr[(i * 4 + k) * 16 + tt] = s;
         }
 }
+
+constexpr int kWarps = kTT / 32;
+constexpr int kScrLin = kC * kC + 3 * kC;   // per-warp scratch of linear_bwd: dW partials | db | dgamma | dbeta
+constexpr int kScrMlp = 2 * 256 + 8;        // per-warp scratch of mlp_bwd per 8 hidden units: dW2 | Q | db1
+constexpr int kScrMlpV = 3 * kC;            // ... and per tile: db2 | dgamma | dbeta
 
 // ------------------------------------------------------------------------------------------------
 // backward of y = W n(a) (+ b), n = LayerNorm or identity:
@@ -333,9 +339,11 @@ __global__ void __launch_bounds__(kTT, 1) linear_bwd(const float* __restrict__ d
     float* bs = gs + C;
     float* accW = bs + C;              // [(i*4+k)][lane]
     float* accv = accW + C * C;        // db | dgamma | dbeta
-    float* SA = accv + 3 * C;          // dy  [o][v]
+    float* scr = accv + 3 * C;         // [warp][kScrLin]
+    float* SA = scr + kWarps * kScrLin;  // dy  [o][v]
     float* SB = SA + C * kRS;          // n(a) [c][v]
     const int tid = threadIdx.x, lane = tid & 31;
+    float* scr_w = scr + (tid >> 5) * kScrLin;
     for (int i = tid; i < C * C; i += kTT) { Ws[i] = W[i]; accW[i] = 0.f; }
     for (int c = tid; c < C; c += kTT) { gs[c] = gamma ? gamma[c] : 1.f; bs[c] = beta ? beta[c] : 0.f; }
     for (int c = tid; c < 3 * C; c += kTT) accv[c] = 0.f;
@@ -346,17 +354,17 @@ __global__ void __launch_bounds__(kTT, 1) linear_bwd(const float* __restrict__ d
         const bool valid = 2 * pv < vox;
         const long long base = b * C * vox + 2 * pv;
         f2 d0[C / 2], d1[C / 2];
+        float r_db, r_dg = 0.f, r_dbeta = 0.f;
         {
             f2 g[C];
             load_cols<C>(dy + base, vox, valid, g);
 #pragma unroll
             for (int o = 0; o < C; ++o) *reinterpret_cast<f2*>(SA + o * kRS + 2 * tid) = g[o];
-            if (db || LN) {
+            {
                 float s[C];
 #pragma unroll
                 for (int o = 0; o < C; ++o) s[o] = g[o].x + g[o].y;
-                const float r = warp_vec_sum<C>(s, lane);
-                atomicAdd(accv + lane, r);
+                r_db = warp_vec_sum<C>(s, lane);
             }
 #pragma unroll
             for (int k = 0; k < C / 2; ++k) d0[k] = d1[k] = make_float2(0.f, 0.f);
@@ -390,10 +398,8 @@ __global__ void __launch_bounds__(kTT, 1) linear_bwd(const float* __restrict__ d
                     *reinterpret_cast<f2*>(da + base + c * vox) = o;
                 }
             }
-            const float rg = warp_vec_sum<C>(sg, lane);
-            atomicAdd(accv + C + lane, rg);
-            const float rb = warp_vec_sum<C>(sb, lane);
-            atomicAdd(accv + 2 * C + lane, rb);
+            r_dg = warp_vec_sum<C>(sg, lane);
+            r_dbeta = warp_vec_sum<C>(sb, lane);
         } else {
 #pragma unroll
             for (int c = 0; c < C; ++c) {
@@ -401,10 +407,20 @@ __global__ void __launch_bounds__(kTT, 1) linear_bwd(const float* __restrict__ d
                 if (valid) *reinterpret_cast<f2*>(da + base + c * vox) = unpair<C>(d0, d1, c);
             }
         }
+        __syncthreads();   // tile staged; the previous tile's scratch has been consumed
+        wgrad_32x32(SA, SB, scr_w, tid);
+        scr_w[C * C + lane] = r_db;
+        scr_w[C * C + C + lane] = r_dg;
+        scr_w[C * C + 2 * C + lane] = r_dbeta;
         __syncthreads();
-        wgrad_32x32(SA, SB, accW, tid);
-        __syncthreads();
+        for (int o = tid; o < kScrLin; o += kTT) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) t += scr[w * kScrLin + o];
+            accW[o] += t;      // accv follows accW in shared memory
+        }
     }
+    __syncthreads();
     // accW[(i*4+k)*32 + lane] is dW[(lane&3) + 4i][(lane>>2) + 8k]
     for (int i = tid; i < C * C; i += kTT) {
         const int e = i >> 5, l = i & 31;
@@ -441,11 +457,13 @@ __global__ void __launch_bounds__(kTT, 1) mlp_bwd(const float* __restrict__ x1, 
     float* accW2 = accQ + HID * C;      // sum_v g dout^T, same tiling
     float* accb1 = accW2 + HID * C;     // [j]
     float* accv = accb1 + HID;          // db2 | dgamma | dbeta
-    float* Snh = accv + 3 * C;          // a_hat [c][v]
+    float* scr = accv + 3 * C;          // [warp][kScrMlp + kScrMlpV]
+    float* Snh = scr + kWarps * (kScrMlp + kScrMlpV);   // a_hat [c][v]
     float* Sdo = Snh + C * kRS;         // dout  [o][v]
     float* Sg = Sdo + C * kRS;          // gelu(h) of the current 8 hidden units [j][v]
     float* Sdh = Sg + 8 * kRS;          // dh of the current 8 hidden units
     const int tid = threadIdx.x, lane = tid & 31;
+    float* scr_w = scr + (tid >> 5) * (kScrMlp + kScrMlpV);
     for (int c = tid; c < C; c += kTT) { gs[c] = gamma ? gamma[c] : 1.f; bs[c] = beta ? beta[c] : 0.f; }
     for (int c = tid; c < 3 * C; c += kTT) accv[c] = 0.f;
     for (int j = tid; j < HID; j += kTT) accb1[j] = 0.f;
@@ -476,17 +494,10 @@ __global__ void __launch_bounds__(kTT, 1) mlp_bwd(const float* __restrict__ x1, 
         const f2 rstd = normalize<C>(nh, eps);
 #pragma unroll
         for (int c = 0; c < C; ++c) *reinterpret_cast<f2*>(Snh + c * kRS + 2 * tid) = nh[c];
-        {
-            float s[C];
 #pragma unroll
-            for (int o = 0; o < C; ++o) {
-                const f2 g = valid ? __ldg(reinterpret_cast<const f2*>(dout + base + o * vox)) : make_float2(0.f, 0.f);
-                *reinterpret_cast<f2*>(Sdo + o * kRS + 2 * tid) = g;
-                s[o] = g.x + g.y;
-            }
-            const float r = warp_vec_sum<C>(s, lane);
-            atomicAdd(accv + lane, r);
-        }
+        for (int o = 0; o < C; ++o)
+            *reinterpret_cast<f2*>(Sdo + o * kRS + 2 * tid) =
+                valid ? __ldg(reinterpret_cast<const f2*>(dout + base + o * vox)) : make_float2(0.f, 0.f);
         f2 dn0[C / 2], dn1[C / 2];   // d(LN output) = W1^T dh
 #pragma unroll
         for (int k = 0; k < C / 2; ++k) dn0[k] = dn1[k] = make_float2(0.f, 0.f);
@@ -518,12 +529,20 @@ __global__ void __launch_bounds__(kTT, 1) mlp_bwd(const float* __restrict__ x1, 
                 sb[2 * k + 1] = dh[2 * k + 1].x + dh[2 * k + 1].y;
             }
             const float r = warp_vec_sum<8>(sb, lane);
-            if ((lane & 3) == 0) atomicAdd(accb1 + j0 + (lane >> 2), r);
             matvec<8, C>(W1s + j0 * C, C, dh, dn0, dn1);
+            __syncthreads();   // the 8 hidden units are staged; the previous scratch has been consumed
+            wgrad_8x32(Sg, Sdo, scr_w, tid);
+            wgrad_8x32(Sdh, Snh, scr_w + 256, tid);
+            if ((lane & 3) == 0) scr_w[512 + (lane >> 2)] = r;
             __syncthreads();
-            wgrad_8x32(Sg, Sdo, accW2 + (j0 >> 3) * 256, tid);
-            wgrad_8x32(Sdh, Snh, accQ + (j0 >> 3) * 256, tid);
-            __syncthreads();
+            for (int o = tid; o < kScrMlp; o += kTT) {
+                float t = 0.f;
+#pragma unroll
+                for (int w = 0; w < kWarps; ++w) t += scr[w * (kScrMlp + kScrMlpV) + o];
+                if (o < 256) accW2[(j0 >> 3) * 256 + o] += t;
+                else if (o < 512) accQ[(j0 >> 3) * 256 + o - 256] += t;
+                else accb1[j0 + o - 512] += t;
+            }
         }
         // through LayerNorm, plus the residual branch
         {
@@ -539,24 +558,29 @@ __global__ void __launch_bounds__(kTT, 1) mlp_bwd(const float* __restrict__ x1, 
                 m2.x = fmaf(t.x, nh[c].x, m2.x); m2.y = fmaf(t.y, nh[c].y, m2.y);
             }
             m1.x *= (1.f / C); m1.y *= (1.f / C); m2.x *= (1.f / C); m2.y *= (1.f / C);
-            if (valid) {
+            scr_w[kScrMlp + C + lane] = warp_vec_sum<C>(sg, lane);
+            scr_w[kScrMlp + 2 * C + lane] = warp_vec_sum<C>(sb, lane);
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const f2 d = unpair<C>(dn0, dn1, c);
-                    const f2 g = *reinterpret_cast<const f2*>(mycol_do + c * kRS);
-                    f2 o;
-                    o.x = g.x + rstd.x * (d.x * gs[c] - m1.x - nh[c].x * m2.x);
-                    o.y = g.y + rstd.y * (d.y * gs[c] - m1.y - nh[c].y * m2.y);
-                    *reinterpret_cast<f2*>(dx1 + base + c * vox) = o;
-                }
+            for (int c = 0; c < C; ++c) {
+                const f2 d = unpair<C>(dn0, dn1, c);
+                const f2 g = *reinterpret_cast<const f2*>(mycol_do + c * kRS);
+                sb[c] = g.x + g.y;
+                f2 o;
+                o.x = g.x + rstd.x * (d.x * gs[c] - m1.x - nh[c].x * m2.x);
+                o.y = g.y + rstd.y * (d.y * gs[c] - m1.y - nh[c].y * m2.y);
+                if (valid) *reinterpret_cast<f2*>(dx1 + base + c * vox) = o;
             }
-            const float rg = warp_vec_sum<C>(sg, lane);
-            atomicAdd(accv + C + lane, rg);
-            const float rb = warp_vec_sum<C>(sb, lane);
-            atomicAdd(accv + 2 * C + lane, rb);
+            scr_w[kScrMlp + lane] = warp_vec_sum<C>(sb, lane);
         }
-        __syncthreads();   // the next tile restages Snh / Sdo
+        __syncthreads();   // per-tile sums are in the scratch; the next tile may restage Snh / Sdo
+        if (tid < kScrMlpV) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) t += scr[w * (kScrMlp + kScrMlpV) + kScrMlp + tid];
+            accv[tid] += t;
+        }
     }
+    __syncthreads();
     // flush: acc[(j0/8)*256 + (i*4+k)*16 + tt] is the (j, r) entry with j = j0 + (tt>>3)*4 + i, r = (tt&7) + 8k
     for (int idx = tid; idx < HID * C; idx += kTT) {
         const int blk = idx >> 8, e = (idx >> 4) & 15, tt = idx & 15;
@@ -595,9 +619,9 @@ int check_common(long long batch, int channels, long long voxels) {
 
 bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) != 0; }
 
-size_t linear_bwd_smem() { return sizeof(float) * (2 * kC * kC + 2 * kC + 3 * kC + 2 * kC * kRS); }
+size_t linear_bwd_smem() { return sizeof(float) * (2 * kC * kC + 2 * kC + 3 * kC + kWarps * kScrLin + 2 * kC * kRS); }
 size_t mlp_fwd_smem(int hid) { return sizeof(float) * (kC * kC + 2 * kC * hid + hid + 4 * kC); }
-size_t mlp_bwd_smem(int hid) { return sizeof(float) * (5 * kC * hid + 2 * hid + 2 * kC + 3 * kC + (2 * kC + 16) * kRS); }
+size_t mlp_bwd_smem(int hid) { return sizeof(float) * (5 * kC * hid + 2 * hid + 2 * kC + 3 * kC + kWarps * (kScrMlp + kScrMlpV) + (2 * kC + 16) * kRS); }
 
 }  // namespace
 }  // namespace fz
