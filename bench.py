@@ -7,11 +7,12 @@ Workload (config.workload): BASELINE config 2 -- ft.SWMatricize(head_dim 8, patc
 ft.NMF(rank 1, 5 HALS sweeps) + inverse, forward + backward on one (1, 32, 128^3) fp32 volume per GPU,
 i.e. the fused FactMixer core that FactorizerBlock runs between its two 1x1 projections.  A "step" is
 one forward + one backward through the C ABI (fz_swnmf_forward / fz_swnmf_backward).  The same line
-also carries the whole FactorizerBlock (BASELINE config 3, PyTorch glue around the fused core) in
+also carries the whole FactorizerBlock (BASELINE config 3: fused glue kernels around the fused core) in
 `block`.
 
 value      voxels/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks)
 e2e        same metric with HOST buffers: pinned-host x and dY copied in, y and dX copied out, every step
+           (steps pipelined over copy-in / kernel / copy-out streams with double-buffered device tensors)
 roofline   dominant kernel (phase_bwd_apply = pass 3 of the backward: reads X and dY, writes dX, i.e. exactly
            the backward's compulsory traffic): algorithmic bytes / event-timed launch duration vs the
            measured HBM peak in MEASURED_PEAKS.json.  The kernel is isolated with the C ABI's measurement
@@ -231,33 +232,58 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     # ---------------- end-to-end with host buffers ----------------
+    # Every step copies its own x and dY in from pinned host memory and its y and dX back out; consecutive steps
+    # are pipelined over three streams (copy-in | kernels | copy-out) with two sets of device buffers, so the
+    # host->device copy of step k+1 and the device->host copy of step k-1 run while step k computes (PCIe is
+    # full duplex).
     hx = torch.rand(1, C, N, N, N).pin_memory()
     hgy = torch.randn(1, C, N, N, N).pin_memory()
     hy = torch.empty(1, C, N, N, N).pin_memory()
     hgx = torch.empty(1, C, N, N, N).pin_memory()
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    bufs = [dict(x=x, gy=gy, y=y, gx=gx),
+            dict(x=torch.empty_like(x), gy=torch.empty_like(x), y=torch.empty_like(x), gx=torch.empty_like(x))]
+    in_ready = [torch.cuda.Event() for _ in range(2)]
+    comp_done = [torch.cuda.Event() for _ in range(2)]
+    out_done = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_step():
-        x.copy_(hx, non_blocking=True)
-        gy.copy_(hgy, non_blocking=True)
-        fwd()
-        hy.copy_(y, non_blocking=True)
-        bwd()
-        hgx.copy_(gx, non_blocking=True)
+    def e2e_step(k):
+        b = bufs[k % 2]
+        s_in.wait_event(comp_done[k % 2])          # the kernels of step k-2 have consumed these input buffers
+        with torch.cuda.stream(s_in):
+            b["x"].copy_(hx, non_blocking=True)
+            b["gy"].copy_(hgy, non_blocking=True)
+            in_ready[k % 2].record(s_in)
+        stream.wait_event(in_ready[k % 2])
+        stream.wait_event(out_done[k % 2])          # step k-2's results have left these output buffers
+        _lib.check(lib.fz_swnmf_forward(b["x"].data_ptr(), u0.data_ptr(), v0.data_ptr(), b["y"].data_ptr(), saved.data_ptr(),
+                                        ws.data_ptr(), ctypes.byref(g), ctypes.byref(s), 1, sp))
+        _lib.check(lib.fz_swnmf_backward(b["x"].data_ptr(), b["gy"].data_ptr(), u0.data_ptr(), v0.data_ptr(), saved.data_ptr(),
+                                         b["gx"].data_ptr(), ws.data_ptr(), ctypes.byref(g), ctypes.byref(s), 1, sp))
+        comp_done[k % 2].record(stream)
+        s_out.wait_event(comp_done[k % 2])
+        with torch.cuda.stream(s_out):
+            hy.copy_(b["y"], non_blocking=True)
+            hgx.copy_(b["gx"], non_blocking=True)
+            out_done[k % 2].record(s_out)
 
-    e2e_steps = max(2, min(args.steps, 10))
-    for _ in range(2):
-        e2e_step()
+    e2e_steps = max(4, min(args.steps, 10))
+    for k in range(2):
+        e2e_step(k)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(e2e_steps):
-        e2e_step()
+    s_in.wait_event(e0)
+    for k in range(e2e_steps):
+        e2e_step(k)
+    stream.wait_stream(s_out)
     e1.record(stream)
     barrier()
     e2e_ms = e0.elapsed_time(e1) / e2e_steps
     clocks = sampler.stop() if rank == 0 else None
+    del bufs
 
-    # ---------------- whole FactorizerBlock (config 3), PyTorch glue around the fused core ----------------
+    # ---------------- whole FactorizerBlock (config 3): fused glue kernels around the fused core ----------------
     block = None
     if not args.no_block:
         torch.backends.cudnn.allow_tf32 = False
@@ -268,6 +294,7 @@ def run_ours(args):
                                  act=torch.nn.ReLU, factorize=ft.NMF, rank=1, num_iters=T_ITERS, init="uniform",
                                  solver="hals", mlp_ratio=2, dropout=0.0).to(dev)
         xb = torch.rand(1, C, N, N, N, device=dev, requires_grad=True)
+        block_fused = blk._fused_args(xb) is not None
         for _ in range(2):
             blk(xb).backward(gy)
         barrier()
@@ -279,8 +306,11 @@ def run_ours(args):
         b1.record(stream)
         barrier()
         bms = b0.elapsed_time(b1) / nb
-        block = {"workload": "FactorizerBlock(32,128^3,LayerNorm,SWMatricize,HALS r1,mlp_ratio=2,dropout=0) fwd+bwd, "
-                             "B=1/GPU, fp32 glue (TF32 off)", "ms_per_step": bms, "voxels_per_s_per_gpu": N ** 3 / (bms * 1e-3)}
+        block = {"workload": "FactorizerBlock(32,128^3,LayerNorm,SWMatricize,HALS r1,mlp_ratio=2,dropout=0) fwd+bwd incl. "
+                             "parameter gradients, B=1/GPU, fp32",
+                 "path": "hand-written glue kernels (fz_block_glue.cu) + fused core: 3 launches fwd, 4 bwd" if block_fused
+                         else "layer by layer (library GEMMs) around the fused core",
+                 "ms_per_step": bms, "voxels_per_s_per_gpu": N ** 3 / (bms * 1e-3)}
 
     # ---------------- reduce over ranks ----------------
     dom_us = passes_us["phase_bwd_apply"] if passes_us else bwd_us
@@ -331,6 +361,8 @@ def run_ours(args):
         if block:
             block["ms_per_step"] = block_ms
             block["voxels_per_s"] = world * voxels / (block_ms * 1e-3)
+            # 20*C bytes per voxel is the absolute floor for the whole block too: x, dOut in; out, dX out
+            block["hbm_frac_of_absolute_floor"] = 5 * n_el * 4 / (block_ms * 1e-3) / 1e9 / peak
             block.pop("voxels_per_s_per_gpu", None)
             line["block"] = block
         if world == 1 and not args.no_cpu:
