@@ -5,5 +5,6 @@ from .layers import *  # noqa: F401,F403
 from .operations import *  # noqa: F401,F403
 from .matrix_factorization import *  # noqa: F401,F403
 from .factorizer import *  # noqa: F401,F403
+from .segmentation import *  # noqa: F401,F403
 
 __version__ = "0.1.0"

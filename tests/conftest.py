@@ -34,4 +34,4 @@ def assert_close(got, ref, rtol=RTOL, atol=ATOL, what=""):
 @pytest.fixture(scope="session")
 def golden():
     d = os.path.join(ROOT, "tests", "golden")
-    return {k: np.load(os.path.join(d, f"{k}.npz")) for k in ("nmf", "sw", "fused", "block")}
+    return {k: np.load(os.path.join(d, f"{k}.npz")) for k in ("nmf", "sw", "fused", "block", "model")}

@@ -81,6 +81,17 @@ BLOCK_CASES = {
 }
 
 
+# --- whole Swin Factorizer (factorizer/factorizer.py:125-171), README.md:78-96 at a small size --------
+MODEL_CASES = {
+    # two encoder levels (32 and 64 channels: fused block path and layer-by-layer path), bottleneck with the
+    # positional embedding, one decoder level with its 64 -> 32 adapter; eval mode (dropout 0.1 inactive)
+    "swin_2level_16": dict(in_channels=2, out_channels=3, spatial=(16, 16, 16), batch=1,
+                           kw=dict(encoder_depth=(1, 1), encoder_width=(32, 64), strides=(1, 2), decoder_depth=(1,),
+                                   rank=1, num_iters=5, init="uniform", solver="hals", mlp_ratio=2, dropout=0.1),
+                           reshape_kw=dict(head_dim=8, patch_size=8)),
+}
+
+
 def _seed(name: str) -> int:
     return int.from_bytes(hashlib.sha256(name.encode()).digest()[:4], "little")
 

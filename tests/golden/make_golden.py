@@ -6,7 +6,7 @@ Build-container only (the reference does not exist on the GPU box):
     python tests/golden/make_golden.py
 
 The reference imports ``opt_einsum`` (factorizer/factorization/matrix_factorization.py:8) but never
-uses it; an empty stub module stands in for it.  Outputs: nmf.npz, sw.npz, fused.npz, block.npz.
+uses it; an empty stub module stands in for it.  Outputs: nmf.npz, sw.npz, fused.npz, block.npz, model.npz.
 """
 from __future__ import annotations
 
@@ -147,8 +147,36 @@ def gen_block():
     print("block.npz", len(out), "arrays")
 
 
+def gen_model():
+    out = {}
+    for name, c in cases.MODEL_CASES.items():
+        torch.manual_seed(cases._seed(name) % (2**31))
+        net = ft.Factorizer(in_channels=c["in_channels"], out_channels=c["out_channels"], spatial_size=c["spatial"],
+                            norm=ft.LayerNorm, reshape=(ft.SWMatricize, c["reshape_kw"]), act=nn.ReLU,
+                            factorize=ft.NMF, **c["kw"]).eval()
+        with torch.no_grad():
+            for p in net.parameters():
+                if p.ndim == 1:
+                    p.add_(0.1 * torch.randn_like(p))
+        xs = (c["batch"], c["in_channels"], *c["spatial"])
+        x = t(cases.make_array(name, xs, "randn")).requires_grad_(True)
+        y = net(x)
+        gy = t(cases.make_array(name, tuple(y.shape), "randn", tag="gy"))
+        params = list(net.parameters())
+        grads = torch.autograd.grad((y * gy).sum(), [x] + params)
+        for k, v in net.state_dict().items():
+            out[f"{name}/sd/{k}"] = v.numpy().copy()
+        out[f"{name}/y"] = y.detach().numpy()
+        out[f"{name}/gx"] = grads[0].numpy()
+        for (k, _), g in zip(net.named_parameters(), grads[1:]):
+            out[f"{name}/gp/{k}"] = g.numpy()
+    np.savez(os.path.join(HERE, "model.npz"), **out)
+    print("model.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
     gen_nmf()
     gen_sw()
     gen_fused()
     gen_block()
+    gen_model()

@@ -194,6 +194,33 @@ def test_factorizer_block_matches_reference(ft, dev, golden, name):
         assert torch.equal(blk(x.detach()), y.detach())
 
 
+@pytest.mark.parametrize("name", list(cases.MODEL_CASES))
+def test_factorizer_model_matches_reference(ft, dev, golden, name):
+    """Whole Swin Factorizer (BASELINE config 4/5 architecture at a small size) from a reference state_dict:
+    output, input gradient and every parameter gradient against the reference's CPU run."""
+    c, g = cases.MODEL_CASES[name], golden["model"]
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    net = ft.Factorizer(in_channels=c["in_channels"], out_channels=c["out_channels"], spatial_size=c["spatial"],
+                        norm=ft.LayerNorm, reshape=(ft.SWMatricize, c["reshape_kw"]), act=nn.ReLU, factorize=ft.NMF,
+                        **c["kw"])
+    net.load_state_dict({k.split("/sd/")[1]: torch.from_numpy(g[k]) for k in g.files if k.startswith(name + "/sd/")})
+    net = net.to(dev).eval()
+    xs = (c["batch"], c["in_channels"], *c["spatial"])
+    x = torch.from_numpy(cases.make_array(name, xs, "randn")).to(dev).requires_grad_(True)
+    y = net(x)
+    assert tuple(y.shape) == g[f"{name}/y"].shape
+    gy = torch.from_numpy(cases.make_array(name, tuple(y.shape), "randn", tag="gy")).to(dev)
+    params = dict(net.named_parameters())
+    grads = torch.autograd.grad((y * gy).sum(), [x] + list(params.values()))
+    assert_close(_np(y), g[f"{name}/y"], rtol=2e-4, atol=2e-5, what="y")
+    assert_close(_np(grads[0]), g[f"{name}/gx"], rtol=2e-4, atol=2e-5, what="gx")
+    for (k, _), gp in zip(params.items(), grads[1:]):
+        ref = g[f"{name}/gp/{k}"]
+        scale = max(1.0, float(np.abs(ref).max()))
+        assert_close(_np(gp) / scale, ref / scale, rtol=2e-4, atol=2e-4, what=f"grad {k}")
+
+
 def _glue_call(fn, *args):
     from factorizer_b200 import _lib as L
     L.check(fn(*[a.data_ptr() if isinstance(a, torch.Tensor) else a for a in args]))

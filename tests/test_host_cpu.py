@@ -72,6 +72,39 @@ def test_readme_shapes_and_state_dict_keys(ft, golden):
         assert tuple(v.shape) == golden["block"][f"block_c16_16/sd/{k}"].shape
 
 
+def _build_model(ft, c):
+    return ft.Factorizer(in_channels=c["in_channels"], out_channels=c["out_channels"], spatial_size=c["spatial"],
+                         norm=ft.LayerNorm, reshape=(ft.SWMatricize, c["reshape_kw"]), act=nn.ReLU, factorize=ft.NMF,
+                         **c["kw"])
+
+
+@pytest.mark.parametrize("name", list(cases.MODEL_CASES))
+def test_factorizer_model_state_dict_matches_reference(ft, golden, name):
+    """ft.Factorizer (reference factorizer/factorizer.py:125-171 on unet.py:177-276): same module tree, hence the
+    same state_dict keys in the same order and the same shapes, and the same consumption of the global RNG at
+    construction (every buffer / parameter drawn before the generator's perturbation is bit-identical)."""
+    c, g = cases.MODEL_CASES[name], golden["model"]
+    torch.manual_seed(cases._seed(name) % (2**31))
+    net = _build_model(ft, c)
+    ref_keys = [k.split("/sd/")[1] for k in g.files if k.startswith(name + "/sd/")]
+    sd = net.state_dict()
+    assert list(sd.keys()) == ref_keys
+    for k, v in sd.items():
+        ref = g[f"{name}/sd/{k}"]
+        assert tuple(v.shape) == ref.shape
+        if v.ndim != 1:   # 1-D parameters were perturbed after construction by make_golden.py
+            np.testing.assert_array_equal(v.numpy(), ref, err_msg=k)
+    net.load_state_dict({k: torch.from_numpy(g[f"{name}/sd/{k}"]) for k in ref_keys})
+    # deep supervision heads (unet.py:252-259, 269-276)
+    net2 = ft.Factorizer(in_channels=1, out_channels=2, spatial_size=(16, 16), encoder_depth=(1, 1, 1),
+                         encoder_width=(8, 16, 32), strides=(1, 2, 2), decoder_depth=(1, 1), num_deep_supr=2,
+                         reshape=(ft.SWMatricize, {"head_dim": 4, "patch_size": 4}), rank=1)
+    assert [k for k in net2.state_dict() if k.startswith("head")] == ["heads.0.weight", "heads.0.bias", "heads.1.weight",
+                                                                     "heads.1.bias"]
+    with pytest.raises(NotImplementedError):
+        ft.UNet(1, 2)
+
+
 @pytest.mark.parametrize("name", list(cases.SW_CASES))
 def test_output_size_matches_reference(ft, golden, name):
     c = cases.SW_CASES[name]
