@@ -24,12 +24,14 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--tf32", action="store_true", help="let the cuDNN / cuBLAS glue use TF32 (off: true fp32)")
+    ap.add_argument("--no-cudnn-benchmark", action="store_true", help="leave cuDNN's heuristic algorithm choice on")
     args = ap.parse_args()
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", 1), ("RANK", 0), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark   # heuristics pick a 20 ms fp32 wgrad for the stem
     torch.backends.cudnn.allow_tf32 = args.tf32
     torch.backends.cuda.matmul.allow_tf32 = args.tf32
     torch.manual_seed(1234)          # identical weights and NMF buffers on every rank
@@ -89,7 +91,7 @@ def main():
     if rank == 0:
         print(json.dumps({"workload": f"Swin Factorizer 4->3 ch, {n}^3, widths (32,64,128,256,512), HALS rank 1, {args.mode}",
                           "params": nparams, "n_gpus": world, "ms_per_step": ms.item(),
-                          "voxels_per_s": world * n ** 3 / (ms.item() * 1e-3), "tf32_glue": args.tf32,
+                          "voxels_per_s": world * n ** 3 / (ms.item() * 1e-3), "tf32_glue": args.tf32, "cudnn_benchmark": not args.no_cudnn_benchmark,
                           "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}))
     if world > 1:
         dist.destroy_process_group()

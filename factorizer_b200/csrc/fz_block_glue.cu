@@ -123,12 +123,31 @@ __device__ __forceinline__ float warp_vec_sum(float (&v)[N], int lane) {
     return r;
 }
 
-__device__ __forceinline__ float gelu(float h) { return 0.5f * h * (1.f + erff(h * 0.70710678118654752f)); }
+// Exact (erf) GELU through Abramowitz-Stegun 7.1.26: erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1/(1 + p z),
+// |error| <= 1.5e-7 for z >= 0, odd extension below.  With z = |h|/sqrt(2) the exponential is exp(-h^2/2), which is
+// also the density the derivative needs; two MUFU ops (RCP, EX2) and ~12 FP32 ops instead of erff + expf (~45).
+// Returns Phi(h) = (1 + erf(h/sqrt 2))/2 and e = exp(-h^2/2).
+__device__ __forceinline__ float gauss_cdf(float h, float& e) {
+    const float z = fabsf(h) * 0.70710678118654752f;
+    const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+    e = exp2f(h * h * -0.72134752044448170f);            // exp(-h^2/2) = 2^(-h^2 / (2 ln 2))
+    float p = fmaf(t, 1.061405429f, -1.453152027f);
+    p = fmaf(t, p, 1.421413741f);
+    p = fmaf(t, p, -0.284496736f);
+    p = fmaf(t, p, 0.254829592f);
+    const float erf_abs = fmaf(-(p * t), e, 1.f);
+    return fmaf(copysignf(0.5f, h), erf_abs, 0.5f);
+}
+__device__ __forceinline__ float gelu(float h) {
+    float e;
+    return h * gauss_cdf(h, e);
+}
 // gelu(h) and its derivative Phi(h) + h phi(h)  (torch: GeluBackward, approximate='none')
 __device__ __forceinline__ void gelu_grad(float h, float& g, float& gp) {
-    const float cdf = 0.5f * (1.f + erff(h * 0.70710678118654752f));
+    float e;
+    const float cdf = gauss_cdf(h, e);
     g = h * cdf;
-    gp = fmaf(h * 0.39894228040143268f, expf(-0.5f * h * h), cdf);
+    gp = fmaf(h * 0.39894228040143268f, e, cdf);
 }
 
 template <int C>
@@ -250,9 +269,11 @@ __global__ void __launch_bounds__(128, 2) mixer_mlp_fwd(const float* __restrict_
 // weight-gradient tiles
 // ------------------------------------------------------------------------------------------------
 // scr[(i*4+k)*32 + lane] = this warp's share of sum_v SA[ro+4i][v] * SB[co+8k][v], ro = lane&3, co = lane>>2:
-// a 32x32 outer-product sum; warp w takes every 8th float4 column and writes to its own scratch slice (fp32
+// a 32x32 outer-product sum; warp w takes every NW-th float4 column and writes to its own scratch slice (fp32
 // atomics on shared memory are compare-and-swap loops on this architecture, hence the two-step reduction).
+template <int TV, int NW>
 __device__ __forceinline__ void wgrad_32x32(const float* __restrict__ SA, const float* __restrict__ SB, float* __restrict__ scr, int tid) {
+    constexpr int RS = TV + 4;
     const int lane = tid & 31, grp = tid >> 5, ro = lane & 3, co = lane >> 2;
     f2 a[8][4];
 #pragma unroll
@@ -260,14 +281,14 @@ __device__ __forceinline__ void wgrad_32x32(const float* __restrict__ SA, const 
 #pragma unroll
         for (int k = 0; k < 4; ++k) a[i][k] = make_float2(0.f, 0.f);
 #pragma unroll 1
-    for (int it = 0; it < kTV / 4 / 8; ++it) {
-        const int v = (it * 8 + grp) * 4;
+    for (int it = 0; it < TV / 4 / NW; ++it) {
+        const int v = (it * NW + grp) * 4;
         float4 B[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) B[k] = *reinterpret_cast<const float4*>(SB + (co + 8 * k) * kRS + v);
+        for (int k = 0; k < 4; ++k) B[k] = *reinterpret_cast<const float4*>(SB + (co + 8 * k) * RS + v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float4 A = *reinterpret_cast<const float4*>(SA + (ro + 4 * i) * kRS + v);
+            const float4 A = *reinterpret_cast<const float4*>(SA + (ro + 4 * i) * RS + v);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 a[i][k] = fma2(make_float2(A.x, A.y), make_float2(B[k].x, B[k].y), a[i][k]);
@@ -326,8 +347,11 @@ constexpr int kScrMlpV = 3 * kC;            // ... and per tile: db2 | dgamma | 
 //   da = W^T dy            (LN: dx = resid + LN'(da))
 //   dW = sum_v dy n(a)^T,  db = sum_v dy,  d(gamma) = sum_v da . a_hat,  d(beta) = sum_v da
 // ------------------------------------------------------------------------------------------------
+// 128 threads / 256-voxel tiles, two CTAs per SM: one loads its tile while the other computes
+constexpr int kLT = 128, kLV = 2 * kLT, kLRS = kLV + 4, kLWarps = kLT / 32;
+
 template <int C, bool LN>
-__global__ void __launch_bounds__(kTT, 1) linear_bwd(const float* __restrict__ dy, const float* __restrict__ a,
+__global__ void __launch_bounds__(kLT, 2) linear_bwd(const float* __restrict__ dy, const float* __restrict__ a,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      const float* __restrict__ W, const float* __restrict__ resid,
                                                      float* __restrict__ da, float* __restrict__ dW, float* __restrict__ db,
@@ -340,17 +364,17 @@ __global__ void __launch_bounds__(kTT, 1) linear_bwd(const float* __restrict__ d
     float* accW = bs + C;              // [(i*4+k)][lane]
     float* accv = accW + C * C;        // db | dgamma | dbeta
     float* scr = accv + 3 * C;         // [warp][kScrLin]
-    float* SA = scr + kWarps * kScrLin;  // dy  [o][v]
-    float* SB = SA + C * kRS;          // n(a) [c][v]
+    float* SA = scr + kLWarps * kScrLin;  // dy  [o][v]
+    float* SB = SA + C * kLRS;          // n(a) [c][v]
     const int tid = threadIdx.x, lane = tid & 31;
     float* scr_w = scr + (tid >> 5) * kScrLin;
-    for (int i = tid; i < C * C; i += kTT) { Ws[i] = W[i]; accW[i] = 0.f; }
-    for (int c = tid; c < C; c += kTT) { gs[c] = gamma ? gamma[c] : 1.f; bs[c] = beta ? beta[c] : 0.f; }
-    for (int c = tid; c < 3 * C; c += kTT) accv[c] = 0.f;
+    for (int i = tid; i < C * C; i += kLT) { Ws[i] = W[i]; accW[i] = 0.f; }
+    for (int c = tid; c < C; c += kLT) { gs[c] = gamma ? gamma[c] : 1.f; bs[c] = beta ? beta[c] : 0.f; }
+    for (int c = tid; c < 3 * C; c += kLT) accv[c] = 0.f;
     __syncthreads();
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const long long b = tile / tiles_per_sample;
-        const long long pv = (tile - b * tiles_per_sample) * kTT + tid;
+        const long long pv = (tile - b * tiles_per_sample) * kLT + tid;
         const bool valid = 2 * pv < vox;
         const long long base = b * C * vox + 2 * pv;
         f2 d0[C / 2], d1[C / 2];
@@ -359,7 +383,7 @@ __global__ void __launch_bounds__(kTT, 1) linear_bwd(const float* __restrict__ d
             f2 g[C];
             load_cols<C>(dy + base, vox, valid, g);
 #pragma unroll
-            for (int o = 0; o < C; ++o) *reinterpret_cast<f2*>(SA + o * kRS + 2 * tid) = g[o];
+            for (int o = 0; o < C; ++o) *reinterpret_cast<f2*>(SA + o * kLRS + 2 * tid) = g[o];
             {
                 float s[C];
 #pragma unroll
@@ -378,7 +402,7 @@ __global__ void __launch_bounds__(kTT, 1) linear_bwd(const float* __restrict__ d
             float sg[C], sb[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                *reinterpret_cast<f2*>(SB + c * kRS + 2 * tid) = make_float2(fmaf(av[c].x, gs[c], bs[c]), fmaf(av[c].y, gs[c], bs[c]));
+                *reinterpret_cast<f2*>(SB + c * kLRS + 2 * tid) = make_float2(fmaf(av[c].x, gs[c], bs[c]), fmaf(av[c].y, gs[c], bs[c]));
                 const f2 d = unpair<C>(d0, d1, c);
                 sg[c] = fmaf(d.x, av[c].x, d.y * av[c].y);
                 sb[c] = d.x + d.y;
@@ -403,30 +427,30 @@ __global__ void __launch_bounds__(kTT, 1) linear_bwd(const float* __restrict__ d
         } else {
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                *reinterpret_cast<f2*>(SB + c * kRS + 2 * tid) = av[c];
+                *reinterpret_cast<f2*>(SB + c * kLRS + 2 * tid) = av[c];
                 if (valid) *reinterpret_cast<f2*>(da + base + c * vox) = unpair<C>(d0, d1, c);
             }
         }
         __syncthreads();   // tile staged; the previous tile's scratch has been consumed
-        wgrad_32x32(SA, SB, scr_w, tid);
+        wgrad_32x32<kLV, kLWarps>(SA, SB, scr_w, tid);
         scr_w[C * C + lane] = r_db;
         scr_w[C * C + C + lane] = r_dg;
         scr_w[C * C + 2 * C + lane] = r_dbeta;
         __syncthreads();
-        for (int o = tid; o < kScrLin; o += kTT) {
+        for (int o = tid; o < kScrLin; o += kLT) {
             float t = 0.f;
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) t += scr[w * kScrLin + o];
+            for (int w = 0; w < kLWarps; ++w) t += scr[w * kScrLin + o];
             accW[o] += t;      // accv follows accW in shared memory
         }
     }
     __syncthreads();
     // accW[(i*4+k)*32 + lane] is dW[(lane&3) + 4i][(lane>>2) + 8k]
-    for (int i = tid; i < C * C; i += kTT) {
+    for (int i = tid; i < C * C; i += kLT) {
         const int e = i >> 5, l = i & 31;
         atomicAdd(dW + ((l & 3) + 4 * (e >> 2)) * C + (l >> 2) + 8 * (e & 3), accW[i]);
     }
-    for (int c = tid; c < C; c += kTT) {
+    for (int c = tid; c < C; c += kLT) {
         if (db) atomicAdd(db + c, accv[c]);
         if (LN && dgamma) atomicAdd(dgamma + c, accv[C + c]);
         if (LN && dbeta) atomicAdd(dbeta + c, accv[2 * C + c]);
@@ -619,7 +643,7 @@ int check_common(long long batch, int channels, long long voxels) {
 
 bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) != 0; }
 
-size_t linear_bwd_smem() { return sizeof(float) * (2 * kC * kC + 2 * kC + 3 * kC + kWarps * kScrLin + 2 * kC * kRS); }
+size_t linear_bwd_smem() { return sizeof(float) * (2 * kC * kC + 2 * kC + 3 * kC + kLWarps * kScrLin + 2 * kC * kLRS); }
 size_t mlp_fwd_smem(int hid) { return sizeof(float) * (kC * kC + 2 * kC * hid + hid + 4 * kC); }
 size_t mlp_bwd_smem(int hid) { return sizeof(float) * (5 * kC * hid + 2 * hid + 2 * kC + 3 * kC + kWarps * (kScrMlp + kScrMlpV) + (2 * kC + 16) * kRS); }
 
@@ -695,13 +719,13 @@ int fz_linear_backward(const float* dy, const float* a, const float* gamma, cons
         FZ_CUDA_CHECK(cudaFuncSetAttribute(linear_bwd<kC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    const int tps = (int)((voxels + kTV - 1) / kTV);
+    const int tps = (int)((voxels + kLV - 1) / kLV);
     const long long tiles = batch * tps;
-    const unsigned blocks = (unsigned)(tiles < sm_count() ? tiles : sm_count());
+    const unsigned blocks = (unsigned)(tiles < 2LL * sm_count() ? tiles : 2LL * sm_count());
     if (layernorm)
-        linear_bwd<kC, true><<<blocks, kTT, smem, st>>>(dy, a, gamma, beta, W, resid, da, dW, db, dgamma, dbeta, voxels, tps, tiles, eps);
+        linear_bwd<kC, true><<<blocks, kLT, smem, st>>>(dy, a, gamma, beta, W, resid, da, dW, db, dgamma, dbeta, voxels, tps, tiles, eps);
     else
-        linear_bwd<kC, false><<<blocks, kTT, smem, st>>>(dy, a, nullptr, nullptr, W, nullptr, da, dW, db, nullptr, nullptr, voxels, tps, tiles, eps);
+        linear_bwd<kC, false><<<blocks, kLT, smem, st>>>(dy, a, nullptr, nullptr, W, nullptr, da, dW, db, nullptr, nullptr, voxels, tps, tiles, eps);
     FZ_LAUNCH_CHECK();
     return FZ_OK;
 }
