@@ -378,3 +378,99 @@ def hals_r1_gram(x, v0, gy, num_iters=5, num_grad_steps=None, eps=EPS):
         m += rd[:, None] * eps * ab
     dx = dx + np.einsum("nij,njk->nik", Mm, x) + m[:, :, None]
     return y, dx.astype(x.dtype)
+
+
+# ----------------------------------------------------------------------------------------------
+# FactorizerBlock glue around the core (factorizer/factorizer.py:34-57, 74-77): channels-first
+# LayerNorm (layers/norm.py:29-34), pointwise Linear = Conv1d k=1 (layers/linear.py:53-58),
+# MLP = Linear -> exact GELU -> Linear (layers/mlp.py:54-60).  Forward and hand-derived backward,
+# pinned against the reference's autograd by tests/test_oracle.py (golden block.npz).
+# ----------------------------------------------------------------------------------------------
+def _erf(a):
+    return np.vectorize(math.erf, otypes=[np.float64])(a).astype(a.dtype)
+
+
+def layernorm_cf(x, gamma, beta, eps=1e-5):
+    """LayerNorm over axis 1 of (B, C, V): biased variance, eps inside the root.  Returns (y, xhat, rstd)."""
+    mean = x.mean(axis=1, keepdims=True)
+    var = ((x - mean) ** 2).mean(axis=1, keepdims=True)
+    rstd = 1.0 / np.sqrt(var + x.dtype.type(eps))
+    xhat = (x - mean) * rstd
+    return xhat * gamma[None, :, None] + beta[None, :, None], xhat, rstd
+
+
+def layernorm_cf_backward(dy, xhat, rstd, gamma):
+    t = dy * gamma[None, :, None]
+    dx = rstd * (t - t.mean(axis=1, keepdims=True) - xhat * (t * xhat).mean(axis=1, keepdims=True))
+    return dx, (dy * xhat).sum(axis=(0, 2)), dy.sum(axis=(0, 2))
+
+
+def linear_cf(x, W, b=None):
+    y = np.einsum("oc,bcv->bov", W, x)
+    return y if b is None else y + b[None, :, None]
+
+
+def gelu(h):
+    return 0.5 * h * (1.0 + _erf(h * h.dtype.type(1.0 / math.sqrt(2.0))))
+
+
+def gelu_grad(h):
+    cdf = 0.5 * (1.0 + _erf(h * h.dtype.type(1.0 / math.sqrt(2.0))))
+    return cdf + h * np.exp(-0.5 * h * h) * h.dtype.type(1.0 / math.sqrt(2.0 * math.pi))
+
+
+def _block_params(sd, dtype):
+    g = lambda k: np.asarray(sd[k], dtype=dtype)
+    sq = lambda k: g(k)[:, :, 0]
+    return dict(g1=g("norm1.norm.weight"), b1=g("norm1.norm.bias"), win=sq("fact.in_proj.linear.weight"),
+                wout=sq("fact.out_proj.linear.weight"), bout=g("fact.out_proj.linear.bias"),
+                g2=g("norm2.norm.weight"), b2=g("norm2.norm.bias"), w1=sq("mlp.block.0.linear.weight"),
+                bb1=g("mlp.block.0.linear.bias"), w2=sq("mlp.block.3.linear.weight"), bb2=g("mlp.block.3.linear.bias"),
+                u0=g("fact.factorize.init.u0"), v0=g("fact.factorize.init.v0"))
+
+
+def block_forward(x, sd, H, d, grid, patch, shifts, num_iters=5, eps_ln=1e-5, keep=False):
+    """FactorizerBlock.forward with norm = LayerNorm, act = ReLU, HALS NMF, no dropout.
+    ``sd``: the block's state_dict as numpy arrays (reference parameter names)."""
+    p = _block_params(sd, x.dtype)
+    shape = x.shape
+    xf = x.reshape(shape[0], shape[1], -1)
+    n1, xh1, r1 = layernorm_cf(xf, p["g1"], p["b1"], eps_ln)
+    z = linear_cf(n1, p["win"])
+    m = swnmf_forward(np.ascontiguousarray(z.reshape(shape)), p["u0"], p["v0"], H, d, grid, patch, shifts,
+                      relu=True, solver="hals", num_iters=num_iters).reshape(xf.shape)
+    x1 = xf + linear_cf(m, p["wout"], p["bout"])
+    n2, xh2, r2 = layernorm_cf(x1, p["g2"], p["b2"], eps_ln)
+    h = linear_cf(n2, p["w1"], p["bb1"])
+    a = gelu(h)
+    out = x1 + linear_cf(a, p["w2"], p["bb2"])
+    if keep:
+        return out.reshape(shape), dict(p=p, xh1=xh1, r1=r1, n1=n1, z=z, m=m, xh2=xh2, r2=r2, n2=n2, h=h, a=a)
+    return out.reshape(shape)
+
+
+def block_backward(x, dout, sd, H, d, grid, patch, shifts, num_iters=5, eps_ln=1e-5):
+    """Gradients of <dout, block_forward(x)> w.r.t. x and every parameter (reference parameter names)."""
+    shape = x.shape
+    _, c = block_forward(x, sd, H, d, grid, patch, shifts, num_iters, eps_ln, keep=True)
+    p = c["p"]
+    do = dout.reshape(shape[0], shape[1], -1)
+    grads = {}
+    grads["mlp.block.3.linear.weight"] = np.einsum("bov,bjv->oj", do, c["a"])[:, :, None]
+    grads["mlp.block.3.linear.bias"] = do.sum(axis=(0, 2))
+    dh = np.einsum("oj,bov->bjv", p["w2"], do) * gelu_grad(c["h"])
+    grads["mlp.block.0.linear.weight"] = np.einsum("bjv,bcv->jc", dh, c["n2"])[:, :, None]
+    grads["mlp.block.0.linear.bias"] = dh.sum(axis=(0, 2))
+    dn2 = np.einsum("jc,bjv->bcv", p["w1"], dh)
+    dx1, grads["norm2.norm.weight"], grads["norm2.norm.bias"] = layernorm_cf_backward(dn2, c["xh2"], c["r2"], p["g2"])
+    dx1 = dx1 + do
+    grads["fact.out_proj.linear.weight"] = np.einsum("bov,bcv->oc", dx1, c["m"])[:, :, None]
+    grads["fact.out_proj.linear.bias"] = dx1.sum(axis=(0, 2))
+    dm = np.einsum("oc,bov->bcv", p["wout"], dx1)
+    dz = swnmf_backward(np.ascontiguousarray(c["z"].reshape(shape)), np.ascontiguousarray(dm.reshape(shape)), p["u0"],
+                        p["v0"], H, d, grid, patch, shifts, relu=True, solver="hals",
+                        num_iters=num_iters).reshape(do.shape)
+    grads["fact.in_proj.linear.weight"] = np.einsum("bov,bcv->oc", dz, c["n1"])[:, :, None]
+    dn1 = np.einsum("oc,bov->bcv", p["win"], dz)
+    dx, grads["norm1.norm.weight"], grads["norm1.norm.bias"] = layernorm_cf_backward(dn1, c["xh1"], c["r1"], p["g1"])
+    return (dx + dx1).reshape(shape), grads

@@ -144,3 +144,25 @@ def test_gram_form_is_well_conditioned(golden, name):
     assert_close(dx, gr, what="gx")
     assert tol_ratio(y, y64) <= tol_ratio(yr, y64) + 0.02
     assert tol_ratio(dx, gx64) <= tol_ratio(gr, gx64) + 0.05
+
+
+@pytest.mark.parametrize("name", list(cases.BLOCK_CASES))
+def test_oracle_block_matches_reference(golden, name):
+    """FactorizerBlock glue of the oracle (LayerNorm / Linear / GELU MLP / residuals around the core), forward
+    and hand-derived backward, against the reference's own forward + autograd (block.npz); fp64 arithmetic
+    on the fp32 inputs, so the bound is the reference's fp32 rounding."""
+    c, g = cases.BLOCK_CASES[name], golden["block"]
+    sd = {k.split("/sd/")[1]: g[k].astype(np.float64) for k in g.files if k.startswith(name + "/sd/")}
+    xs = (c["batch"], c["channels"], *c["spatial"])
+    x = cases.make_array(name, xs, "randn").astype(np.float64)
+    gy = cases.make_array(name, xs, "randn", tag="gy").astype(np.float64)
+    H, d, grid, patch = O.resolve_geometry((None, *xs[1:]), **c["kw"])
+    shifts = O.normalise_shifts(O.default_shifts(patch), len(patch))
+    y = O.block_forward(x, sd, H, d, grid, patch, shifts)
+    gx, gp = O.block_backward(x, gy, sd, H, d, grid, patch, shifts)
+    assert_close(y, g[f"{name}/y"], what="y")
+    assert_close(gx, g[f"{name}/gx"], what="gx")
+    for k, v in gp.items():
+        ref = g[f"{name}/gp/{k}"]
+        scale = max(1.0, float(np.abs(ref).max()))
+        assert_close(v / scale, ref / scale, rtol=1e-4, atol=1e-4, what=f"grad {k}")
