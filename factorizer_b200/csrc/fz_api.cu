@@ -77,6 +77,10 @@ int fz_nmf_forward(const float* x, const float* u0, const float* v0, float* u, f
     if (int e = check_solver(s, M, N, &K)) return e;
     if (n < 0) return fail(FZ_ERR_INVALID, "n=%lld < 0", (long long)n);
     if (!x || !u0 || !v0) return fail(FZ_ERR_INVALID, "null input buffer");
+    if (g_forced_path != 0 && y && !u && !v && small_supported(M, N, *s)) {
+        tls().path = 3;
+        return small_direct(x, u0, v0, nullptr, y, n, M, N, *s, K, false, (cudaStream_t)stream);
+    }
     NmfArgs a;
     memset(&a, 0, sizeof(a));
     a.x = x; a.u0 = u0; a.v0 = v0; a.u = u; a.v = v; a.y = y;
@@ -93,6 +97,10 @@ int fz_nmf_backward(const float* x, const float* u0, const float* v0, const floa
     if (int e = check_solver(s, M, N, &K)) return e;
     if (n < 0) return fail(FZ_ERR_INVALID, "n=%lld < 0", (long long)n);
     if (!x || !u0 || !v0 || !gx) return fail(FZ_ERR_INVALID, "null buffer");
+    if (g_forced_path != 0 && gy && !gu && !gv && small_supported(M, N, *s)) {
+        tls().path = 3;
+        return small_direct(x, u0, v0, gy, gx, n, M, N, *s, K, true, (cudaStream_t)stream);
+    }
     NmfArgs a;
     memset(&a, 0, sizeof(a));
     a.x = x; a.u0 = u0; a.v0 = v0; a.gy = gy; a.gu = gu; a.gv = gv; a.gx = gx;
@@ -134,6 +142,10 @@ int fz_swnmf_forward(const float* x, const float* u0, const float* v0, float* y,
         tls().path = 1;
         return fast_forward(x, u0, v0, y, saved, workspace, G, *s, relu_input, (cudaStream_t)stream);
     }
+    if (g_forced_path != 0 && small_window_supported(G, *s)) {
+        tls().path = 3;
+        return small_window(x, u0, v0, nullptr, y, G, *s, K, relu_input, false, (cudaStream_t)stream);
+    }
     tls().path = 0;
     NmfArgs a;
     memset(&a, 0, sizeof(a));
@@ -160,6 +172,10 @@ int fz_swnmf_backward(const float* x, const float* gy, const float* u0, const fl
         tls().path = 1;
         return fast_backward(x, gy, u0, v0, saved, gx, workspace, G, *s, K, relu_input,
                              (cudaStream_t)stream);
+    }
+    if (g_forced_path != 0 && small_window_supported(G, *s)) {
+        tls().path = 3;
+        return small_window(x, u0, v0, gy, gx, G, *s, K, relu_input, true, (cudaStream_t)stream);
     }
     tls().path = 0;
     NmfArgs a;

@@ -41,6 +41,14 @@ int fast_backward(const float* x, const float* gy, const float* u0, const float*
                   const void* saved, float* gx, void* workspace, const DevGeom& G,
                   const fz_solver& s, int K, int relu, cudaStream_t st);
 
+// fz_swnmf_small.cu: rank-1 HALS / MU on small matrices (N = 64 with M = 4, 8, 16, 32; 8x16, 8x128, 8x256), a sub-warp each
+bool small_supported(int M, int N, const fz_solver& s);
+bool small_window_supported(const DevGeom& G, const fz_solver& s);
+int small_direct(const float* x, const float* u0, const float* v0, const float* gy, float* out, long long n, int M, int N,
+                 const fz_solver& s, int K, bool bwd, cudaStream_t st);
+int small_window(const float* x, const float* u0, const float* v0, const float* gy, float* out, const DevGeom& G,
+                 const fz_solver& s, int K, int relu, bool bwd, cudaStream_t st);
+
 // fz_swnmf_phase.cu: three-pass "octant" formulation for [unshifted, shifted by patch/2], act = ReLU
 bool phase_supported(const DevGeom& G, const fz_solver& s, int relu);
 void phase_set_pass_mask(int mask);

@@ -1,0 +1,521 @@
+// Rank-1 NMF (HALS or MU) on SMALL matrices, a sub-warp per matrix, everything in registers.
+//
+// Serves the window geometries of the reference's model-zoo bundles and tests whose matrices are tiny
+// (patch 4x4x4 or 8x8 -> 64 columns; head_dim 4..32: model_zoo/factorizer_isles22/configs/train.yaml:49-53,
+// tests/test_factorizer.py:112-165) and ft.NMF on small pre-matricised batches.  The generic kernels
+// (fz_nmf_generic.cu) give such a matrix a whole CTA and a dozen block barriers per sweep; here L lanes of a warp
+// own one M x N matrix (N = L * CPL columns, column j lives in lane j % L), hold it in M*CPL = 64 registers per
+// lane, and run the reference's updates literally (no Gram reformulation, so any act / sign of X works):
+//   HALS  u <- relu((X v + eps) / (v.v + eps)),  v <- relu((X^T u + eps) / (u.u + eps))
+//         (factorizer/factorization/matrix_factorization.py:210-229 with R = 1, project = ReLU :609)
+//   MU    u <- (u . X v + eps) / (u (v.v) + eps), v likewise                                  (:241-247)
+// X v needs one sub-warp all-reduce of M values per sweep; X^T u is lane-local.  The backward recomputes the
+// iterates (u_t, v_t parked in shared memory, T <= 5) and runs the hand-derived adjoint of the unrolled loop (same
+// math as oracle/factorizer_oracle.py::_half_bwd), truncated to the last K sweeps (num_grad_steps, :506-512).
+// Window mode gathers straight from the NCDHW volume with the roll folded into the index math
+// (operations.py:266-272) and accumulates the window sets in shift order, the last one dividing by S
+// (operations.py:426-433); consecutive sub-warps take windows that are neighbours along W, so a warp-wide
+// load still covers whole 32-byte sectors.  Division is reciprocal (MUFU + one Newton step) times numerator,
+// <= 1 ulp from the reference's true division (same deviation as the 8x512 kernels).
+#include "fz_common.cuh"
+#include "fz_internal.cuh"
+
+namespace fz {
+namespace {
+
+constexpr int kTMax = 5;          // iterates kept (in shared memory) by the backward
+constexpr int kSmallThreads = 128;
+
+struct SmallParams {
+    const float* x;       // window mode: volume; direct mode: (n, M, N)
+    const float* gy;      // backward: dL/dy, same layout as x
+    float* out;           // forward: y; backward: dL/dx
+    const float* u0;      // (M)
+    const float* v0;      // (N)
+    long long n;          // matrices in this launch (windows of ONE set in window mode)
+    int T, K, kind, relu, set, S, window;
+    float eps;
+    DevGeom G;
+};
+
+__device__ __forceinline__ float rcp_nr(float d) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    return fmaf(r, fmaf(-d, r, 1.f), r);
+}
+
+template <int L>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// element offsets (relative to the (batch, head) base) of this lane's CPL columns of matrix `mid`
+template <int M, int CPL, int L>
+struct Locator {
+    int rel[CPL];     // offset of column k*L + lane relative to the window origin (no wrap)
+    int q[CPL];       // its (q0, q1, q2) packed 10 bits each
+    __device__ __forceinline__ void init(const SmallParams& P, int lane) {
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+            const int j = k * L + lane;
+            if (P.window) {
+                const int q2 = j % P.G.p[2];
+                const int t = j / P.G.p[2];
+                const int q1 = t % P.G.p[1], q0 = t / P.G.p[1];
+                rel[k] = (q0 * P.G.n[1] + q1) * P.G.n[2] + q2;
+                q[k] = q0 | (q1 << 10) | (q2 << 20);
+            } else {
+                rel[k] = j;
+                q[k] = 0;
+            }
+        }
+    }
+    // returns the base offset (channel row 0) and fills off[]
+    __device__ __forceinline__ long long locate(const SmallParams& P, long long mid, int (&off)[CPL]) const {
+        if (!P.window) {
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) off[k] = rel[k];
+            return mid * (long long)(M * CPL * L);
+        }
+        const DevGeom& G = P.G;
+        const int w = (int)(mid % G.G);
+        const long long t = mid / G.G;
+        const int h = (int)(t % G.heads), b = (int)(t / G.heads);
+        const int g2 = w % G.g[2];
+        const int tt = w / G.g[2];
+        const int g1 = tt % G.g[1], g0 = tt / G.g[1];
+        const int o0 = g0 * G.p[0] - G.sh[P.set][0], o1 = g1 * G.p[1] - G.sh[P.set][1], o2 = g2 * G.p[2] - G.sh[P.set][2];
+        if ((o0 | o1 | o2) >= 0) {
+            const int org = (o0 * G.n[1] + o1) * G.n[2] + o2;
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) off[k] = org + rel[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                int i0 = o0 + (q[k] & 1023), i1 = o1 + ((q[k] >> 10) & 1023), i2 = o2 + (q[k] >> 20);
+                if (i0 < 0) i0 += G.n[0];
+                if (i1 < 0) i1 += G.n[1];
+                if (i2 < 0) i2 += G.n[2];
+                off[k] = (i0 * G.n[1] + i1) * G.n[2] + i2;
+            }
+        }
+        return ((long long)b * G.C + (long long)h * G.d) * G.vox;
+    }
+};
+
+// one half-step for the M side: a = X v (all-reduced), b = v.v;  u <- update
+template <int M, int CPL, int L>
+__device__ __forceinline__ void step_u(const float (&x)[M][CPL], const float (&v)[CPL], float (&u)[M], float (&a)[M], float& b,
+                                       int kind, float eps) {
+    float bb = 0.f;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) bb = fmaf(v[k], v[k], bb);
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) s = fmaf(x[i][k], v[k], s);
+        a[i] = s;
+    }
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) {
+        bb += __shfl_xor_sync(0xffffffffu, bb, o);
+#pragma unroll
+        for (int i = 0; i < M; ++i) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+    }
+    b = bb;
+    if (kind == FZ_SOLVER_HALS) {
+        const float r = rcp_nr(bb + eps);
+#pragma unroll
+        for (int i = 0; i < M; ++i) u[i] = fmaxf((a[i] + eps) * r, 0.f);
+    } else {
+#pragma unroll
+        for (int i = 0; i < M; ++i) u[i] = fmaf(u[i], a[i], eps) * rcp_nr(fmaf(u[i], bb, eps));
+    }
+}
+
+// ... and for the N side: c = X^T u (lane-local), d = u.u;  v <- update
+template <int M, int CPL>
+__device__ __forceinline__ void step_v(const float (&x)[M][CPL], const float (&u)[M], float (&v)[CPL], float (&c)[CPL], float& d,
+                                       int kind, float eps) {
+    float dd = 0.f;
+#pragma unroll
+    for (int i = 0; i < M; ++i) dd = fmaf(u[i], u[i], dd);
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < M; ++i) s = fmaf(x[i][k], u[i], s);
+        c[k] = s;
+    }
+    d = dd;
+    if (kind == FZ_SOLVER_HALS) {
+        const float r = rcp_nr(dd + eps);
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) v[k] = fmaxf((c[k] + eps) * r, 0.f);
+    } else {
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) v[k] = fmaf(v[k], c[k], eps) * rcp_nr(fmaf(v[k], dd, eps));
+    }
+}
+
+template <int M, int CPL, int L>
+__global__ void __launch_bounds__(kSmallThreads) small_fwd(const SmallParams P) {
+    const int lane = threadIdx.x & (L - 1);
+    const long long groups = (long long)gridDim.x * (kSmallThreads / L);
+    const long long g0 = ((long long)blockIdx.x * kSmallThreads + threadIdx.x) / L;
+    Locator<M, CPL, L> loc;
+    loc.init(P, lane);
+    float u0r[M], v0r[CPL];
+#pragma unroll
+    for (int i = 0; i < M; ++i) u0r[i] = __ldg(P.u0 + i);
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) v0r[k] = __ldg(P.v0 + k * L + lane);
+    const long long stride = P.window ? P.G.vox : (long long)CPL * L;
+    for (long long first = 0; first < P.n; first += groups) {      // trip count is uniform across the warp
+        const long long mid = first + g0;
+        const bool valid = mid < P.n;
+        int off[CPL];
+        const long long base = loc.locate(P, valid ? mid : 0, off);
+        float x[M][CPL];
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                float t = valid ? __ldg(P.x + base + i * stride + off[k]) : 0.f;
+                x[i][k] = P.relu ? fmaxf(t, 0.f) : t;
+            }
+        float u[M], v[CPL], a[M], c[CPL], b, d;
+#pragma unroll
+        for (int i = 0; i < M; ++i) u[i] = u0r[i];
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) v[k] = v0r[k];
+        for (int t = 0; t < P.T; ++t) {
+            step_u<M, CPL, L>(x, v, u, a, b, P.kind, P.eps);
+            step_v<M, CPL>(x, u, v, c, d, P.kind, P.eps);
+        }
+        if (valid) {
+            const bool add = P.window && P.set > 0, last = P.window && P.set == P.S - 1 && P.S > 1;
+            const float fs = (float)P.S;
+#pragma unroll
+            for (int i = 0; i < M; ++i)
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) {
+                    float* dst = P.out + base + i * stride + off[k];
+                    float y = u[i] * v[k];
+                    if (add) y = __fadd_rn(*dst, y);
+                    if (last) y = __fdiv_rn(y, fs);
+                    *dst = y;
+                }
+        }
+    }
+}
+
+// floats of history per sub-warp: (T_max + 1) x (M + N), padded so that the sub-warps of a warp start L banks apart
+template <int M, int CPL, int L>
+struct Hist {
+    static constexpr int raw = (kTMax + 1) * (M + CPL * L);
+    static constexpr int floats = L < 32 ? raw + ((L - raw % 32) + 32) % 32 : raw;
+};
+
+template <int M, int CPL, int L>
+__global__ void __launch_bounds__(kSmallThreads) small_bwd(const SmallParams P) {
+    extern __shared__ float hist_all[];
+    constexpr int kHS = M + CPL * L;
+    float* hist = hist_all + (threadIdx.x / L) * Hist<M, CPL, L>::floats;
+    const int lane = threadIdx.x & (L - 1);
+    const long long groups = (long long)gridDim.x * (kSmallThreads / L);
+    const long long g0 = ((long long)blockIdx.x * kSmallThreads + threadIdx.x) / L;
+    Locator<M, CPL, L> loc;
+    loc.init(P, lane);
+    float u0r[M], v0r[CPL];
+#pragma unroll
+    for (int i = 0; i < M; ++i) u0r[i] = __ldg(P.u0 + i);
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) v0r[k] = __ldg(P.v0 + k * L + lane);
+    const long long stride = P.window ? P.G.vox : (long long)CPL * L;
+    const float eps = P.eps;
+    const int T = P.T, K = P.K;
+    for (long long first = 0; first < P.n; first += groups) {
+        const long long mid = first + g0;
+        const bool valid = mid < P.n;
+        int off[CPL];
+        const long long base = loc.locate(P, valid ? mid : 0, off);
+        float x[M][CPL];
+        unsigned long long mask = 0;       // x > 0 before the ReLU (M*CPL = 64 bits)
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                float t = valid ? __ldg(P.x + base + i * stride + off[k]) : 0.f;
+                if (P.relu) {
+                    if (t > 0.f) mask |= 1ULL << (i * CPL + k);
+                    t = fmaxf(t, 0.f);
+                }
+                x[i][k] = t;
+            }
+        // ---- recompute the iterates; u_t, v_t (t = 0..T) go to this sub-warp's slice of shared memory ----
+        {
+            float u[M], v[CPL];
+#pragma unroll
+            for (int i = 0; i < M; ++i) u[i] = u0r[i];
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) v[k] = v0r[k];
+            __syncwarp();                      // the previous matrix's history is no longer read
+            for (int t = 0;; ++t) {
+                if (lane == 0) {
+#pragma unroll
+                    for (int i = 0; i < M; ++i) hist[t * kHS + i] = u[i];
+                }
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) hist[t * kHS + M + k * L + lane] = v[k];
+                if (t == T) break;
+                float a[M], c[CPL], b, d;
+                step_u<M, CPL, L>(x, v, u, a, b, P.kind, eps);
+                step_v<M, CPL>(x, u, v, c, d, P.kind, eps);
+            }
+            __syncwarp();
+        }
+        // ---- seed: y = u_T v_T^T ----
+        float xb[M][CPL];                  // dL/dx accumulator; first holds dL/dy
+        const float invS = P.window ? __fdiv_rn(1.f, (float)P.S) : 1.f;
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                const float g = valid ? __ldg(P.gy + base + i * stride + off[k]) : 0.f;
+                xb[i][k] = P.window ? __fdiv_rn(g, (float)P.S) : g;
+            }
+        (void)invS;
+        float ub[M], vb[CPL];
+#pragma unroll
+        for (int t = kTMax; t >= 1; --t) {
+            if (t == T) {
+#pragma unroll
+                for (int i = 0; i < M; ++i) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int k = 0; k < CPL; ++k) s = fmaf(xb[i][k], hist[t * kHS + M + k * L + lane], s);
+                    ub[i] = group_sum<L>(s);
+                }
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int i = 0; i < M; ++i) s = fmaf(xb[i][k], hist[t * kHS + i], s);
+                    vb[k] = s;
+                }
+#pragma unroll
+                for (int i = 0; i < M; ++i)
+#pragma unroll
+                    for (int k = 0; k < CPL; ++k) xb[i][k] = 0.f;
+            }
+            if (t <= T && t > T - K) {
+                float ut[M], up[M], vt[CPL], vp[CPL];
+#pragma unroll
+                for (int i = 0; i < M; ++i) { ut[i] = hist[t * kHS + i]; up[i] = hist[(t - 1) * kHS + i]; }
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) { vt[k] = hist[t * kHS + M + k * L + lane]; vp[k] = hist[(t - 1) * kHS + M + k * L + lane]; }
+                // ---- adjoint of the v half-step ----
+                float d = 0.f;
+#pragma unroll
+                for (int i = 0; i < M; ++i) d = fmaf(ut[i], ut[i], d);
+                float cb[CPL], dbar = 0.f;
+                if (P.kind == FZ_SOLVER_HALS) {
+                    const float rd = rcp_nr(d + eps);
+#pragma unroll
+                    for (int k = 0; k < CPL; ++k) {
+                        const float qb = vt[k] > 0.f ? vb[k] : 0.f;
+                        cb[k] = qb * rd;
+                        dbar = fmaf(qb, vt[k], dbar);
+                        vb[k] = 0.f;                       // v_{t-1} enters only through the u half-step
+                    }
+                    dbar = -rd * group_sum<L>(dbar);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < CPL; ++k) {
+                        float c = 0.f;
+#pragma unroll
+                        for (int i = 0; i < M; ++i) c = fmaf(x[i][k], ut[i], c);
+                        const float rden = rcp_nr(fmaf(vp[k], d, eps));
+                        const float nb = vb[k] * rden, db = -nb * vt[k];
+                        cb[k] = nb * vp[k];
+                        dbar = fmaf(db, vp[k], dbar);
+                        vb[k] = fmaf(nb, c, db * d);
+                    }
+                    dbar = group_sum<L>(dbar);
+                }
+                float un[M];                               // dL/du_t
+#pragma unroll
+                for (int i = 0; i < M; ++i) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int k = 0; k < CPL; ++k) { s = fmaf(x[i][k], cb[k], s); xb[i][k] = fmaf(ut[i], cb[k], xb[i][k]); }
+                    un[i] = s;
+                }
+#pragma unroll
+                for (int o = L / 2; o > 0; o >>= 1)
+#pragma unroll
+                    for (int i = 0; i < M; ++i) un[i] += __shfl_xor_sync(0xffffffffu, un[i], o);
+#pragma unroll
+                for (int i = 0; i < M; ++i) un[i] = ub[i] + fmaf(2.f * dbar, ut[i], un[i]);
+                // ---- adjoint of the u half-step ----
+                float b = 0.f;
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) b = fmaf(vp[k], vp[k], b);
+                b = group_sum<L>(b);
+                float ab[M], bbar = 0.f;
+                if (P.kind == FZ_SOLVER_HALS) {
+                    const float rb = rcp_nr(b + eps);
+#pragma unroll
+                    for (int i = 0; i < M; ++i) {
+                        const float pb = ut[i] > 0.f ? un[i] : 0.f;
+                        ab[i] = pb * rb;
+                        bbar = fmaf(pb, ut[i], bbar);
+                        ub[i] = 0.f;
+                    }
+                    bbar *= -rb;
+                } else {
+                    float a[M];
+#pragma unroll
+                    for (int i = 0; i < M; ++i) {
+                        float s = 0.f;
+#pragma unroll
+                        for (int k = 0; k < CPL; ++k) s = fmaf(x[i][k], vp[k], s);
+                        a[i] = s;
+                    }
+#pragma unroll
+                    for (int o = L / 2; o > 0; o >>= 1)
+#pragma unroll
+                        for (int i = 0; i < M; ++i) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+#pragma unroll
+                    for (int i = 0; i < M; ++i) {
+                        const float rden = rcp_nr(fmaf(up[i], b, eps));
+                        const float nb = un[i] * rden, db = -nb * ut[i];
+                        ab[i] = nb * up[i];
+                        bbar = fmaf(db, up[i], bbar);
+                        ub[i] = fmaf(nb, a[i], db * b);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int i = 0; i < M; ++i) { s = fmaf(x[i][k], ab[i], s); xb[i][k] = fmaf(ab[i], vp[k], xb[i][k]); }
+                    vb[k] += fmaf(2.f * bbar, vp[k], s);
+                }
+            }
+        }
+        if (valid) {
+            const bool add = P.window && P.set > 0;
+#pragma unroll
+            for (int i = 0; i < M; ++i)
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) {
+                    float* dst = P.out + base + i * stride + off[k];
+                    float g = xb[i][k];
+                    if (P.relu && !((mask >> (i * CPL + k)) & 1ULL)) g = 0.f;
+                    if (add) g = __fadd_rn(*dst, g);
+                    *dst = g;
+                }
+        }
+    }
+}
+
+int small_sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+template <int M, int CPL, int L>
+int launch_small(const SmallParams& P, bool bwd, cudaStream_t st) {
+    const long long per_cta = kSmallThreads / L;
+    long long ctas = (P.n + per_cta - 1) / per_cta;
+    const long long cap = 8LL * small_sm_count();
+    if (ctas > cap) ctas = cap;
+    if (bwd) {
+        const size_t smem = sizeof(float) * Hist<M, CPL, L>::floats * (kSmallThreads / L);
+        static bool configured = false;
+        if (!configured) {
+            FZ_CUDA_CHECK(cudaFuncSetAttribute(small_bwd<M, CPL, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+        small_bwd<M, CPL, L><<<(unsigned)ctas, kSmallThreads, smem, st>>>(P);
+    } else {
+        small_fwd<M, CPL, L><<<(unsigned)ctas, kSmallThreads, 0, st>>>(P);
+    }
+    FZ_LAUNCH_CHECK();
+    return FZ_OK;
+}
+
+int dispatch_small(const SmallParams& P, int M, int N, bool bwd, cudaStream_t st) {
+    if (N == 64) {
+        switch (M) {
+            case 4: return launch_small<4, 16, 4>(P, bwd, st);
+            case 8: return launch_small<8, 8, 8>(P, bwd, st);
+            case 16: return launch_small<16, 4, 16>(P, bwd, st);
+            case 32: return launch_small<32, 2, 32>(P, bwd, st);
+        }
+    }
+    if (N == 128 && M == 8) return launch_small<8, 8, 16>(P, bwd, st);
+    if (N == 256 && M == 8) return launch_small<8, 8, 32>(P, bwd, st);
+    if (N == 16 && M == 8) return launch_small<8, 4, 4>(P, bwd, st);
+    return fail(FZ_ERR_UNSUPPORTED, "no small-matrix kernel for %dx%d", M, N);
+}
+
+}  // namespace
+
+bool small_supported(int M, int N, const fz_solver& s) {
+    if (s.rank != 1 || s.num_iters < 1 || s.num_iters > kTMax) return false;
+    if (s.kind != FZ_SOLVER_HALS && s.kind != FZ_SOLVER_MU) return false;
+    if (N == 64) return M == 4 || M == 8 || M == 16 || M == 32;
+    return M == 8 && (N == 128 || N == 256 || N == 16);
+}
+
+bool small_window_supported(const DevGeom& G, const fz_solver& s) {
+    if (!small_supported(G.d, G.P, s)) return false;
+    for (int k = 0; k < 3; ++k)
+        if (G.p[k] > 1023 || G.n[k] > (1 << 20)) return false;
+    return G.mats_per_shift > 0;
+}
+
+int small_direct(const float* x, const float* u0, const float* v0, const float* gy, float* out, long long n, int M, int N,
+                 const fz_solver& s, int K, bool bwd, cudaStream_t st) {
+    SmallParams P;
+    memset(&P, 0, sizeof(P));
+    P.x = x; P.gy = gy; P.out = out; P.u0 = u0; P.v0 = v0; P.n = n;
+    P.T = s.num_iters; P.K = K; P.kind = s.kind; P.eps = s.eps; P.S = 1;
+    if (n == 0) return FZ_OK;
+    return dispatch_small(P, M, N, bwd, st);
+}
+
+int small_window(const float* x, const float* u0, const float* v0, const float* gy, float* out, const DevGeom& G,
+                 const fz_solver& s, int K, int relu, bool bwd, cudaStream_t st) {
+    SmallParams P;
+    memset(&P, 0, sizeof(P));
+    P.x = x; P.gy = gy; P.out = out; P.u0 = u0; P.v0 = v0; P.n = G.mats_per_shift;
+    P.T = s.num_iters; P.K = K; P.kind = s.kind; P.eps = s.eps; P.S = G.S; P.window = 1; P.relu = relu;
+    P.G = G;
+    for (int q = 0; q < G.S; ++q)       // torch.roll semantics: any integer shift, reduced to [0, n)
+        for (int k = 0; k < 3; ++k) {
+            int v = G.sh[q][k] % G.n[k];
+            if (v < 0) v += G.n[k];
+            P.G.sh[q][k] = v;
+        }
+    if (P.n == 0) return FZ_OK;
+    for (int q = 0; q < G.S; ++q) {
+        P.set = q;
+        if (int e = dispatch_small(P, G.d, G.P, bwd, st)) return e;
+    }
+    return FZ_OK;
+}
+
+}  // namespace fz

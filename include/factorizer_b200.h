@@ -167,7 +167,9 @@ int fz_linear_backward(const float* dy, const float* a, const float* gamma, cons
 /* Which implementation the last fz_swnmf_* call on this thread used: 0 = generic shared-memory
  * kernels, 1 = the window-at-a-time TMA/register kernels (8x512 windows, rank-1 HALS, any shifts),
  * 2 = the three-pass octant kernels (the same with shifts [0, patch/2] and ReLU: the default
- * Swin-Factorizer block).  For tests and the benchmark's bookkeeping. */
+ * Swin-Factorizer block), 3 = the sub-warp-per-matrix register kernels for small matrices (64 columns with
+ * 4..32 rows, 8x16, 8x128, 8x256; rank-1 HALS / MU, at most 5 sweeps; also used by fz_nmf_* when only y / dy
+ * are involved).  For tests and the benchmark's bookkeeping. */
 int fz_last_path(void);
 /* Number of kernel launches issued by the last fz_* call on this thread. */
 int fz_last_launches(void);

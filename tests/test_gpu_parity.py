@@ -141,6 +141,25 @@ def test_fused_core_matches_reference(ft, dev, golden, name, path):
     assert_close(_np(gx), g[f"{name}/gx"], what="gx")
 
 
+def test_kernel_path_selection(ft, dev, golden):
+    """Which kernel family serves which geometry (fz_last_path): 2 = three-pass octant kernels (default Swin
+    geometry), 1 = window-at-a-time 8x512 kernels (other shifts), 3 = sub-warp register kernels (64-column
+    windows of the isles22 bundle / reference tests, small ft.NMF batches), 0 = generic shared-memory kernels."""
+    from factorizer_b200 import _lib, _ops
+    lib = _lib.lib()
+    want = {"fused_cfg2_16": 2, "fused_brats_s4": 1, "fused_isles_s4": 3, "fused_nh8_ps4": 3, "fused_2d": 3,
+            "fused_mu_r2": 0, "fused_global_mu": 0}
+    for name, path in want.items():
+        c = cases.FUSED_CASES[name]
+        reshape, nmf = _fused_module(ft, c, golden["fused"], name, dev)
+        x = torch.from_numpy(cases.make_array(name, c["x_shape"], c["dist"])).to(dev)
+        _ops.SWNMF.apply(x, nmf.init.u0, nmf.init.v0, reshape._geom, nmf.solver_spec(), c["relu"])
+        assert lib.fz_last_path() == path, (name, lib.fz_last_path())
+    nmf = ft.NMF(size=(16, 64), rank=1, solver="mu").to(dev)
+    nmf(torch.rand(3, 16, 64, device=dev))
+    assert lib.fz_last_path() == 3
+
+
 @pytest.mark.parametrize("name", ["fused_cfg2_16", "fused_mu_r2"])
 def test_unfused_chain_equals_fused(ft, dev, golden, name):
     """reshape -> act -> factorize -> inverse through the standalone kernels agrees with the fused op."""
