@@ -4,8 +4,8 @@
 // (patch 4x4x4 or 8x8 -> 64 columns; head_dim 4..32: model_zoo/factorizer_isles22/configs/train.yaml:49-53,
 // tests/test_factorizer.py:112-165) and ft.NMF on small pre-matricised batches.  The generic kernels
 // (fz_nmf_generic.cu) give such a matrix a whole CTA and a dozen block barriers per sweep; here L lanes of a warp
-// own one M x N matrix (N = L * CPL columns, column j lives in lane j % L), hold it in M*CPL = 64 registers per
-// lane, and run the reference's updates literally (no Gram reformulation, so any act / sign of X works):
+// own one M x N matrix (N = L * CPL columns, column pair j/2 lives in lane (j/2) % L), hold it in M*CPL = 64 registers
+// per lane (float2 pairs, packed FFMA2), and run the reference's updates literally (no Gram reformulation, so any act / sign of X works):
 //   HALS  u <- relu((X v + eps) / (v.v + eps)),  v <- relu((X^T u + eps) / (u.u + eps))
 //         (factorizer/factorization/matrix_factorization.py:210-229 with R = 1, project = ReLU :609)
 //   MU    u <- (u . X v + eps) / (u (v.v) + eps), v likewise                                  (:241-247)
@@ -54,12 +54,12 @@ __device__ __forceinline__ float group_sum(float v) {
 // element offsets (relative to the (batch, head) base) of this lane's CPL columns of matrix `mid`
 template <int M, int CPL, int L>
 struct Locator {
-    int rel[CPL];     // offset of column k*L + lane relative to the window origin (no wrap)
+    int rel[CPL];     // offset of column 2 ((k >> 1) L + lane) + (k & 1) relative to the window origin (no wrap)
     int q[CPL];       // its (q0, q1, q2) packed 10 bits each
     __device__ __forceinline__ void init(const SmallParams& P, int lane) {
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
-            const int j = k * L + lane;
+            const int j = 2 * ((k >> 1) * L + lane) + (k & 1);
             if (P.window) {
                 const int q2 = j % P.G.p[2];
                 const int t = j / P.G.p[2];
@@ -105,19 +105,25 @@ struct Locator {
     }
 };
 
+typedef float2 f2;
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 dup(float a) { return make_float2(a, a); }
+
+// Columns come in pairs (float2, packed FFMA2): pair kp of a lane = columns 2 (kp L + lane), +1.
 // one half-step for the M side: a = X v (all-reduced), b = v.v;  u <- update
-template <int M, int CPL, int L>
-__device__ __forceinline__ void step_u(const float (&x)[M][CPL], const float (&v)[CPL], float (&u)[M], float (&a)[M], float& b,
+template <int M, int H, int L>
+__device__ __forceinline__ void step_u(const f2 (&x)[M][H], const f2 (&v)[H], float (&u)[M], float (&a)[M], float& b,
                                        int kind, float eps) {
-    float bb = 0.f;
+    f2 b2 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < CPL; ++k) bb = fmaf(v[k], v[k], bb);
+    for (int k = 0; k < H; ++k) b2 = fma2(v[k], v[k], b2);
+    float bb = b2.x + b2.y;
 #pragma unroll
     for (int i = 0; i < M; ++i) {
-        float s = 0.f;
+        f2 s = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < CPL; ++k) s = fmaf(x[i][k], v[k], s);
-        a[i] = s;
+        for (int k = 0; k < H; ++k) s = fma2(x[i][k], v[k], s);
+        a[i] = s.x + s.y;
     }
 #pragma unroll
     for (int o = L / 2; o > 0; o >>= 1) {
@@ -137,77 +143,93 @@ __device__ __forceinline__ void step_u(const float (&x)[M][CPL], const float (&v
 }
 
 // ... and for the N side: c = X^T u (lane-local), d = u.u;  v <- update
-template <int M, int CPL>
-__device__ __forceinline__ void step_v(const float (&x)[M][CPL], const float (&u)[M], float (&v)[CPL], float (&c)[CPL], float& d,
+template <int M, int H>
+__device__ __forceinline__ void step_v(const f2 (&x)[M][H], const float (&u)[M], f2 (&v)[H], f2 (&c)[H], float& d,
                                        int kind, float eps) {
     float dd = 0.f;
 #pragma unroll
     for (int i = 0; i < M; ++i) dd = fmaf(u[i], u[i], dd);
 #pragma unroll
-    for (int k = 0; k < CPL; ++k) {
-        float s = 0.f;
+    for (int k = 0; k < H; ++k) c[k] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < M; ++i) s = fmaf(x[i][k], u[i], s);
-        c[k] = s;
+    for (int i = 0; i < M; ++i) {
+        const f2 ui = dup(u[i]);
+#pragma unroll
+        for (int k = 0; k < H; ++k) c[k] = fma2(x[i][k], ui, c[k]);
     }
     d = dd;
     if (kind == FZ_SOLVER_HALS) {
         const float r = rcp_nr(dd + eps);
 #pragma unroll
-        for (int k = 0; k < CPL; ++k) v[k] = fmaxf((c[k] + eps) * r, 0.f);
+        for (int k = 0; k < H; ++k) v[k] = make_float2(fmaxf((c[k].x + eps) * r, 0.f), fmaxf((c[k].y + eps) * r, 0.f));
     } else {
 #pragma unroll
-        for (int k = 0; k < CPL; ++k) v[k] = fmaf(v[k], c[k], eps) * rcp_nr(fmaf(v[k], dd, eps));
+        for (int k = 0; k < H; ++k)
+            v[k] = make_float2(fmaf(v[k].x, c[k].x, eps) * rcp_nr(fmaf(v[k].x, dd, eps)),
+                               fmaf(v[k].y, c[k].y, eps) * rcp_nr(fmaf(v[k].y, dd, eps)));
     }
+}
+
+// x / S: exact multiplication when S is a power of two, true division otherwise (operations.py:433)
+__device__ __forceinline__ float div_sets(float v, int S, float inv) {
+    return (S & (S - 1)) ? __fdiv_rn(v, (float)S) : v * inv;
 }
 
 template <int M, int CPL, int L>
 __global__ void __launch_bounds__(kSmallThreads) small_fwd(const SmallParams P) {
+    constexpr int H = CPL / 2;
     const int lane = threadIdx.x & (L - 1);
     const long long groups = (long long)gridDim.x * (kSmallThreads / L);
     const long long g0 = ((long long)blockIdx.x * kSmallThreads + threadIdx.x) / L;
     Locator<M, CPL, L> loc;
     loc.init(P, lane);
-    float u0r[M], v0r[CPL];
+    float u0r[M];
+    f2 v0r[H];
 #pragma unroll
     for (int i = 0; i < M; ++i) u0r[i] = __ldg(P.u0 + i);
 #pragma unroll
-    for (int k = 0; k < CPL; ++k) v0r[k] = __ldg(P.v0 + k * L + lane);
+    for (int k = 0; k < H; ++k) v0r[k] = __ldg(reinterpret_cast<const f2*>(P.v0) + k * L + lane);
     const long long stride = P.window ? P.G.vox : (long long)CPL * L;
+    const float invS = 1.f / (float)P.S;
     for (long long first = 0; first < P.n; first += groups) {      // trip count is uniform across the warp
         const long long mid = first + g0;
         const bool valid = mid < P.n;
         int off[CPL];
         const long long base = loc.locate(P, valid ? mid : 0, off);
-        float x[M][CPL];
+        const float* src = P.x + base;
+        f2 x[M][H];
 #pragma unroll
         for (int i = 0; i < M; ++i)
 #pragma unroll
-            for (int k = 0; k < CPL; ++k) {
-                float t = valid ? __ldg(P.x + base + i * stride + off[k]) : 0.f;
-                x[i][k] = P.relu ? fmaxf(t, 0.f) : t;
+            for (int k = 0; k < H; ++k) {
+                float t0 = valid ? __ldg(src + i * stride + off[2 * k]) : 0.f;
+                float t1 = valid ? __ldg(src + i * stride + off[2 * k + 1]) : 0.f;
+                if (P.relu) { t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f); }
+                x[i][k] = make_float2(t0, t1);
             }
-        float u[M], v[CPL], a[M], c[CPL], b, d;
+        float u[M], a[M], b, d;
+        f2 v[H], c[H];
 #pragma unroll
         for (int i = 0; i < M; ++i) u[i] = u0r[i];
 #pragma unroll
-        for (int k = 0; k < CPL; ++k) v[k] = v0r[k];
+        for (int k = 0; k < H; ++k) v[k] = v0r[k];
         for (int t = 0; t < P.T; ++t) {
-            step_u<M, CPL, L>(x, v, u, a, b, P.kind, P.eps);
-            step_v<M, CPL>(x, u, v, c, d, P.kind, P.eps);
+            step_u<M, H, L>(x, v, u, a, b, P.kind, P.eps);
+            step_v<M, H>(x, u, v, c, d, P.kind, P.eps);
         }
         if (valid) {
             const bool add = P.window && P.set > 0, last = P.window && P.set == P.S - 1 && P.S > 1;
-            const float fs = (float)P.S;
+            float* dstb = P.out + base;
 #pragma unroll
             for (int i = 0; i < M; ++i)
 #pragma unroll
-                for (int k = 0; k < CPL; ++k) {
-                    float* dst = P.out + base + i * stride + off[k];
-                    float y = u[i] * v[k];
-                    if (add) y = __fadd_rn(*dst, y);
-                    if (last) y = __fdiv_rn(y, fs);
-                    *dst = y;
+                for (int k = 0; k < H; ++k) {
+                    float* d0 = dstb + i * stride + off[2 * k];
+                    float* d1 = dstb + i * stride + off[2 * k + 1];
+                    float y0 = u[i] * v[k].x, y1 = u[i] * v[k].y;
+                    if (add) { y0 = __fadd_rn(*d0, y0); y1 = __fadd_rn(*d1, y1); }
+                    if (last) { y0 = div_sets(y0, P.S, invS); y1 = div_sets(y1, P.S, invS); }
+                    *d0 = y0; *d1 = y1;
                 }
         }
     }
@@ -222,7 +244,8 @@ struct Hist {
 
 template <int M, int CPL, int L>
 __global__ void __launch_bounds__(kSmallThreads) small_bwd(const SmallParams P) {
-    extern __shared__ float hist_all[];
+    extern __shared__ __align__(8) float hist_all[];
+    constexpr int H = CPL / 2;
     constexpr int kHS = M + CPL * L;
     float* hist = hist_all + (threadIdx.x / L) * Hist<M, CPL, L>::floats;
     const int lane = threadIdx.x & (L - 1);
@@ -230,39 +253,47 @@ __global__ void __launch_bounds__(kSmallThreads) small_bwd(const SmallParams P) 
     const long long g0 = ((long long)blockIdx.x * kSmallThreads + threadIdx.x) / L;
     Locator<M, CPL, L> loc;
     loc.init(P, lane);
-    float u0r[M], v0r[CPL];
+    float u0r[M];
+    f2 v0r[H];
 #pragma unroll
     for (int i = 0; i < M; ++i) u0r[i] = __ldg(P.u0 + i);
 #pragma unroll
-    for (int k = 0; k < CPL; ++k) v0r[k] = __ldg(P.v0 + k * L + lane);
+    for (int k = 0; k < H; ++k) v0r[k] = __ldg(reinterpret_cast<const f2*>(P.v0) + k * L + lane);
     const long long stride = P.window ? P.G.vox : (long long)CPL * L;
     const float eps = P.eps;
     const int T = P.T, K = P.K;
+    const float invS = 1.f / (float)P.S;
+    // v_t of this lane: pair k at hist[t * kHS + M + 2 (k L + lane)]
+    auto vh = [&](int t, int k) -> f2& { return *reinterpret_cast<f2*>(hist + t * kHS + M + 2 * (k * L + lane)); };
     for (long long first = 0; first < P.n; first += groups) {
         const long long mid = first + g0;
         const bool valid = mid < P.n;
         int off[CPL];
         const long long base = loc.locate(P, valid ? mid : 0, off);
-        float x[M][CPL];
+        const float* src = P.x + base;
+        f2 x[M][H];
         unsigned long long mask = 0;       // x > 0 before the ReLU (M*CPL = 64 bits)
 #pragma unroll
         for (int i = 0; i < M; ++i)
 #pragma unroll
-            for (int k = 0; k < CPL; ++k) {
-                float t = valid ? __ldg(P.x + base + i * stride + off[k]) : 0.f;
+            for (int k = 0; k < H; ++k) {
+                float t0 = valid ? __ldg(src + i * stride + off[2 * k]) : 0.f;
+                float t1 = valid ? __ldg(src + i * stride + off[2 * k + 1]) : 0.f;
                 if (P.relu) {
-                    if (t > 0.f) mask |= 1ULL << (i * CPL + k);
-                    t = fmaxf(t, 0.f);
+                    if (t0 > 0.f) mask |= 1ULL << (i * CPL + 2 * k);
+                    if (t1 > 0.f) mask |= 1ULL << (i * CPL + 2 * k + 1);
+                    t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f);
                 }
-                x[i][k] = t;
+                x[i][k] = make_float2(t0, t1);
             }
         // ---- recompute the iterates; u_t, v_t (t = 0..T) go to this sub-warp's slice of shared memory ----
         {
-            float u[M], v[CPL];
+            float u[M];
+            f2 v[H];
 #pragma unroll
             for (int i = 0; i < M; ++i) u[i] = u0r[i];
 #pragma unroll
-            for (int k = 0; k < CPL; ++k) v[k] = v0r[k];
+            for (int k = 0; k < H; ++k) v[k] = v0r[k];
             __syncwarp();                      // the previous matrix's history is no longer read
             for (int t = 0;; ++t) {
                 if (lane == 0) {
@@ -270,155 +301,183 @@ __global__ void __launch_bounds__(kSmallThreads) small_bwd(const SmallParams P) 
                     for (int i = 0; i < M; ++i) hist[t * kHS + i] = u[i];
                 }
 #pragma unroll
-                for (int k = 0; k < CPL; ++k) hist[t * kHS + M + k * L + lane] = v[k];
+                for (int k = 0; k < H; ++k) vh(t, k) = v[k];
                 if (t == T) break;
-                float a[M], c[CPL], b, d;
-                step_u<M, CPL, L>(x, v, u, a, b, P.kind, eps);
-                step_v<M, CPL>(x, u, v, c, d, P.kind, eps);
+                float a[M], b, d;
+                f2 c[H];
+                step_u<M, H, L>(x, v, u, a, b, P.kind, eps);
+                step_v<M, H>(x, u, v, c, d, P.kind, eps);
             }
             __syncwarp();
         }
         // ---- seed: y = u_T v_T^T ----
-        float xb[M][CPL];                  // dL/dx accumulator; first holds dL/dy
-        const float invS = P.window ? __fdiv_rn(1.f, (float)P.S) : 1.f;
+        f2 xb[M][H];                       // dL/dx accumulator; first holds dL/dy
+        {
+            const float* gsrc = P.gy + base;
 #pragma unroll
-        for (int i = 0; i < M; ++i)
+            for (int i = 0; i < M; ++i)
 #pragma unroll
-            for (int k = 0; k < CPL; ++k) {
-                const float g = valid ? __ldg(P.gy + base + i * stride + off[k]) : 0.f;
-                xb[i][k] = P.window ? __fdiv_rn(g, (float)P.S) : g;
+                for (int k = 0; k < H; ++k) {
+                    float g0v = valid ? __ldg(gsrc + i * stride + off[2 * k]) : 0.f;
+                    float g1v = valid ? __ldg(gsrc + i * stride + off[2 * k + 1]) : 0.f;
+                    if (P.window) { g0v = div_sets(g0v, P.S, invS); g1v = div_sets(g1v, P.S, invS); }
+                    xb[i][k] = make_float2(g0v, g1v);
+                }
+        }
+        float ub[M];
+        f2 vb[H];
+        {
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+                f2 s = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < H; ++k) s = fma2(xb[i][k], vh(T, k), s);
+                ub[i] = group_sum<L>(s.x + s.y);
             }
-        (void)invS;
-        float ub[M], vb[CPL];
 #pragma unroll
-        for (int t = kTMax; t >= 1; --t) {
-            if (t == T) {
+            for (int k = 0; k < H; ++k) vb[k] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+                const f2 ui = dup(hist[T * kHS + i]);
+#pragma unroll
+                for (int k = 0; k < H; ++k) { vb[k] = fma2(xb[i][k], ui, vb[k]); }
+            }
+#pragma unroll
+            for (int i = 0; i < M; ++i)
+#pragma unroll
+                for (int k = 0; k < H; ++k) xb[i][k] = make_float2(0.f, 0.f);
+        }
+        for (int t = T; t > T - K; --t) {
+            float ut[M], up[M];
+            f2 vt[H], vp[H];
+#pragma unroll
+            for (int i = 0; i < M; ++i) { ut[i] = hist[t * kHS + i]; up[i] = hist[(t - 1) * kHS + i]; }
+#pragma unroll
+            for (int k = 0; k < H; ++k) { vt[k] = vh(t, k); vp[k] = vh(t - 1, k); }
+            // ---- adjoint of the v half-step ----
+            float d = 0.f;
+#pragma unroll
+            for (int i = 0; i < M; ++i) d = fmaf(ut[i], ut[i], d);
+            f2 cb[H];
+            float dbar = 0.f;
+            if (P.kind == FZ_SOLVER_HALS) {
+                const float rd = rcp_nr(d + eps);
+#pragma unroll
+                for (int k = 0; k < H; ++k) {
+                    const f2 qb = make_float2(vt[k].x > 0.f ? vb[k].x : 0.f, vt[k].y > 0.f ? vb[k].y : 0.f);
+                    cb[k] = make_float2(qb.x * rd, qb.y * rd);
+                    dbar = fmaf(qb.x, vt[k].x, fmaf(qb.y, vt[k].y, dbar));
+                    vb[k] = make_float2(0.f, 0.f);     // v_{t-1} enters only through the u half-step
+                }
+                dbar = -rd * group_sum<L>(dbar);
+            } else {
+                f2 c[H];
+#pragma unroll
+                for (int k = 0; k < H; ++k) c[k] = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int i = 0; i < M; ++i) {
-                    float s = 0.f;
+                    const f2 ui = dup(ut[i]);
 #pragma unroll
-                    for (int k = 0; k < CPL; ++k) s = fmaf(xb[i][k], hist[t * kHS + M + k * L + lane], s);
-                    ub[i] = group_sum<L>(s);
+                    for (int k = 0; k < H; ++k) c[k] = fma2(x[i][k], ui, c[k]);
                 }
 #pragma unroll
-                for (int k = 0; k < CPL; ++k) {
-                    float s = 0.f;
-#pragma unroll
-                    for (int i = 0; i < M; ++i) s = fmaf(xb[i][k], hist[t * kHS + i], s);
-                    vb[k] = s;
+                for (int k = 0; k < H; ++k) {
+                    const float r0 = rcp_nr(fmaf(vp[k].x, d, eps)), r1 = rcp_nr(fmaf(vp[k].y, d, eps));
+                    const float n0 = vb[k].x * r0, n1 = vb[k].y * r1;
+                    const float e0 = -n0 * vt[k].x, e1 = -n1 * vt[k].y;
+                    cb[k] = make_float2(n0 * vp[k].x, n1 * vp[k].y);
+                    dbar = fmaf(e0, vp[k].x, fmaf(e1, vp[k].y, dbar));
+                    vb[k] = make_float2(fmaf(n0, c[k].x, e0 * d), fmaf(n1, c[k].y, e1 * d));
                 }
-#pragma unroll
-                for (int i = 0; i < M; ++i)
-#pragma unroll
-                    for (int k = 0; k < CPL; ++k) xb[i][k] = 0.f;
+                dbar = group_sum<L>(dbar);
             }
-            if (t <= T && t > T - K) {
-                float ut[M], up[M], vt[CPL], vp[CPL];
+            float un[M];                               // dL/du_t
 #pragma unroll
-                for (int i = 0; i < M; ++i) { ut[i] = hist[t * kHS + i]; up[i] = hist[(t - 1) * kHS + i]; }
+            for (int i = 0; i < M; ++i) {
+                f2 s = make_float2(0.f, 0.f);
+                const f2 ui = dup(ut[i]);
 #pragma unroll
-                for (int k = 0; k < CPL; ++k) { vt[k] = hist[t * kHS + M + k * L + lane]; vp[k] = hist[(t - 1) * kHS + M + k * L + lane]; }
-                // ---- adjoint of the v half-step ----
-                float d = 0.f;
+                for (int k = 0; k < H; ++k) { s = fma2(x[i][k], cb[k], s); xb[i][k] = fma2(ui, cb[k], xb[i][k]); }
+                un[i] = s.x + s.y;
+            }
 #pragma unroll
-                for (int i = 0; i < M; ++i) d = fmaf(ut[i], ut[i], d);
-                float cb[CPL], dbar = 0.f;
-                if (P.kind == FZ_SOLVER_HALS) {
-                    const float rd = rcp_nr(d + eps);
+            for (int o = L / 2; o > 0; o >>= 1)
 #pragma unroll
-                    for (int k = 0; k < CPL; ++k) {
-                        const float qb = vt[k] > 0.f ? vb[k] : 0.f;
-                        cb[k] = qb * rd;
-                        dbar = fmaf(qb, vt[k], dbar);
-                        vb[k] = 0.f;                       // v_{t-1} enters only through the u half-step
-                    }
-                    dbar = -rd * group_sum<L>(dbar);
-                } else {
+                for (int i = 0; i < M; ++i) un[i] += __shfl_xor_sync(0xffffffffu, un[i], o);
 #pragma unroll
-                    for (int k = 0; k < CPL; ++k) {
-                        float c = 0.f;
+            for (int i = 0; i < M; ++i) un[i] = ub[i] + fmaf(2.f * dbar, ut[i], un[i]);
+            // ---- adjoint of the u half-step ----
+            f2 b2 = make_float2(0.f, 0.f);
 #pragma unroll
-                        for (int i = 0; i < M; ++i) c = fmaf(x[i][k], ut[i], c);
-                        const float rden = rcp_nr(fmaf(vp[k], d, eps));
-                        const float nb = vb[k] * rden, db = -nb * vt[k];
-                        cb[k] = nb * vp[k];
-                        dbar = fmaf(db, vp[k], dbar);
-                        vb[k] = fmaf(nb, c, db * d);
-                    }
-                    dbar = group_sum<L>(dbar);
-                }
-                float un[M];                               // dL/du_t
+            for (int k = 0; k < H; ++k) b2 = fma2(vp[k], vp[k], b2);
+            const float b = group_sum<L>(b2.x + b2.y);
+            float ab[M], bbar = 0.f;
+            if (P.kind == FZ_SOLVER_HALS) {
+                const float rb = rcp_nr(b + eps);
 #pragma unroll
                 for (int i = 0; i < M; ++i) {
-                    float s = 0.f;
+                    const float pb = ut[i] > 0.f ? un[i] : 0.f;
+                    ab[i] = pb * rb;
+                    bbar = fmaf(pb, ut[i], bbar);
+                    ub[i] = 0.f;
+                }
+                bbar *= -rb;
+            } else {
+                float a[M];
 #pragma unroll
-                    for (int k = 0; k < CPL; ++k) { s = fmaf(x[i][k], cb[k], s); xb[i][k] = fmaf(ut[i], cb[k], xb[i][k]); }
-                    un[i] = s;
+                for (int i = 0; i < M; ++i) {
+                    f2 s = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int k = 0; k < H; ++k) s = fma2(x[i][k], vp[k], s);
+                    a[i] = s.x + s.y;
                 }
 #pragma unroll
                 for (int o = L / 2; o > 0; o >>= 1)
 #pragma unroll
-                    for (int i = 0; i < M; ++i) un[i] += __shfl_xor_sync(0xffffffffu, un[i], o);
+                    for (int i = 0; i < M; ++i) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
 #pragma unroll
-                for (int i = 0; i < M; ++i) un[i] = ub[i] + fmaf(2.f * dbar, ut[i], un[i]);
-                // ---- adjoint of the u half-step ----
-                float b = 0.f;
-#pragma unroll
-                for (int k = 0; k < CPL; ++k) b = fmaf(vp[k], vp[k], b);
-                b = group_sum<L>(b);
-                float ab[M], bbar = 0.f;
-                if (P.kind == FZ_SOLVER_HALS) {
-                    const float rb = rcp_nr(b + eps);
-#pragma unroll
-                    for (int i = 0; i < M; ++i) {
-                        const float pb = ut[i] > 0.f ? un[i] : 0.f;
-                        ab[i] = pb * rb;
-                        bbar = fmaf(pb, ut[i], bbar);
-                        ub[i] = 0.f;
-                    }
-                    bbar *= -rb;
-                } else {
-                    float a[M];
-#pragma unroll
-                    for (int i = 0; i < M; ++i) {
-                        float s = 0.f;
-#pragma unroll
-                        for (int k = 0; k < CPL; ++k) s = fmaf(x[i][k], vp[k], s);
-                        a[i] = s;
-                    }
-#pragma unroll
-                    for (int o = L / 2; o > 0; o >>= 1)
-#pragma unroll
-                        for (int i = 0; i < M; ++i) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
-#pragma unroll
-                    for (int i = 0; i < M; ++i) {
-                        const float rden = rcp_nr(fmaf(up[i], b, eps));
-                        const float nb = un[i] * rden, db = -nb * ut[i];
-                        ab[i] = nb * up[i];
-                        bbar = fmaf(db, up[i], bbar);
-                        ub[i] = fmaf(nb, a[i], db * b);
-                    }
+                for (int i = 0; i < M; ++i) {
+                    const float rden = rcp_nr(fmaf(up[i], b, eps));
+                    const float nb = un[i] * rden, db = -nb * ut[i];
+                    ab[i] = nb * up[i];
+                    bbar = fmaf(db, up[i], bbar);
+                    ub[i] = fmaf(nb, a[i], db * b);
                 }
+            }
+            {
+                f2 s[H];
 #pragma unroll
-                for (int k = 0; k < CPL; ++k) {
-                    float s = 0.f;
+                for (int k = 0; k < H; ++k) s[k] = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int i = 0; i < M; ++i) { s = fmaf(x[i][k], ab[i], s); xb[i][k] = fmaf(ab[i], vp[k], xb[i][k]); }
-                    vb[k] += fmaf(2.f * bbar, vp[k], s);
+                for (int i = 0; i < M; ++i) {
+                    const f2 ai = dup(ab[i]);
+#pragma unroll
+                    for (int k = 0; k < H; ++k) { s[k] = fma2(x[i][k], ai, s[k]); xb[i][k] = fma2(ai, vp[k], xb[i][k]); }
+                }
+                const f2 tb = dup(2.f * bbar);
+#pragma unroll
+                for (int k = 0; k < H; ++k) {
+                    const f2 w = fma2(tb, vp[k], s[k]);
+                    vb[k] = make_float2(vb[k].x + w.x, vb[k].y + w.y);
                 }
             }
         }
         if (valid) {
             const bool add = P.window && P.set > 0;
+            float* dstb = P.out + base;
 #pragma unroll
             for (int i = 0; i < M; ++i)
 #pragma unroll
-                for (int k = 0; k < CPL; ++k) {
-                    float* dst = P.out + base + i * stride + off[k];
-                    float g = xb[i][k];
-                    if (P.relu && !((mask >> (i * CPL + k)) & 1ULL)) g = 0.f;
-                    if (add) g = __fadd_rn(*dst, g);
-                    *dst = g;
+                for (int k = 0; k < H; ++k) {
+                    float* d0 = dstb + i * stride + off[2 * k];
+                    float* d1 = dstb + i * stride + off[2 * k + 1];
+                    float g0v = xb[i][k].x, g1v = xb[i][k].y;
+                    if (P.relu) {
+                        if (!((mask >> (i * CPL + 2 * k)) & 1ULL)) g0v = 0.f;
+                        if (!((mask >> (i * CPL + 2 * k + 1)) & 1ULL)) g1v = 0.f;
+                    }
+                    if (add) { g0v = __fadd_rn(*d0, g0v); g1v = __fadd_rn(*d1, g1v); }
+                    *d0 = g0v; *d1 = g1v;
                 }
         }
     }
