@@ -26,7 +26,7 @@ CASES = [
     ("tests/test_factorizer.py stage 2 (8x64)", 3, 64, (32,) * 3, dict(num_heads=8, patch_size=4)),
     ("tests/test_factorizer.py stage 4 (32x64)", 3, 256, (8,) * 3, dict(num_heads=8, patch_size=4)),
 ]
-PATH = {0: "generic smem", 1: "window-at-a-time TMA", 2: "three-pass octant", 3: "sub-warp register"}
+PATH = {0: "generic smem", 1: "window-at-a-time TMA", 2: "three-pass octant", 3: "sub-warp register", 4: "octant x pairs (rolled)"}
 print("| geometry | x shape | matrix | windows | path | fwd us | bwd us | fwd+bwd % of HBM roofline |")
 print("|---|---|---|---|---|---|---|---|")
 for name, B, C, size, kw in CASES:

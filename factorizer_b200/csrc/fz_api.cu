@@ -111,6 +111,7 @@ int fz_nmf_backward(const float* x, const float* u0, const float* v0, const floa
 size_t fz_swnmf_saved_bytes(const fz_geom* g, const fz_solver* s) {
     DevGeom G;
     if (make_dev_geom(g, &G) || !s) return 0;
+    if (!phase_supported(G, *s, 1) && pairs_supported(G, *s, 1)) return pairs_saved_bytes(G, *s);
     return fast_saved_bytes(G, *s);
 }
 
@@ -120,6 +121,9 @@ size_t fz_swnmf_workspace_bytes(const fz_geom* g, const fz_solver* s) {
     size_t a = fast_workspace_bytes(G, *s);
     if (phase_supported(G, *s, 1)) {
         const size_t b = phase_workspace_bytes(G, *s);
+        if (b > a) a = b;
+    } else if (pairs_supported(G, *s, 1)) {
+        const size_t b = pairs_workspace_bytes(G, *s);
         if (b > a) a = b;
     }
     return a;
@@ -137,6 +141,12 @@ int fz_swnmf_forward(const float* x, const float* u0, const float* v0, float* y,
     if ((g_forced_path == -1 || g_forced_path == 2) && phase_supported(G, *s, relu_input)) {
         tls().path = 2;
         return phase_forward(x, v0, y, saved, workspace, G, *s, (cudaStream_t)stream);
+    }
+    if ((g_forced_path == -1 || g_forced_path == 2) && pairs_supported(G, *s, relu_input)) {
+        tls().path = 4;
+        const int e = pairs_forward(x, v0, y, saved, workspace, G, *s, (cudaStream_t)stream);
+        tls().path = 4;
+        return e;
     }
     if (g_forced_path != 0 && fast_supported(G, *s)) {
         tls().path = 1;
@@ -167,6 +177,10 @@ int fz_swnmf_backward(const float* x, const float* gy, const float* u0, const fl
     if ((g_forced_path == -1 || g_forced_path == 2) && phase_supported(G, *s, relu_input)) {
         tls().path = 2;
         return phase_backward(x, gy, v0, saved, gx, workspace, G, *s, K, (cudaStream_t)stream);
+    }
+    if ((g_forced_path == -1 || g_forced_path == 2) && pairs_supported(G, *s, relu_input)) {
+        tls().path = 4;
+        return pairs_backward(x, gy, v0, saved, gx, workspace, G, *s, K, (cudaStream_t)stream);
     }
     if (g_forced_path != 0 && fast_supported(G, *s)) {
         tls().path = 1;

@@ -58,4 +58,13 @@ int phase_forward(const float* x, const float* v0, float* y, void* saved, void* 
 int phase_backward(const float* x, const float* gy, const float* v0, const void* saved, float* gx,
                    void* workspace, const DevGeom& G, const fz_solver& s, int K, cudaStream_t st);
 
+// ... and window sets that pair up as (a, a + patch/2): one octant problem per pair on the volume rolled by a
+bool pairs_supported(const DevGeom& G, const fz_solver& s, int relu);
+size_t pairs_saved_bytes(const DevGeom& G, const fz_solver& s);
+size_t pairs_workspace_bytes(const DevGeom& G, const fz_solver& s);
+int pairs_forward(const float* x, const float* v0, float* y, void* saved, void* workspace, const DevGeom& G,
+                  const fz_solver& s, cudaStream_t st);
+int pairs_backward(const float* x, const float* gy, const float* v0, const void* saved, float* gx, void* workspace,
+                   const DevGeom& G, const fz_solver& s, int K, cudaStream_t st);
+
 }  // namespace fz

@@ -22,6 +22,7 @@
 // wrapped or misaligned boxes, no partial-sum round trip, and the volume-sized transfers drop to 3
 // forward and 5 backward.
 #include <cuda.h>
+#include <type_traits>
 #include <stdlib.h>
 #include <string.h>
 
@@ -1059,6 +1060,212 @@ int phase_backward(const float* x, const float* gy, const float* v0, const void*
         if (mask & 4) {
             phase_bwd_apply<<<grid_for(P.t_count, kWB), kWB * 32, kWB * 4 * kTileBytes, st>>>(P);
             FZ_LAUNCH_CHECK();
+        }
+    }
+    return FZ_OK;
+}
+
+
+// =====================================================================================================
+// Window sets that pair up as (a, a + patch/2): every pair is the octant problem on the volume rolled by a
+//   sum_{s in {a, a+4}} inv_s(NMF(win(roll(x, s)))) = roll( octant(roll(x, a)), -a )
+// (torch.roll composes: roll(x, a + 4) = roll(roll(x, a), 4); operations.py:266-280), so e.g. the brats23
+// bundle's shifts [0, 2, 4, 6] (model_zoo/factorizer_brats23/configs/train.yaml:50-54) run as two octant
+// problems plus one roll and one roll-and-combine pass per pair instead of four window-at-a-time sweeps.
+// =====================================================================================================
+namespace {
+
+struct RollParams { int n0, n1, n2, s0, s1, s2; long long rows, vox; };
+
+// out[r][i] = in[r][(i - s) mod n]   (torch.roll).  One CTA per (row, i0) plane; V = 2 or 4 neighbouring voxels per
+// thread (n2 and s2 multiples of V), 32-bit index math.
+template <int V>
+__global__ void __launch_bounds__(256) roll_volume(const float* __restrict__ in, float* __restrict__ out, const RollParams R) {
+    typedef typename std::conditional<V == 4, float4, float2>::type vec;
+    const int hv = R.n2 / V, per_plane = R.n1 * hv;
+    for (long long pl = blockIdx.x; pl < R.rows * R.n0; pl += gridDim.x) {
+        const long long r = pl / R.n0;
+        const int i0 = (int)(pl - r * R.n0);
+        int j0 = i0 - R.s0;
+        if (j0 < 0) j0 += R.n0;
+        const float* src = in + r * R.vox + (long long)j0 * R.n1 * R.n2;
+        float* dst = out + r * R.vox + (long long)i0 * R.n1 * R.n2;
+        for (int t = threadIdx.x; t < per_plane; t += blockDim.x) {
+            const int i1 = t / hv, i2 = (t - i1 * hv) * V;
+            int j1 = i1 - R.s1, j2 = i2 - R.s2;
+            if (j1 < 0) j1 += R.n1;
+            if (j2 < 0) j2 += R.n2;
+            *reinterpret_cast<vec*>(dst + i1 * R.n2 + i2) = __ldcs(reinterpret_cast<const vec*>(src + j1 * R.n2 + j2));
+        }
+    }
+}
+
+// acc[r][i] = ((first ? 0 : acc[r][i]) + part[r][(i + s) mod n]) * scale   (the inverse roll, summed over the pairs)
+template <int V>
+__global__ void __launch_bounds__(256) unroll_combine(float* __restrict__ acc, const float* __restrict__ part, const RollParams R,
+                                                      int first, float scale) {
+    typedef typename std::conditional<V == 4, float4, float2>::type vec;
+    const int hv = R.n2 / V, per_plane = R.n1 * hv;
+    for (long long pl = blockIdx.x; pl < R.rows * R.n0; pl += gridDim.x) {
+        const long long r = pl / R.n0;
+        const int i0 = (int)(pl - r * R.n0);
+        int j0 = i0 + R.s0;
+        if (j0 >= R.n0) j0 -= R.n0;
+        const float* src = part + r * R.vox + (long long)j0 * R.n1 * R.n2;
+        float* dst = acc + r * R.vox + (long long)i0 * R.n1 * R.n2;
+        for (int t = threadIdx.x; t < per_plane; t += blockDim.x) {
+            const int i1 = t / hv, i2 = (t - i1 * hv) * V;
+            int j1 = i1 + R.s1, j2 = i2 + R.s2;
+            if (j1 >= R.n1) j1 -= R.n1;
+            if (j2 >= R.n2) j2 -= R.n2;
+            vec v = __ldcs(reinterpret_cast<const vec*>(src + j1 * R.n2 + j2));
+            float* vf = reinterpret_cast<float*>(&v);
+            vec* d = reinterpret_cast<vec*>(dst + i1 * R.n2 + i2);
+            if (!first) {
+                const vec o = *d;
+                const float* of = reinterpret_cast<const float*>(&o);
+#pragma unroll
+                for (int q = 0; q < V; ++q) vf[q] += of[q];
+            }
+#pragma unroll
+            for (int q = 0; q < V; ++q) vf[q] *= scale;
+            *d = v;
+        }
+    }
+}
+
+int norm_shift(int v, int n) { v %= n; return v < 0 ? v + n : v; }
+
+// base shift of every pair (normalised to [0, n)); false if the sets do not pair up
+bool find_pairs(const DevGeom& G, int (*base)[3]) {
+    if (G.S < 2 || G.S % 2) return false;
+    bool used[FZ_MAX_SHIFTS] = {false};
+    int np = 0;
+    for (int a = 0; a < G.S; ++a) {
+        if (used[a]) continue;
+        int b = -1;
+        for (int c = 0; c < G.S && b < 0; ++c) {
+            if (c == a || used[c]) continue;
+            bool ok = true;
+            for (int k = 0; k < 3; ++k)
+                if (norm_shift(G.sh[c][k] - G.sh[a][k], G.n[k]) != 4 % G.n[k]) ok = false;
+            if (ok) b = c;
+        }
+        if (b < 0) return false;
+        used[a] = used[b] = true;
+        for (int k = 0; k < 3; ++k) base[np][k] = norm_shift(G.sh[a][k], G.n[k]);
+        ++np;
+    }
+    return true;
+}
+
+DevGeom pair_geom(const DevGeom& G) {
+    DevGeom P = G;
+    P.S = 2;
+    for (int q = 0; q < FZ_MAX_SHIFTS; ++q)
+        for (int k = 0; k < 3; ++k) P.sh[q][k] = q == 1 ? 4 : 0;
+    return P;
+}
+
+size_t vol_bytes(const DevGeom& G) { return align_up((size_t)G.B * G.C * G.vox * sizeof(float), 256); }
+
+int launch_roll(const float* in, float* out, const DevGeom& G, const int* a, cudaStream_t st) {
+    RollParams R = {G.n[0], G.n[1], G.n[2], a[0], a[1], a[2], (long long)G.B * G.C, G.vox};
+    const long long planes = R.rows * R.n0;
+    const unsigned grid = (unsigned)(planes < 65535LL * 16 ? planes : 65535LL * 16);
+    if (R.n2 % 4 == 0 && R.s2 % 4 == 0) roll_volume<4><<<grid, 256, 0, st>>>(in, out, R);
+    else roll_volume<2><<<grid, 256, 0, st>>>(in, out, R);
+    FZ_LAUNCH_CHECK();
+    return FZ_OK;
+}
+int launch_combine(float* acc, const float* part, const DevGeom& G, const int* a, int first, float scale, cudaStream_t st) {
+    RollParams R = {G.n[0], G.n[1], G.n[2], a[0], a[1], a[2], (long long)G.B * G.C, G.vox};
+    const long long planes = R.rows * R.n0;
+    const unsigned grid = (unsigned)(planes < 65535LL * 16 ? planes : 65535LL * 16);
+    if (R.n2 % 4 == 0 && R.s2 % 4 == 0) unroll_combine<4><<<grid, 256, 0, st>>>(acc, part, R, first, scale);
+    else unroll_combine<2><<<grid, 256, 0, st>>>(acc, part, R, first, scale);
+    FZ_LAUNCH_CHECK();
+    return FZ_OK;
+}
+
+}  // namespace
+
+bool pairs_supported(const DevGeom& G, const fz_solver& s, int relu) {
+    if (G.S < 2 || G.S % 2 || G.n[2] % 2) return false;
+    int base[FZ_MAX_SHIFTS][3];
+    if (!find_pairs(G, base)) return false;
+    for (int q = 0; q < G.S / 2; ++q)
+        if (base[q][2] % 2) return false;          // the roll kernels move voxel pairs
+    return phase_supported(pair_geom(G), s, relu);
+}
+
+size_t pairs_saved_bytes(const DevGeom& G, const fz_solver& s) {
+    return (size_t)G.S * G.mats_per_shift * (rec_head_for(s.num_iters) + 72) * sizeof(float);
+}
+
+size_t pairs_workspace_bytes(const DevGeom& G, const fz_solver& s) {
+    return align_up(phase_workspace_bytes(pair_geom(G), s), 256) + 3 * vol_bytes(G);
+}
+
+int pairs_forward(const float* x, const float* v0, float* y, void* saved, void* workspace, const DevGeom& G,
+                  const fz_solver& s, cudaStream_t st) {
+    if (!workspace) return fail(FZ_ERR_INVALID, "fz_swnmf_forward: workspace of %zu bytes required", pairs_workspace_bytes(G, s));
+    const DevGeom Gp = pair_geom(G);
+    int base[FZ_MAX_SHIFTS][3];
+    find_pairs(G, base);
+    const int np = G.S / 2;
+    char* ws = static_cast<char*>(workspace);
+    float* bufA = reinterpret_cast<float*>(ws + align_up(phase_workspace_bytes(Gp, s), 256));
+    float* bufB = reinterpret_cast<float*>(reinterpret_cast<char*>(bufA) + vol_bytes(G));
+    const size_t saved_stride = (size_t)2 * Gp.mats_per_shift * (rec_head_for(s.num_iters) + 72) * sizeof(float);
+    for (int k = 0; k < np; ++k) {
+        const bool rolled = base[k][0] || base[k][1] || base[k][2];
+        const float* xin = x;
+        if (rolled) {
+            if (int e = launch_roll(x, bufA, G, base[k], st)) return e;
+            xin = bufA;
+        }
+        const bool direct = !rolled && k == 0;       // the unshifted pair writes (the start of) the sum in place
+        void* sv = saved ? static_cast<char*>(saved) + k * saved_stride : nullptr;
+        if (int e = phase_forward(xin, v0, direct ? y : bufB, sv, workspace, Gp, s, st)) return e;
+        const float scale = k == np - 1 ? 1.f / (float)np : 1.f;
+        if (!direct) {
+            if (int e = launch_combine(y, bufB, G, base[k], k == 0, scale, st)) return e;
+        } else if (np == 1) {
+            return FZ_OK;
+        }
+    }
+    return FZ_OK;
+}
+
+int pairs_backward(const float* x, const float* gy, const float* v0, const void* saved, float* gx, void* workspace,
+                   const DevGeom& G, const fz_solver& s, int K, cudaStream_t st) {
+    if (!workspace) return fail(FZ_ERR_INVALID, "fz_swnmf_backward: workspace of %zu bytes required", pairs_workspace_bytes(G, s));
+    if (!saved) return fail(FZ_ERR_INVALID, "fz_swnmf_backward: the `saved` buffer written by fz_swnmf_forward is required");
+    const DevGeom Gp = pair_geom(G);
+    int base[FZ_MAX_SHIFTS][3];
+    find_pairs(G, base);
+    const int np = G.S / 2;
+    char* ws = static_cast<char*>(workspace);
+    float* bufA = reinterpret_cast<float*>(ws + align_up(phase_workspace_bytes(Gp, s), 256));
+    float* bufB = reinterpret_cast<float*>(reinterpret_cast<char*>(bufA) + vol_bytes(G));
+    float* bufC = reinterpret_cast<float*>(reinterpret_cast<char*>(bufB) + vol_bytes(G));
+    const size_t saved_stride = (size_t)2 * Gp.mats_per_shift * (rec_head_for(s.num_iters) + 72) * sizeof(float);
+    const float inv_np = 1.f / (float)np;
+    for (int k = 0; k < np; ++k) {
+        const bool rolled = base[k][0] || base[k][1] || base[k][2];
+        const float *xin = x, *gin = gy;
+        if (rolled) {
+            if (int e = launch_roll(x, bufA, G, base[k], st)) return e;
+            if (int e = launch_roll(gy, bufB, G, base[k], st)) return e;
+            xin = bufA; gin = bufB;
+        }
+        const bool direct = !rolled && k == 0;
+        const void* sv = static_cast<const char*>(saved) + k * saved_stride;
+        if (int e = phase_backward(xin, gin, v0, sv, direct ? gx : bufC, workspace, Gp, s, K, st)) return e;
+        const float scale = k == np - 1 ? inv_np : 1.f;
+        if (!direct) {
+            if (int e = launch_combine(gx, bufC, G, base[k], k == 0, scale, st)) return e;
         }
     }
     return FZ_OK;

@@ -143,11 +143,12 @@ def test_fused_core_matches_reference(ft, dev, golden, name, path):
 
 def test_kernel_path_selection(ft, dev, golden):
     """Which kernel family serves which geometry (fz_last_path): 2 = three-pass octant kernels (default Swin
-    geometry), 1 = window-at-a-time 8x512 kernels (other shifts), 3 = sub-warp register kernels (64-column
+    geometry), 4 = the same per pair of window sets on a rolled volume (brats23 shifts), 1 = window-at-a-time 8x512
+    kernels (any other shifts), 3 = sub-warp register kernels (64-column
     windows of the isles22 bundle / reference tests, small ft.NMF batches), 0 = generic shared-memory kernels."""
     from factorizer_b200 import _lib, _ops
     lib = _lib.lib()
-    want = {"fused_cfg2_16": 2, "fused_brats_s4": 1, "fused_isles_s4": 3, "fused_nh8_ps4": 3, "fused_2d": 3,
+    want = {"fused_cfg2_16": 2, "fused_brats_s4": 4, "fused_isles_s4": 3, "fused_nh8_ps4": 3, "fused_2d": 3,
             "fused_mu_r2": 0, "fused_global_mu": 0}
     for name, path in want.items():
         c = cases.FUSED_CASES[name]
