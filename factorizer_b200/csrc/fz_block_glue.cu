@@ -30,7 +30,7 @@ __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c
 __device__ __forceinline__ f2 dup(float a) { return make_float2(a, a); }
 
 constexpr int kC = 32;            // channels the kernels are written for
-constexpr int kMaxHidden = 64;    // MLP hidden width limit of the backward kernel (shared memory)
+constexpr int kMaxHidden = 64;    // hidden units per launch of the backward kernel (shared memory); wider MLPs go slice by slice
 constexpr int kTT = 256;          // threads per CTA of the tiled (staging) kernels
 constexpr int kTV = 2 * kTT;      // voxels per tile
 constexpr int kRS = kTV + 4;      // staged row stride in floats: = 4 (mod 32)
@@ -467,7 +467,11 @@ __global__ void __launch_bounds__(kTT, 1) mlp_bwd(const float* __restrict__ x1, 
                                                   const float* __restrict__ W2, float* __restrict__ dx1,
                                                   float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dW1,
                                                   float* __restrict__ db1, float* __restrict__ dW2, float* __restrict__ db2, int HID,
-                                                  long long vox, int tiles_per_sample, long long total_tiles, float eps) {
+                                                  int ldw2, int accumulate, long long vox, int tiles_per_sample,
+                                                  long long total_tiles, float eps) {
+    // HID: the hidden units this launch covers (a slice of at most kMaxHidden; W1 / b1 / dW1 / db1 point at the
+    // slice's first row, W2 / dW2 at its first column, rows ldw2 apart).  accumulate: dx1 already holds
+    // dout + the other slices' contributions (the backward is additive over hidden units).
     extern __shared__ __align__(16) float sm[];
     // weights: W1T has gamma folded in ([c][j] = W1[j][c] gamma[c]) and b1f = b1 + W1 beta, so the hidden
     // pre-activation is W1T^T a_hat + b1f with a_hat the normalised (pre-affine) input kept in registers
@@ -497,7 +501,7 @@ __global__ void __launch_bounds__(kTT, 1) mlp_bwd(const float* __restrict__ x1, 
         const float w = W1[i];
         W1s[i] = w;
         W1T[c * HID + j] = w * gs[c];
-        W2s[i] = W2[i];
+        W2s[i] = W2[(i / HID) * ldw2 + i % HID];
         accQ[i] = 0.f;
         accW2[i] = 0.f;
     }
@@ -590,9 +594,13 @@ __global__ void __launch_bounds__(kTT, 1) mlp_bwd(const float* __restrict__ x1, 
                 const f2 g = *reinterpret_cast<const f2*>(mycol_do + c * kRS);
                 sb[c] = g.x + g.y;
                 f2 o;
-                o.x = g.x + rstd.x * (d.x * gs[c] - m1.x - nh[c].x * m2.x);
-                o.y = g.y + rstd.y * (d.y * gs[c] - m1.y - nh[c].y * m2.y);
-                if (valid) *reinterpret_cast<f2*>(dx1 + base + c * vox) = o;
+                o.x = rstd.x * (d.x * gs[c] - m1.x - nh[c].x * m2.x);
+                o.y = rstd.y * (d.y * gs[c] - m1.y - nh[c].y * m2.y);
+                if (valid) {
+                    f2* dp = reinterpret_cast<f2*>(dx1 + base + c * vox);
+                    const f2 prev = accumulate ? *dp : g;
+                    *dp = make_float2(prev.x + o.x, prev.y + o.y);
+                }
             }
             scr_w[kScrMlp + lane] = warp_vec_sum<C>(sb, lane);
         }
@@ -609,7 +617,7 @@ __global__ void __launch_bounds__(kTT, 1) mlp_bwd(const float* __restrict__ x1, 
     for (int idx = tid; idx < HID * C; idx += kTT) {
         const int blk = idx >> 8, e = (idx >> 4) & 15, tt = idx & 15;
         const int j = blk * 8 + (tt >> 3) * 4 + (e >> 2), r = (tt & 7) + 8 * (e & 3);
-        atomicAdd(dW2 + r * HID + j, accW2[idx]);
+        atomicAdd(dW2 + r * ldw2 + j, accW2[idx]);
         // dW1[j][c] = sum_v dh[j] (gamma[c] a_hat[c] + beta[c])
         atomicAdd(dW1 + j * C + r, fmaf(gs[r], accQ[idx], bs[r] * accb1[j]));
     }
@@ -655,7 +663,7 @@ using namespace fz;
 extern "C" {
 
 int fz_glue_supported(int32_t channels, int32_t hidden, int64_t voxels) {
-    return channels == kC && voxels > 0 && voxels % 2 == 0 && hidden >= 8 && hidden % 8 == 0 && hidden <= kMaxHidden;
+    return channels == kC && voxels > 0 && voxels % 2 == 0 && hidden >= 8 && hidden % 8 == 0 && hidden <= 256;
 }
 
 int fz_ln_linear_forward(const float* x, const float* gamma, const float* beta, const float* W, float* y, int64_t batch,
@@ -736,8 +744,8 @@ int fz_mlp_backward(const float* x1, const float* dout, const float* gamma, cons
                     void* stream) {
     tls().launches = 0;
     if (int e = check_common(batch, channels, voxels)) return e;
-    if (hidden < 8 || hidden % 8 || hidden > kMaxHidden)
-        return fail(FZ_ERR_UNSUPPORTED, "hidden width %d: the MLP backward kernel needs a multiple of 8 up to %d", hidden, kMaxHidden);
+    if (hidden < 8 || hidden % 8 || hidden > 256)
+        return fail(FZ_ERR_UNSUPPORTED, "hidden width %d: need a multiple of 8 up to 256", hidden);
     if (!x1 || !dout || !W1 || !W2 || !dx1 || !dW1 || !dW2) return fail(FZ_ERR_INVALID, "null buffer");
     if (misaligned(x1) || misaligned(dout) || misaligned(dx1)) return fail(FZ_ERR_INVALID, "buffers must be 8-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
@@ -748,18 +756,24 @@ int fz_mlp_backward(const float* x1, const float* dout, const float* gamma, cons
     if (dgamma) FZ_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, kC * sizeof(float), st));
     if (dbeta) FZ_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, kC * sizeof(float), st));
     if (batch == 0 || voxels == 0) return FZ_OK;
-    const size_t smem = mlp_bwd_smem(hidden);
-    static size_t configured = 0;
-    if (smem > configured) {
-        FZ_CUDA_CHECK(cudaFuncSetAttribute(mlp_bwd<kC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
     const int tps = (int)((voxels + kTV - 1) / kTV);
     const long long tiles = batch * tps;
     const unsigned blocks = (unsigned)(tiles < sm_count() ? tiles : sm_count());
-    mlp_bwd<kC><<<blocks, kTT, smem, st>>>(x1, dout, gamma, beta, W1, b1, W2, dx1, dgamma, dbeta, dW1, db1, dW2, db2, hidden, voxels,
-                                           tps, tiles, eps);
-    FZ_LAUNCH_CHECK();
+    // the kernel holds the weights and weight-gradient accumulators of at most kMaxHidden hidden units in shared
+    // memory; wider MLPs (mlp_ratio 4: model_zoo/factorizer_brats23/configs/train.yaml) run slice by slice
+    for (int h0 = 0; h0 < hidden; h0 += kMaxHidden) {
+        const int hs = hidden - h0 < kMaxHidden ? hidden - h0 : kMaxHidden;
+        const size_t smem = mlp_bwd_smem(hs);
+        static size_t configured = 0;
+        if (smem > configured) {
+            FZ_CUDA_CHECK(cudaFuncSetAttribute(mlp_bwd<kC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        mlp_bwd<kC><<<blocks, kTT, smem, st>>>(x1, dout, gamma, beta, W1 + (size_t)h0 * kC, b1 ? b1 + h0 : nullptr, W2 + h0, dx1,
+                                               dgamma, dbeta, dW1 + (size_t)h0 * kC, db1 ? db1 + h0 : nullptr, dW2 + h0,
+                                               h0 == 0 ? db2 : nullptr, hs, hidden, h0 > 0, voxels, tps, tiles, eps);
+        FZ_LAUNCH_CHECK();
+    }
     return FZ_OK;
 }
 

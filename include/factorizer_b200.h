@@ -135,7 +135,7 @@ int fz_layernorm_cf_backward(const float* x, const float* gamma, const float* dy
  * weights squeezed to (out, in) (factorizer/layers/linear.py:43-50).  Gradient outputs are OVERWRITTEN. */
 
 /* 1 if the four kernels below handle this block: 32 channels, an even number of voxels, MLP hidden width a
- * multiple of 8 up to 64. */
+ * multiple of 8 up to 256 (the backward runs in slices of 64 hidden units). */
 int fz_glue_supported(int32_t channels, int32_t hidden, int64_t voxels);
 
 /* z = W LN(x): norm1 + bias-free in_proj (factorizer/factorizer.py:26,38,75; layers/norm.py:29-34). */

@@ -76,6 +76,9 @@ BLOCK_CASES = {
     # sample (a partial 512-voxel tile) and 8x64 windows (generic core kernels)
     "block_c32_16": dict(channels=32, spatial=(16, 16, 16), batch=1, mlp_ratio=2,
                          kw=dict(head_dim=8, patch_size=8), nmf=dict(rank=1, num_iters=5, init="uniform", solver="hals")),
+    # mlp_ratio 4 as in model_zoo/factorizer_brats23/configs/train.yaml: hidden width 128 = two slices of the MLP backward
+    "block_c32_r4": dict(channels=32, spatial=(8, 8, 8), batch=2, mlp_ratio=4,
+                         kw=dict(head_dim=8, patch_size=8), nmf=dict(rank=1, num_iters=5, init="uniform", solver="hals")),
     "block_c32_p4": dict(channels=32, spatial=(4, 8, 12), batch=2, mlp_ratio=1.5,
                          kw=dict(head_dim=8, patch_size=4), nmf=dict(rank=1, num_iters=5, init="uniform", solver="hals")),
 }

@@ -246,8 +246,9 @@ def _glue_call(fn, *args):
     L.check(fn(*[a.data_ptr() if isinstance(a, torch.Tensor) else a for a in args]))
 
 
+@pytest.mark.parametrize("HID", [48, 136])
 @pytest.mark.parametrize("shape", [(1, 32, 8, 8, 8), (2, 32, 6, 10, 7), (3, 32, 1030)])
-def test_glue_kernels_against_torch_fp64(ft, dev, shape):
+def test_glue_kernels_against_torch_fp64(ft, dev, shape, HID):
     """Each kernel of csrc/fz_block_glue.cu through the C ABI against fp64 torch autograd of the same
     layers (LayerNorm over channels, k=1 Conv1d, exact GELU: the reference's factorizer/layers/*)."""
     from factorizer_b200 import _lib as L
@@ -257,7 +258,6 @@ def test_glue_kernels_against_torch_fp64(ft, dev, shape):
     vox = int(np.prod(shape[2:]))
     if vox % 2:
         pytest.skip("odd voxel count")
-    HID = 48
     st = torch.cuda.current_stream().cuda_stream
     r = lambda *s: torch.randn(*s, device=dev)
     x, m, gout = 2 * r(B, C, vox) + 0.5, r(B, C, vox), r(B, C, vox)
@@ -321,7 +321,8 @@ def test_glue_rejects_unsupported(ft, dev):
     from factorizer_b200 import _lib as L
     lib = L.lib()
     assert lib.fz_glue_supported(32, 64, 512) == 1
-    assert lib.fz_glue_supported(16, 32, 512) == 0 and lib.fz_glue_supported(32, 128, 512) == 0
+    assert lib.fz_glue_supported(16, 32, 512) == 0 and lib.fz_glue_supported(32, 128, 512) == 1
+    assert lib.fz_glue_supported(32, 264, 512) == 0 and lib.fz_glue_supported(32, 60, 512) == 0
     assert lib.fz_glue_supported(32, 64, 511) == 0
     x = torch.zeros(1, 16, 64, device=dev)
     with pytest.raises(NotImplementedError):
