@@ -692,11 +692,8 @@ int fz_mixer_mlp_forward(const float* x, const float* m, const float* Wout, cons
     if (misaligned(x) || misaligned(m) || misaligned(out) || misaligned(x1)) return fail(FZ_ERR_INVALID, "buffers must be 8-byte aligned");
     if (batch == 0 || voxels == 0) return FZ_OK;
     const size_t smem = mlp_fwd_smem(hidden);
-    static size_t configured = 0;
-    if (smem > configured) {
-        FZ_CUDA_CHECK(cudaFuncSetAttribute(mixer_mlp_fwd<kC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static SmemConfig cfg;
+    FZ_CUDA_CHECK(cfg.ensure(mixer_mlp_fwd<kC>, smem));
     const long long pps = voxels / 2, total = batch * pps;
     long long blocks = (total + 127) / 128;
     const long long cap = 2LL * sm_count();
@@ -721,12 +718,9 @@ int fz_linear_backward(const float* dy, const float* a, const float* gamma, cons
     if (dbeta) FZ_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, kC * sizeof(float), st));
     if (batch == 0 || voxels == 0) return FZ_OK;
     const size_t smem = linear_bwd_smem();
-    static bool configured = false;
-    if (!configured) {
-        FZ_CUDA_CHECK(cudaFuncSetAttribute(linear_bwd<kC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        FZ_CUDA_CHECK(cudaFuncSetAttribute(linear_bwd<kC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static SmemConfig cfg_ln, cfg_plain;
+    FZ_CUDA_CHECK(cfg_ln.ensure(linear_bwd<kC, true>, smem));
+    FZ_CUDA_CHECK(cfg_plain.ensure(linear_bwd<kC, false>, smem));
     const int tps = (int)((voxels + kLV - 1) / kLV);
     const long long tiles = batch * tps;
     const unsigned blocks = (unsigned)(tiles < 2LL * sm_count() ? tiles : 2LL * sm_count());
@@ -764,11 +758,8 @@ int fz_mlp_backward(const float* x1, const float* dout, const float* gamma, cons
     for (int h0 = 0; h0 < hidden; h0 += kMaxHidden) {
         const int hs = hidden - h0 < kMaxHidden ? hidden - h0 : kMaxHidden;
         const size_t smem = mlp_bwd_smem(hs);
-        static size_t configured = 0;
-        if (smem > configured) {
-            FZ_CUDA_CHECK(cudaFuncSetAttribute(mlp_bwd<kC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
+        static SmemConfig cfg;
+        FZ_CUDA_CHECK(cfg.ensure(mlp_bwd<kC>, smem));
         mlp_bwd<kC><<<blocks, kTT, smem, st>>>(x1, dout, gamma, beta, W1 + (size_t)h0 * kC, b1 ? b1 + h0 : nullptr, W2 + h0, dx1,
                                                dgamma, dbeta, dW1 + (size_t)h0 * kC, db1 ? db1 + h0 : nullptr, dW2 + h0,
                                                h0 == 0 ? db2 : nullptr, hs, hidden, h0 > 0, voxels, tps, tiles, eps);

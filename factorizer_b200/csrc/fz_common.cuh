@@ -32,6 +32,24 @@ int fail(int code, const char* fmt, ...);
         FZ_CUDA_CHECK(cudaGetLastError());                                                      \
     } while (0)
 
+// Per-device high-water mark of the dynamic shared memory a kernel has been configured for
+// (cudaFuncSetAttribute applies to the current device only).  Not synchronised: the worst case is a repeated,
+// idempotent attribute call.
+struct SmemConfig {
+    size_t bytes[64] = {0};
+    template <typename K>
+    cudaError_t ensure(K kernel, size_t need) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        size_t& have = bytes[dev & 63];
+        if (need <= have) return cudaSuccess;
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+        if (e == cudaSuccess) have = need;
+        return e;
+    }
+};
+
 // ---- device-side geometry ----------------------------------------------------------------------
 // Derived from fz_geom once on the host; passed to kernels by value.
 struct DevGeom {

@@ -55,8 +55,9 @@ __device__ __forceinline__ float group_sum(float v) {
 template <int M, int CPL, int L>
 struct Locator {
     int rel[CPL];     // offset of column 2 ((k >> 1) L + lane) + (k & 1) relative to the window origin (no wrap)
-    int q[CPL];       // its (q0, q1, q2) packed 10 bits each
+    int lane_;
     __device__ __forceinline__ void init(const SmallParams& P, int lane) {
+        lane_ = lane;
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
             const int j = 2 * ((k >> 1) * L + lane) + (k & 1);
@@ -65,10 +66,8 @@ struct Locator {
                 const int t = j / P.G.p[2];
                 const int q1 = t % P.G.p[1], q0 = t / P.G.p[1];
                 rel[k] = (q0 * P.G.n[1] + q1) * P.G.n[2] + q2;
-                q[k] = q0 | (q1 << 10) | (q2 << 20);
             } else {
                 rel[k] = j;
-                q[k] = 0;
             }
         }
     }
@@ -93,8 +92,10 @@ struct Locator {
             for (int k = 0; k < CPL; ++k) off[k] = org + rel[k];
         } else {
 #pragma unroll
-            for (int k = 0; k < CPL; ++k) {
-                int i0 = o0 + (q[k] & 1023), i1 = o1 + ((q[k] >> 10) & 1023), i2 = o2 + (q[k] >> 20);
+            for (int k = 0; k < CPL; ++k) {       // a window that wraps around the volume: rare, index math redone
+                const int j = 2 * ((k >> 1) * L + lane_) + (k & 1);
+                const int q2 = j % G.p[2], tq = j / G.p[2];
+                int i0 = o0 + tq / G.p[1], i1 = o1 + tq % G.p[1], i2 = o2 + q2;
                 if (i0 < 0) i0 += G.n[0];
                 if (i1 < 0) i1 += G.n[1];
                 if (i2 < 0) i2 += G.n[2];
@@ -170,49 +171,46 @@ __device__ __forceinline__ void step_v(const f2 (&x)[M][H], const float (&u)[M],
     }
 }
 
-// x / S: exact multiplication when S is a power of two, true division otherwise (operations.py:433)
-__device__ __forceinline__ float div_sets(float v, int S, float inv) {
-    return (S & (S - 1)) ? __fdiv_rn(v, (float)S) : v * inv;
-}
-
 template <int M, int CPL, int L>
-__global__ void __launch_bounds__(kSmallThreads) small_fwd(const SmallParams P) {
+__global__ void __launch_bounds__(kSmallThreads, 3) small_fwd(const SmallParams P) {
     constexpr int H = CPL / 2;
     const int lane = threadIdx.x & (L - 1);
     const long long groups = (long long)gridDim.x * (kSmallThreads / L);
     const long long g0 = ((long long)blockIdx.x * kSmallThreads + threadIdx.x) / L;
     Locator<M, CPL, L> loc;
     loc.init(P, lane);
-    float u0r[M];
-    f2 v0r[H];
-#pragma unroll
-    for (int i = 0; i < M; ++i) u0r[i] = __ldg(P.u0 + i);
-#pragma unroll
-    for (int k = 0; k < H; ++k) v0r[k] = __ldg(reinterpret_cast<const f2*>(P.v0) + k * L + lane);
-    const long long stride = P.window ? P.G.vox : (long long)CPL * L;
+    const int istride = P.window ? (int)P.G.vox : CPL * L;
     const float invS = 1.f / (float)P.S;
+    const float lo = P.relu ? 0.f : -__int_as_float(0x7f800000);
     for (long long first = 0; first < P.n; first += groups) {      // trip count is uniform across the warp
         const long long mid = first + g0;
         const bool valid = mid < P.n;
         int off[CPL];
         const long long base = loc.locate(P, valid ? mid : 0, off);
+        // every load is issued unconditionally (an idle sub-warp re-reads matrix 0) and back to back: the kernel lives
+        // on memory-level parallelism; 32-bit element offsets, one IMAD.WIDE per address
         const float* src = P.x + base;
         f2 x[M][H];
+        constexpr int RB = 16 / CPL > 0 ? 16 / CPL : 1;      // rows per batch of 16 loads
+#pragma unroll
+        for (int ib = 0; ib < M; ib += RB) {
+#pragma unroll
+            for (int i = ib; i < ib + RB; ++i)
+#pragma unroll
+                for (int k = 0; k < H; ++k)
+                    x[i][k] = make_float2(__ldg(src + (i * istride + off[2 * k])), __ldg(src + (i * istride + off[2 * k + 1])));
+            asm volatile("" ::: "memory");              // keep the batches (and their 64-bit addresses) apart
+        }
 #pragma unroll
         for (int i = 0; i < M; ++i)
 #pragma unroll
-            for (int k = 0; k < H; ++k) {
-                float t0 = valid ? __ldg(src + i * stride + off[2 * k]) : 0.f;
-                float t1 = valid ? __ldg(src + i * stride + off[2 * k + 1]) : 0.f;
-                if (P.relu) { t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f); }
-                x[i][k] = make_float2(t0, t1);
-            }
+            for (int k = 0; k < H; ++k) x[i][k] = make_float2(fmaxf(x[i][k].x, lo), fmaxf(x[i][k].y, lo));
         float u[M], a[M], b, d;
         f2 v[H], c[H];
 #pragma unroll
-        for (int i = 0; i < M; ++i) u[i] = u0r[i];
+        for (int i = 0; i < M; ++i) u[i] = __ldg(P.u0 + i);          // L1-resident; not worth 16 registers for the whole kernel
 #pragma unroll
-        for (int k = 0; k < H; ++k) v[k] = v0r[k];
+        for (int k = 0; k < H; ++k) v[k] = __ldg(reinterpret_cast<const f2*>(P.v0) + k * L + lane);
         for (int t = 0; t < P.T; ++t) {
             step_u<M, H, L>(x, v, u, a, b, P.kind, P.eps);
             step_v<M, H>(x, u, v, c, d, P.kind, P.eps);
@@ -220,17 +218,27 @@ __global__ void __launch_bounds__(kSmallThreads) small_fwd(const SmallParams P) 
         if (valid) {
             const bool add = P.window && P.set > 0, last = P.window && P.set == P.S - 1 && P.S > 1;
             float* dstb = P.out + base;
+            const float fin = last ? ((P.S & (P.S - 1)) ? 0.f : invS) : 1.f;    // 0: true division below
+            int is2 = istride;
+            asm volatile("" : "+r"(is2));                 // recompute the 64 offsets here instead of carrying them in registers
 #pragma unroll
-            for (int i = 0; i < M; ++i)
+            for (int i = 0; i < M; ++i) {                 // one channel row at a time: read-add-store
+                f2 y[H];
+#pragma unroll
+                for (int k = 0; k < H; ++k) y[k] = make_float2(0.f, 0.f);
+                if (add) {
+#pragma unroll
+                    for (int k = 0; k < H; ++k) y[k] = make_float2(dstb[i * is2 + off[2 * k]], dstb[i * is2 + off[2 * k + 1]]);
+                }
 #pragma unroll
                 for (int k = 0; k < H; ++k) {
-                    float* d0 = dstb + i * stride + off[2 * k];
-                    float* d1 = dstb + i * stride + off[2 * k + 1];
-                    float y0 = u[i] * v[k].x, y1 = u[i] * v[k].y;
-                    if (add) { y0 = __fadd_rn(*d0, y0); y1 = __fadd_rn(*d1, y1); }
-                    if (last) { y0 = div_sets(y0, P.S, invS); y1 = div_sets(y1, P.S, invS); }
-                    *d0 = y0; *d1 = y1;
+                    float y0 = __fadd_rn(y[k].x, u[i] * v[k].x), y1 = __fadd_rn(y[k].y, u[i] * v[k].y);
+                    if (fin == 0.f) { y0 = __fdiv_rn(y0, (float)P.S); y1 = __fdiv_rn(y1, (float)P.S); }
+                    else { y0 *= fin; y1 *= fin; }
+                    dstb[i * is2 + off[2 * k]] = y0;
+                    dstb[i * is2 + off[2 * k + 1]] = y1;
                 }
+            }
         }
     }
 }
@@ -259,7 +267,8 @@ __global__ void __launch_bounds__(kSmallThreads) small_bwd(const SmallParams P) 
     for (int i = 0; i < M; ++i) u0r[i] = __ldg(P.u0 + i);
 #pragma unroll
     for (int k = 0; k < H; ++k) v0r[k] = __ldg(reinterpret_cast<const f2*>(P.v0) + k * L + lane);
-    const long long stride = P.window ? P.G.vox : (long long)CPL * L;
+    const int istride = P.window ? (int)P.G.vox : CPL * L;
+    const float lo = P.relu ? 0.f : -__int_as_float(0x7f800000);
     const float eps = P.eps;
     const int T = P.T, K = P.K;
     const float invS = 1.f / (float)P.S;
@@ -272,20 +281,26 @@ __global__ void __launch_bounds__(kSmallThreads) small_bwd(const SmallParams P) 
         const long long base = loc.locate(P, valid ? mid : 0, off);
         const float* src = P.x + base;
         f2 x[M][H];
+        constexpr int RB = 16 / CPL > 0 ? 16 / CPL : 1;      // rows per batch of 16 loads
+#pragma unroll
+        for (int ib = 0; ib < M; ib += RB) {
+#pragma unroll
+            for (int i = ib; i < ib + RB; ++i)
+#pragma unroll
+                for (int k = 0; k < H; ++k)
+                    x[i][k] = make_float2(__ldg(src + (i * istride + off[2 * k])), __ldg(src + (i * istride + off[2 * k + 1])));
+            asm volatile("" ::: "memory");              // keep the batches (and their 64-bit addresses) apart
+        }
         unsigned long long mask = 0;       // x > 0 before the ReLU (M*CPL = 64 bits)
 #pragma unroll
         for (int i = 0; i < M; ++i)
 #pragma unroll
             for (int k = 0; k < H; ++k) {
-                float t0 = valid ? __ldg(src + i * stride + off[2 * k]) : 0.f;
-                float t1 = valid ? __ldg(src + i * stride + off[2 * k + 1]) : 0.f;
-                if (P.relu) {
-                    if (t0 > 0.f) mask |= 1ULL << (i * CPL + 2 * k);
-                    if (t1 > 0.f) mask |= 1ULL << (i * CPL + 2 * k + 1);
-                    t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f);
-                }
-                x[i][k] = make_float2(t0, t1);
+                if (x[i][k].x > 0.f) mask |= 1ULL << (i * CPL + 2 * k);
+                if (x[i][k].y > 0.f) mask |= 1ULL << (i * CPL + 2 * k + 1);
+                x[i][k] = make_float2(fmaxf(x[i][k].x, lo), fmaxf(x[i][k].y, lo));
             }
+        if (!P.relu) mask = ~0ULL;
         // ---- recompute the iterates; u_t, v_t (t = 0..T) go to this sub-warp's slice of shared memory ----
         {
             float u[M];
@@ -314,15 +329,26 @@ __global__ void __launch_bounds__(kSmallThreads) small_bwd(const SmallParams P) 
         f2 xb[M][H];                       // dL/dx accumulator; first holds dL/dy
         {
             const float* gsrc = P.gy + base;
+            int is3 = istride;
+            asm volatile("" : "+r"(is3));
 #pragma unroll
-            for (int i = 0; i < M; ++i)
+            for (int ib = 0; ib < M; ib += RB) {
 #pragma unroll
-                for (int k = 0; k < H; ++k) {
-                    float g0v = valid ? __ldg(gsrc + i * stride + off[2 * k]) : 0.f;
-                    float g1v = valid ? __ldg(gsrc + i * stride + off[2 * k + 1]) : 0.f;
-                    if (P.window) { g0v = div_sets(g0v, P.S, invS); g1v = div_sets(g1v, P.S, invS); }
-                    xb[i][k] = make_float2(g0v, g1v);
-                }
+                for (int i = ib; i < ib + RB; ++i)
+#pragma unroll
+                    for (int k = 0; k < H; ++k)
+                        xb[i][k] = make_float2(__ldg(gsrc + (i * is3 + off[2 * k])), __ldg(gsrc + (i * is3 + off[2 * k + 1])));
+                asm volatile("" ::: "memory");
+            }
+            if (P.window) {
+                const bool pow2 = !(P.S & (P.S - 1));
+#pragma unroll
+                for (int i = 0; i < M; ++i)
+#pragma unroll
+                    for (int k = 0; k < H; ++k)
+                        xb[i][k] = pow2 ? make_float2(xb[i][k].x * invS, xb[i][k].y * invS)
+                                        : make_float2(__fdiv_rn(xb[i][k].x, (float)P.S), __fdiv_rn(xb[i][k].y, (float)P.S));
+            }
         }
         float ub[M];
         f2 vb[H];
@@ -465,20 +491,25 @@ __global__ void __launch_bounds__(kSmallThreads) small_bwd(const SmallParams P) 
         if (valid) {
             const bool add = P.window && P.set > 0;
             float* dstb = P.out + base;
+            int is2 = istride;
+            asm volatile("" : "+r"(is2));
 #pragma unroll
-            for (int i = 0; i < M; ++i)
+            for (int i = 0; i < M; ++i) {
+                f2 o[H];
+#pragma unroll
+                for (int k = 0; k < H; ++k) o[k] = make_float2(0.f, 0.f);
+                if (add) {
+#pragma unroll
+                    for (int k = 0; k < H; ++k) o[k] = make_float2(dstb[i * is2 + off[2 * k]], dstb[i * is2 + off[2 * k + 1]]);
+                }
 #pragma unroll
                 for (int k = 0; k < H; ++k) {
-                    float* d0 = dstb + i * stride + off[2 * k];
-                    float* d1 = dstb + i * stride + off[2 * k + 1];
-                    float g0v = xb[i][k].x, g1v = xb[i][k].y;
-                    if (P.relu) {
-                        if (!((mask >> (i * CPL + 2 * k)) & 1ULL)) g0v = 0.f;
-                        if (!((mask >> (i * CPL + 2 * k + 1)) & 1ULL)) g1v = 0.f;
-                    }
-                    if (add) { g0v = __fadd_rn(*d0, g0v); g1v = __fadd_rn(*d1, g1v); }
-                    *d0 = g0v; *d1 = g1v;
+                    const float g0v = ((mask >> (i * CPL + 2 * k)) & 1ULL) ? xb[i][k].x : 0.f;
+                    const float g1v = ((mask >> (i * CPL + 2 * k + 1)) & 1ULL) ? xb[i][k].y : 0.f;
+                    dstb[i * is2 + off[2 * k]] = __fadd_rn(o[k].x, g0v);
+                    dstb[i * is2 + off[2 * k + 1]] = __fadd_rn(o[k].y, g1v);
                 }
+            }
         }
     }
 }
@@ -502,11 +533,8 @@ int launch_small(const SmallParams& P, bool bwd, cudaStream_t st) {
     if (ctas > cap) ctas = cap;
     if (bwd) {
         const size_t smem = sizeof(float) * Hist<M, CPL, L>::floats * (kSmallThreads / L);
-        static bool configured = false;
-        if (!configured) {
-            FZ_CUDA_CHECK(cudaFuncSetAttribute(small_bwd<M, CPL, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
-        }
+        static SmemConfig cfg;
+        FZ_CUDA_CHECK(cfg.ensure(small_bwd<M, CPL, L>, smem));
         small_bwd<M, CPL, L><<<(unsigned)ctas, kSmallThreads, smem, st>>>(P);
     } else {
         small_fwd<M, CPL, L><<<(unsigned)ctas, kSmallThreads, 0, st>>>(P);
@@ -543,6 +571,7 @@ bool small_window_supported(const DevGeom& G, const fz_solver& s) {
     if (!small_supported(G.d, G.P, s)) return false;
     for (int k = 0; k < 3; ++k)
         if (G.p[k] > 1023 || G.n[k] > (1 << 20)) return false;
+    if ((long long)G.d * G.vox >= (1LL << 31)) return false;      // 32-bit element offsets inside a (batch, head) slab
     return G.mats_per_shift > 0;
 }
 
