@@ -60,6 +60,7 @@ def cpu_reference_rate(sample_n: int, reps: int):
 
     from oracle import c_oracle
 
+    c_oracle.use_all_cores()
     rng = np.random.default_rng(0)
     x = rng.random((1, C, sample_n, sample_n, sample_n), dtype=np.float32)
     gy = rng.standard_normal(x.shape, dtype=np.float32)

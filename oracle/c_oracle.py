@@ -67,3 +67,13 @@ def swnmf_backward(x, gy, v0, head_dim, patch, shifts, relu=True, num_iters=5, n
 
 def num_threads() -> int:
     return int(lib().fzo_num_threads())
+
+
+def use_all_cores() -> int:
+    """Run the OpenMP loops on every core this process may use (launchers such as torchrun set OMP_NUM_THREADS=1)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().fzo_set_num_threads(int(n))
+    return num_threads()

@@ -47,6 +47,15 @@ static void window_offsets(const fzo_geom* g, int s, int w, int* off) {
     }
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the benchmark's CPU legs ask for all host cores explicitly */
+void fzo_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int fzo_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
