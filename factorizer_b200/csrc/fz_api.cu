@@ -137,6 +137,7 @@ int fz_swnmf_forward(const float* x, const float* u0, const float* v0, float* y,
     if (int e = make_dev_geom(g, &G)) return e;
     int K;
     if (int e = check_solver(s, G.d, G.P, &K)) return e;
+    if (G.B == 0) return FZ_OK;                       // empty batch: tensors carry null data pointers
     if (!x || !u0 || !v0 || !y) return fail(FZ_ERR_INVALID, "null buffer");
     if ((g_forced_path == -1 || g_forced_path == 2) && phase_supported(G, *s, relu_input)) {
         tls().path = 2;
@@ -173,6 +174,7 @@ int fz_swnmf_backward(const float* x, const float* gy, const float* u0, const fl
     if (int e = make_dev_geom(g, &G)) return e;
     int K;
     if (int e = check_solver(s, G.d, G.P, &K)) return e;
+    if (G.B == 0) return FZ_OK;
     if (!x || !gy || !u0 || !v0 || !gx) return fail(FZ_ERR_INVALID, "null buffer");
     if ((g_forced_path == -1 || g_forced_path == 2) && phase_supported(G, *s, relu_input)) {
         tls().path = 2;

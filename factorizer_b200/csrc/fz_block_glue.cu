@@ -670,9 +670,9 @@ int fz_ln_linear_forward(const float* x, const float* gamma, const float* beta, 
                          int32_t channels, int64_t voxels, float eps, void* stream) {
     tls().launches = 0;
     if (int e = check_common(batch, channels, voxels)) return e;
+    if (batch == 0 || voxels == 0) return FZ_OK;          // empty tensors carry null data pointers
     if (!x || !W || !y) return fail(FZ_ERR_INVALID, "null buffer");
     if (misaligned(x) || misaligned(y)) return fail(FZ_ERR_INVALID, "buffers must be 8-byte aligned");
-    if (batch == 0 || voxels == 0) return FZ_OK;
     const long long pps = voxels / 2, total = batch * pps;
     long long blocks = (total + 127) / 128;
     const long long cap = 3LL * sm_count();
@@ -688,9 +688,9 @@ int fz_mixer_mlp_forward(const float* x, const float* m, const float* Wout, cons
     tls().launches = 0;
     if (int e = check_common(batch, channels, voxels)) return e;
     if (hidden < 8 || hidden % 8 || hidden > 256) return fail(FZ_ERR_UNSUPPORTED, "hidden width %d: need a multiple of 8 up to 256", hidden);
+    if (batch == 0 || voxels == 0) return FZ_OK;
     if (!x || !m || !Wout || !W1 || !W2 || !out) return fail(FZ_ERR_INVALID, "null buffer");
     if (misaligned(x) || misaligned(m) || misaligned(out) || misaligned(x1)) return fail(FZ_ERR_INVALID, "buffers must be 8-byte aligned");
-    if (batch == 0 || voxels == 0) return FZ_OK;
     const size_t smem = mlp_fwd_smem(hidden);
     static SmemConfig cfg;
     FZ_CUDA_CHECK(cfg.ensure(mixer_mlp_fwd<kC>, smem));
@@ -709,7 +709,8 @@ int fz_linear_backward(const float* dy, const float* a, const float* gamma, cons
                        int32_t channels, int64_t voxels, float eps, int32_t layernorm, void* stream) {
     tls().launches = 0;
     if (int e = check_common(batch, channels, voxels)) return e;
-    if (!dy || !a || !W || !da || !dW) return fail(FZ_ERR_INVALID, "null buffer");
+    const bool empty = batch == 0 || voxels == 0;
+    if (!W || !dW || (!empty && (!dy || !a || !da))) return fail(FZ_ERR_INVALID, "null buffer");
     if (misaligned(dy) || misaligned(a) || misaligned(da) || misaligned(resid)) return fail(FZ_ERR_INVALID, "buffers must be 8-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     FZ_CUDA_CHECK(cudaMemsetAsync(dW, 0, kC * kC * sizeof(float), st));
@@ -740,7 +741,8 @@ int fz_mlp_backward(const float* x1, const float* dout, const float* gamma, cons
     if (int e = check_common(batch, channels, voxels)) return e;
     if (hidden < 8 || hidden % 8 || hidden > 256)
         return fail(FZ_ERR_UNSUPPORTED, "hidden width %d: need a multiple of 8 up to 256", hidden);
-    if (!x1 || !dout || !W1 || !W2 || !dx1 || !dW1 || !dW2) return fail(FZ_ERR_INVALID, "null buffer");
+    const bool empty = batch == 0 || voxels == 0;
+    if (!W1 || !W2 || !dW1 || !dW2 || (!empty && (!x1 || !dout || !dx1))) return fail(FZ_ERR_INVALID, "null buffer");
     if (misaligned(x1) || misaligned(dout) || misaligned(dx1)) return fail(FZ_ERR_INVALID, "buffers must be 8-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     FZ_CUDA_CHECK(cudaMemsetAsync(dW1, 0, (size_t)hidden * kC * sizeof(float), st));

@@ -181,8 +181,8 @@ int fz_layernorm_cf_supported(int32_t channels, int64_t voxels) {
 int fz_layernorm_cf_forward(const float* x, const float* gamma, const float* beta, float* y, int64_t batch,
                             int32_t channels, int64_t voxels, float eps, void* stream) {
     tls().launches = 0;
+    if (batch == 0 || voxels == 0) return FZ_OK;          // empty tensors carry null data pointers
     if (int e = check_args(x, y, batch, channels, voxels)) return e;
-    if (batch == 0 || voxels == 0) return FZ_OK;
     cudaStream_t st = (cudaStream_t)stream;
     switch (channels) {
         case 8: return launch_fwd<8>(x, gamma, beta, y, batch, voxels, eps, st);
@@ -194,14 +194,14 @@ int fz_layernorm_cf_forward(const float* x, const float* gamma, const float* bet
 int fz_layernorm_cf_backward(const float* x, const float* gamma, const float* dy, float* dx, float* dgamma,
                              float* dbeta, int64_t batch, int32_t channels, int64_t voxels, float eps, void* stream) {
     tls().launches = 0;
-    if (int e = check_args(x, dx, batch, channels, voxels)) return e;
-    if (!dy) return fail(FZ_ERR_INVALID, "null buffer");
     cudaStream_t st = (cudaStream_t)stream;
     if (batch == 0 || voxels == 0) {
         if (dgamma) FZ_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, channels * sizeof(float), st));
         if (dbeta) FZ_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, channels * sizeof(float), st));
         return FZ_OK;
     }
+    if (int e = check_args(x, dx, batch, channels, voxels)) return e;
+    if (!dy) return fail(FZ_ERR_INVALID, "null buffer");
     switch (channels) {
         case 8: return launch_bwd<8>(x, gamma, dy, dx, dgamma, dbeta, batch, voxels, eps, st);
         case 16: return launch_bwd<16>(x, gamma, dy, dx, dgamma, dbeta, batch, voxels, eps, st);

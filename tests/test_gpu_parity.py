@@ -241,6 +241,40 @@ def test_factorizer_model_matches_reference(ft, dev, golden, name):
         assert_close(_np(gp) / scale, ref / scale, rtol=2e-4, atol=2e-4, what=f"grad {k}")
 
 
+def test_block_path_choice_and_edge_inputs(ft, dev):
+    """README.md:56-73 block (dropout 0.1): training mode keeps the layer-by-layer path (dropout masks come from
+    torch), eval mode and dropout 0 take the fused kernels and agree with the layer-by-layer result; an empty batch
+    and a non-contiguous input go through the fused path too."""
+    torch.manual_seed(5)
+    mk = lambda p: ft.FactorizerBlock(channels=32, spatial_size=(8, 8, 16), norm=ft.LayerNorm,
+                                      reshape=(ft.SWMatricize, {"head_dim": 8, "patch_size": 8}), act=nn.ReLU,
+                                      factorize=ft.NMF, rank=1, num_iters=5, init="uniform", solver="hals", mlp_ratio=2,
+                                      dropout=p).to(dev)
+    blk = mk(0.1)
+    x = torch.randn(2, 32, 8, 8, 16, device=dev, requires_grad=True)
+    assert blk.training and blk._fused_args(x) is None
+    assert torch.isfinite(blk(x)).all()
+    blk.eval()
+    assert blk._fused_args(x) is not None
+    y = blk(x)
+    (gx,) = torch.autograd.grad(y.square().sum(), x)
+    # the same block, layer by layer (fused core + library GEMMs), as the reference composes it
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    y2 = x + blk.fact(blk.norm1(x))
+    y2 = y2 + blk.mlp(blk.norm2(y2))
+    (gx2,) = torch.autograd.grad(y2.square().sum(), x)
+    assert_close(_np(y), _np(y2), what="fused vs layer-by-layer y")
+    assert_close(_np(gx), _np(gx2), rtol=2e-4, atol=2e-4, what="fused vs layer-by-layer gx")
+    # non-contiguous input view
+    xt = torch.randn(2, 32, 8, 16, 8, device=dev).transpose(3, 4)
+    assert not xt.is_contiguous()
+    assert torch.equal(blk(xt), blk(xt.contiguous()))
+    # empty batch
+    e = blk(torch.empty(0, 32, 8, 8, 16, device=dev))
+    assert e.shape == (0, 32, 8, 8, 16)
+
+
 def _glue_call(fn, *args):
     from factorizer_b200 import _lib as L
     L.check(fn(*[a.data_ptr() if isinstance(a, torch.Tensor) else a for a in args]))
