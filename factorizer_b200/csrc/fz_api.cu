@@ -21,6 +21,16 @@ int fail(int code, const char* fmt, ...) {
 
 static volatile int g_forced_path = -1;  // process-wide: autograd runs backward on its own thread
 
+// One window per (sample, head), no roll, and more elements than a CTA can hold: Matricize(grid_size=1), the
+// reference's default FactMixer reshape (factorizer/factorizer.py:17).  The matrix is the contiguous block
+// x[b, h*d:(h+1)*d, :].
+static bool big_window(const DevGeom& G, const fz_solver& s) {
+    if (G.G != 1 || G.S != 1) return false;
+    for (int k = 0; k < 3; ++k)
+        if (G.sh[0][k] % G.n[k]) return false;
+    return (long long)G.d * G.P >= 16384 && big_supported(G.d, G.P, s);
+}
+
 int make_dev_geom(const fz_geom* g, DevGeom* o) {
     if (!g) return fail(FZ_ERR_INVALID, "null geometry");
     if (g->batch < 0 || g->channels < 1 || g->head_dim < 1)
@@ -112,6 +122,7 @@ size_t fz_swnmf_saved_bytes(const fz_geom* g, const fz_solver* s) {
     DevGeom G;
     if (make_dev_geom(g, &G) || !s) return 0;
     if (!phase_supported(G, *s, 1) && pairs_supported(G, *s, 1)) return pairs_saved_bytes(G, *s);
+    if (big_window(G, *s)) return big_saved_bytes(G.mats_per_shift, G.d, G.P, *s);
     return fast_saved_bytes(G, *s);
 }
 
@@ -124,6 +135,10 @@ size_t fz_swnmf_workspace_bytes(const fz_geom* g, const fz_solver* s) {
         if (b > a) a = b;
     } else if (pairs_supported(G, *s, 1)) {
         const size_t b = pairs_workspace_bytes(G, *s);
+        if (b > a) a = b;
+    }
+    if (big_window(G, *s)) {
+        const size_t b = big_workspace_bytes(G.mats_per_shift, G.d, G.P, *s);
         if (b > a) a = b;
     }
     return a;
@@ -156,6 +171,10 @@ int fz_swnmf_forward(const float* x, const float* u0, const float* v0, float* y,
     if (g_forced_path != 0 && small_window_supported(G, *s)) {
         tls().path = 3;
         return small_window(x, u0, v0, nullptr, y, G, *s, K, relu_input, false, (cudaStream_t)stream);
+    }
+    if (big_window(G, *s)) {
+        tls().path = 5;
+        return big_forward(x, u0, v0, y, saved, workspace, G.mats_per_shift, G.d, G.P, *s, relu_input, (cudaStream_t)stream);
     }
     tls().path = 0;
     NmfArgs a;
@@ -192,6 +211,11 @@ int fz_swnmf_backward(const float* x, const float* gy, const float* u0, const fl
     if (g_forced_path != 0 && small_window_supported(G, *s)) {
         tls().path = 3;
         return small_window(x, u0, v0, gy, gx, G, *s, K, relu_input, true, (cudaStream_t)stream);
+    }
+    if (big_window(G, *s)) {
+        tls().path = 5;
+        return big_backward(x, gy, u0, v0, saved, gx, workspace, G.mats_per_shift, G.d, G.P, *s, K, relu_input,
+                            (cudaStream_t)stream);
     }
     tls().path = 0;
     NmfArgs a;

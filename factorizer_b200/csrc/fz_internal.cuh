@@ -58,6 +58,16 @@ int phase_forward(const float* x, const float* v0, float* y, void* saved, void* 
 int phase_backward(const float* x, const float* gy, const float* v0, const void* saved, float* gx,
                    void* workspace, const DevGeom& G, const fz_solver& s, int K, cudaStream_t st);
 
+// fz_nmf_big.cu: rank-1 MU / HALS on matrices too large for one CTA (global Matricize: M channels x all voxels), one
+// grid-wide pass per sweep
+bool big_supported(int M, long long N, const fz_solver& s);
+size_t big_saved_bytes(long long n, int M, long long N, const fz_solver& s);
+size_t big_workspace_bytes(long long n, int M, long long N, const fz_solver& s);
+int big_forward(const float* x, const float* u0, const float* v0, float* y, void* saved, void* workspace, long long n, int M,
+                long long N, const fz_solver& s, int relu, cudaStream_t st);
+int big_backward(const float* x, const float* gy, const float* u0, const float* v0, const void* saved, float* gx,
+                 void* workspace, long long n, int M, long long N, const fz_solver& s, int K, int relu, cudaStream_t st);
+
 // ... and window sets that pair up as (a, a + patch/2): one octant problem per pair on the volume rolled by a
 bool pairs_supported(const DevGeom& G, const fz_solver& s, int relu);
 size_t pairs_saved_bytes(const DevGeom& G, const fz_solver& s);

@@ -170,7 +170,8 @@ int fz_linear_backward(const float* dy, const float* a, const float* gamma, cons
  * Swin-Factorizer block), 3 = the sub-warp-per-matrix register kernels for small matrices (64 columns with
  * 4..32 rows, 8x16, 8x128, 8x256; rank-1 HALS / MU, at most 5 sweeps; also used by fz_nmf_* when only y / dy
  * are involved), 4 = the octant kernels once per pair of window sets (a, a + patch/2) on the volume rolled by a
- * (e.g. shifts [0, 2, 4, 6]).  For tests and the benchmark's bookkeeping. */
+ * (e.g. shifts [0, 2, 4, 6]), 5 = one grid-wide pass per sweep for a single huge matrix per (sample, head)
+ * (Matricize(grid_size=1), rank-1 MU / HALS).  For tests and the benchmark's bookkeeping. */
 int fz_last_path(void);
 /* Number of kernel launches issued by the last fz_* call on this thread. */
 int fz_last_launches(void);

@@ -60,6 +60,14 @@ FUSED_CASES = {
                           nmf=dict(rank=1, num_iters=5, solver="hals"), relu=True, dist="randn"),
     "fused_global_mu": dict(x_shape=(2, 16, 8, 8, 8), cls="Matricize", kw=dict(num_heads=1, grid_size=1),
                             nmf=dict(rank=1, num_iters=5, solver="mu"), relu=True, dist="uniform"),
+    # reference default reshape (factorizer/factorizer.py:17, tests/test_factorizer.py:14-110) at sizes beyond one CTA:
+    # one grid-wide pass per sweep (csrc/fz_nmf_big.cu)
+    "fused_global_mu_big": dict(x_shape=(2, 16, 8, 16, 16), cls="Matricize", kw=dict(num_heads=1, grid_size=1),
+                                nmf=dict(rank=1, num_iters=5, solver="mu"), relu=True, dist="uniform"),
+    "fused_global_hals_big": dict(x_shape=(1, 32, 8, 8, 24), cls="Matricize", kw=dict(num_heads=1, grid_size=1),
+                                  nmf=dict(rank=1, num_iters=5, solver="hals"), relu=True, dist="randn"),
+    "fused_global_mu_k2": dict(x_shape=(1, 16, 16, 12, 24), cls="Matricize", kw=dict(num_heads=2, grid_size=1),
+                               nmf=dict(rank=1, num_iters=4, solver="mu", num_grad_steps=2), relu=False, dist="uniform"),
     "fused_mu_r2": dict(x_shape=(1, 16, 8, 8, 8), cls="SWMatricize", kw=dict(head_dim=8, patch_size=4),
                         nmf=dict(rank=2, num_iters=5, solver="mu"), relu=False, dist="uniform"),
     "fused_2d": dict(x_shape=(2, 16, 32, 32), cls="SWMatricize", kw=dict(head_dim=4, patch_size=8),

@@ -145,11 +145,13 @@ def test_kernel_path_selection(ft, dev, golden):
     """Which kernel family serves which geometry (fz_last_path): 2 = three-pass octant kernels (default Swin
     geometry), 4 = the same per pair of window sets on a rolled volume (brats23 shifts), 1 = window-at-a-time 8x512
     kernels (any other shifts), 3 = sub-warp register kernels (64-column
-    windows of the isles22 bundle / reference tests, small ft.NMF batches), 0 = generic shared-memory kernels."""
+    windows of the isles22 bundle / reference tests, small ft.NMF batches), 5 = one grid-wide pass per sweep for the
+    huge matrices of Matricize(grid_size=1), 0 = generic shared-memory kernels."""
     from factorizer_b200 import _lib, _ops
     lib = _lib.lib()
     want = {"fused_cfg2_16": 2, "fused_brats_s4": 4, "fused_isles_s4": 3, "fused_nh8_ps4": 3, "fused_2d": 3,
-            "fused_mu_r2": 0, "fused_global_mu": 0}
+            "fused_mu_r2": 0, "fused_global_mu": 0, "fused_global_mu_big": 5, "fused_global_hals_big": 5,
+            "fused_global_mu_k2": 5}
     for name, path in want.items():
         c = cases.FUSED_CASES[name]
         reshape, nmf = _fused_module(ft, c, golden["fused"], name, dev)
