@@ -25,14 +25,19 @@ CASES = [
     ("tests/test_factorizer.py: num_heads=8, patch 4 (4x64)", 3, 32, (64,) * 3, dict(num_heads=8, patch_size=4)),
     ("tests/test_factorizer.py stage 2 (8x64)", 3, 64, (32,) * 3, dict(num_heads=8, patch_size=4)),
     ("tests/test_factorizer.py stage 4 (32x64)", 3, 256, (8,) * 3, dict(num_heads=8, patch_size=4)),
+    ("default FactMixer reshape Matricize(num_heads=1, grid_size=1), MU (tests/test_factorizer.py:14-110)", 1, 16, (64,) * 3,
+     dict(cls="Matricize", num_heads=1, grid_size=1, solver="mu")),
+    ("same, 32 channels, batch 2, HALS", 2, 32, (64,) * 3, dict(cls="Matricize", num_heads=1, grid_size=1)),
 ]
-PATH = {0: "generic smem", 1: "window-at-a-time TMA", 2: "three-pass octant", 3: "sub-warp register", 4: "octant x pairs (rolled)"}
+PATH = {0: "generic smem", 1: "window-at-a-time TMA", 2: "three-pass octant", 3: "sub-warp register", 4: "octant x pairs (rolled)", 5: "grid-wide pass per sweep"}
 print("| geometry | x shape | matrix | windows | path | fwd us | bwd us | fwd+bwd % of HBM roofline |")
 print("|---|---|---|---|---|---|---|---|")
 for name, B, C, size, kw in CASES:
-    sw = ft.SWMatricize((None, C, *size), **kw)
+    kw = dict(kw)
+    cls, solver = kw.pop("cls", "SWMatricize"), kw.pop("solver", "hals")
+    sw = getattr(ft, cls)((None, C, *size), **kw)
     M, N = sw.output_size[2:]
-    nmf = ft.NMF((M, N), rank=1, num_iters=5, init='uniform', solver='hals').to(dev)
+    nmf = ft.NMF((M, N), rank=1, num_iters=5, init='uniform', solver=solver).to(dev)
     g, s = sw._geom.c_geom(B), nmf.solver_spec().c_solver()
     x = torch.rand(B, C, *size, device=dev); gy = torch.randn_like(x)
     y = torch.empty_like(x); gx = torch.empty_like(x)
