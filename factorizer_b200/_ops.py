@@ -160,6 +160,18 @@ def _flatten_batch(x: torch.Tensor, size) -> torch.Tensor:
     return x.reshape(-1, M, N)
 
 
+# a rank-1 matrix this large has no single-CTA kernel: it runs as the one-window-per-sample case of the fused core
+# (csrc/fz_nmf_big.cu), whose entry points carry the scratch buffers the grid-wide passes need
+_BIG_ELEMS = 16384
+
+
+def _as_one_window_volume(spec: SolverSpec, size):
+    M, N = size
+    if spec.rank != 1 or M * N < _BIG_ELEMS:
+        return None
+    return Geometry(channels=M, size=(N,), patch=(N,), head_dim=M, shifts=[(0,)])
+
+
 class NMFReconstruct(torch.autograd.Function):
     """MatrixFactorization.forward = reconstruct(decompose(x))
     (reference matrix_factorization.py:514-533, 544-546) as one kernel per direction."""
@@ -170,16 +182,24 @@ class NMFReconstruct(torch.autograd.Function):
         x3 = _flatten_batch(x, size)
         u0 = L.require_cuda_f32(u0, "u0")
         v0 = L.require_cuda_f32(v0, "v0")
-        _, _, y = _nmf_forward(x3, u0, v0, spec, want_uv=False, want_y=True)
-        ctx.save_for_backward(x3, u0, v0)
-        ctx.spec, ctx.shape = spec, x.shape
+        geom = _as_one_window_volume(spec, size) if x3.shape[0] > 0 else None
+        saved = None
+        if geom is not None:
+            y, saved = _swnmf_forward(x3, u0, v0, geom, spec, False, ctx.needs_input_grad[0])
+        else:
+            _, _, y = _nmf_forward(x3, u0, v0, spec, want_uv=False, want_y=True)
+        ctx.save_for_backward(x3, u0, v0, saved)
+        ctx.spec, ctx.shape, ctx.geom = spec, x.shape, geom
         return y.reshape(x.shape)
 
     @staticmethod
     def backward(ctx, gy):
-        x3, u0, v0 = ctx.saved_tensors
+        x3, u0, v0, saved = ctx.saved_tensors
         gy = L.require_cuda_f32(gy, "grad").reshape(x3.shape)
-        gx = _nmf_backward(x3, u0, v0, gy, None, None, ctx.spec)
+        if ctx.geom is not None:
+            gx = _swnmf_backward(x3, gy, u0, v0, saved, ctx.geom, ctx.spec, False)
+        else:
+            gx = _nmf_backward(x3, u0, v0, gy, None, None, ctx.spec)
         return gx.reshape(ctx.shape), None, None, None, None
 
 

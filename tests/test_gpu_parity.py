@@ -381,6 +381,28 @@ def test_reference_test_nmf_port(ft, dev):
     assert loss.shape == size[:1] and (loss >= 0).all()
 
 
+def test_standalone_nmf_on_large_matrices(ft, dev):
+    """ft.NMF on matrices beyond a CTA's shared memory (rank 1): forward and input gradient against the reference
+    golden of the identical computation through Matricize(num_heads=1, grid_size=1), which is a pure view."""
+    from factorizer_b200 import _lib
+    name = "fused_global_mu_big"
+    c = cases.FUSED_CASES[name]
+    import os
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "fused.npz"))
+    xs = c["x_shape"]
+    M, N = xs[1], int(np.prod(xs[2:]))
+    nmf = ft.NMF(size=(M, N), rank=1, num_iters=5, init="uniform", solver="mu")
+    nmf.load_state_dict({"init.u0": torch.from_numpy(gold[f"{name}/u0"]), "init.v0": torch.from_numpy(gold[f"{name}/v0"])})
+    nmf = nmf.to(dev)
+    x = torch.from_numpy(cases.make_array(name, xs, c["dist"])).to(dev).reshape(xs[0], M, N).requires_grad_(True)
+    gy = torch.from_numpy(cases.make_array(name, xs, "randn", tag="gy")).to(dev).reshape(xs[0], M, N)
+    y = nmf(x)                       # x >= 0 here, so the golden's ReLU is the identity
+    assert _lib.lib().fz_last_path() == 5
+    (gx,) = torch.autograd.grad((y * gy).sum(), x)
+    assert_close(_np(y).reshape(xs), gold[f"{name}/y"], what="y")
+    assert_close(_np(gx).reshape(xs), gold[f"{name}/gx"], what="gx")
+
+
 def test_empty_batch(ft, dev):
     nmf = ft.NMF(size=(8, 16), rank=1).to(dev)
     y = nmf(torch.empty(0, 8, 16, device=dev))
