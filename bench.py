@@ -99,6 +99,28 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_cpus(index: int):
+    """Run this rank on the CPU cores NVML reports as local to its GPU, so that the pinned host buffers of the
+    end-to-end leg are first-touched on the NUMA node next to the GPU (with one rank per GPU every rank otherwise
+    allocates wherever the launcher happened to start it, and the copies of several ranks share one socket's
+    memory controllers and inter-socket links).  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        masks = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(masks) for b in range(64) if (m >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = cpus & allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            return f"bound to {len(cpus)} GPU-local cores"
+        return "all cores are GPU-local"
+    except Exception as e:       # no NVML / not permitted: keep the inherited affinity
+        return f"not bound ({type(e).__name__})"
+
+
 class ClockSampler:
     def __init__(self, index: int):
         self.path = f"/tmp/fz_clocks_{os.getpid()}.csv"
@@ -156,6 +178,8 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_cpus(local)       # before any pinned allocation: first touch decides the NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib()
@@ -340,6 +364,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "volumes_per_gpu": 1, "parallelism": f"batch-sharded x{world}, no data-path collective",
                        "l2": "inputs (3 x 256 MiB per step) are larger than the 126 MB L2; no explicit flush",
+                       "host_affinity": numa,
                        "path": {0: "generic", 1: "window-at-a-time TMA/register kernels", 2: "three-pass octant kernels"}[fast_path],
                        "fwd_us": fwd_us, "bwd_us": bwd_us,
                        "fused_op_hbm_frac": (fwd_bytes + bwd_bytes) / ((fwd_us + bwd_us) * 1e-6) / 1e9 / peak},
@@ -367,6 +392,7 @@ def run_ours(args):
             block.pop("voxels_per_s_per_gpu", None)
             line["block"] = block
         if world == 1 and not args.no_cpu:
+            os.sched_setaffinity(0, all_cpus)       # the CPU baseline gets every core again
             rate, times, threads = cpu_reference_rate(64, 3)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"(1,{C},64^3) = 1/8 of the workload volume, same geometry/solver, fwd+bwd, "
