@@ -20,7 +20,10 @@
 // accumulator, and the CTA adds its total to the global gradient once at the end (fp32 atomics).
 // Per-channel sums (bias / LayerNorm parameter gradients) use a transposing warp reduction (31 shuffles
 // for 32 values).
+#include <stdlib.h>
+
 #include "fz_common.cuh"
+#include "fz_internal.cuh"
 
 namespace fz {
 namespace {
@@ -691,6 +694,14 @@ int fz_mixer_mlp_forward(const float* x, const float* m, const float* Wout, cons
     if (batch == 0 || voxels == 0) return FZ_OK;
     if (!x || !m || !Wout || !W1 || !W2 || !out) return fail(FZ_ERR_INVALID, "null buffer");
     if (misaligned(x) || misaligned(m) || misaligned(out) || misaligned(x1)) return fail(FZ_ERR_INVALID, "buffers must be 8-byte aligned");
+    {
+        // tensor-core path (tcgen05, 3xTF32) unless FZ_GLUE_TC=0 asks for the FP32-pipe kernel
+        static int use_tc = -1;
+        if (use_tc < 0) { const char* e = getenv("FZ_GLUE_TC"); use_tc = !(e && e[0] == '0'); }
+        if (use_tc && mixer_mlp_tc_supported(hidden))
+            return mixer_mlp_tc_launch(x, m, Wout, bout, gamma, beta, W1, b1, W2, b2, x1, out, batch, hidden, voxels, eps,
+                                       (cudaStream_t)stream);
+    }
     const size_t smem = mlp_fwd_smem(hidden);
     static SmemConfig cfg;
     FZ_CUDA_CHECK(cfg.ensure(mixer_mlp_fwd<kC>, smem));

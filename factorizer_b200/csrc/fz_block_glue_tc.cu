@@ -1,0 +1,295 @@
+// Tensor-core (tcgen05 / TMEM) version of mixer_mlp_fwd for 32-channel blocks:
+//     x1 = x + W_out m + b_out ;  out = x1 + W2 gelu(W1 LN(x1) + b1) + b2
+// (reference factorizer/factorizer.py:53,75-76, layers/mlp.py:54-60, layers/norm.py:29-34).
+//
+// The three projections are GEMMs with M = voxels: a CTA of 128 threads owns 128 voxels per tile, thread = voxel.
+//   * A operands (m, LN(x1), gelu(h)) live in shared memory exactly as they lie in an NCDHW tensor -- voxel-contiguous
+//     = "MN-major" -- in the one layout tcgen05 accepts for 32-bit MN-major data, SWIZZLE_128B_BASE32B: atoms of
+//     4 channels x 32 voxels, a channel row = 128 contiguous bytes whose 32-byte chunks are XOR-ed with (channel % 4).
+//     A warp writes one such row per channel: conflict-free.
+//   * B operands = the weights, (out, in) row-major = K-major, 8 x 16-byte core matrices, staged once per CTA.
+//   * D lives in TMEM (128 lanes = voxels x N columns); tcgen05.ld 32x32b returns to every thread ITS voxel's row,
+//     so bias / residual / LayerNorm / GELU run per thread in registers with no shuffles, and the next A operand is
+//     written straight back to shared memory.
+// fp32 parity rules out one TF32 pass (error 5e-3 on O(1) sums): every product is 3xTF32,
+//     a b ~= a_lo b_hi + a_hi b_lo + a_hi b_hi,   x_hi = x with the low 13 mantissa bits cleared (what the tensor core
+//     reads anyway), x_lo = x - x_hi (exact, fits TF32),
+// measured 5e-7 relative (profiles/r01_probes.md).  Descriptor encodings were pinned by bench_probes/tcgen05_probe.cu.
+#include "fz_common.cuh"
+
+namespace fz {
+namespace {
+
+constexpr int kC = 32;
+constexpr int kTM = 128;              // voxels per tile = threads per CTA
+constexpr int kMaxHid = 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+    d |= (uint64_t)(layout_type & 7) << 61;
+    return d;
+}
+// instruction descriptor: D = F32, A = B = TF32, A MN-major, B K-major, M = 128
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// A element (voxel m of the tile, channel k): SWIZZLE_128B_BASE32B, K groups of 4 channels 2 KiB apart
+__device__ __forceinline__ uint32_t a_off(int m, int k) {
+    const int r = k & 3, j = m & 31;
+    return (uint32_t)((k >> 2) * 2048 + (m >> 5) * 512 + r * 128 + (((j >> 3) ^ r) << 5) + (j & 7) * 4);
+}
+// W element (output n, input k) of an (N, KC) matrix: 8 x 4 core matrices of 128 B, K-adjacent, N groups KC*32 B apart
+__device__ __forceinline__ uint32_t b_off(int n, int k, int KC) {
+    return (uint32_t)((n >> 3) * (KC * 32) + (k >> 2) * 128 + (n & 7) * 16 + (k & 3) * 4);
+}
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+
+__device__ __forceinline__ void put_a(unsigned char* hi, unsigned char* lo, int m, int k, float v) {
+    const uint32_t o = a_off(m, k);
+    const float h = tf32_hi(v);
+    *reinterpret_cast<float*>(hi + o) = v;
+    *reinterpret_cast<float*>(lo + o) = v - h;
+}
+
+// D[tmem_d .. +N) (+)= A[128 x KC] W[N x KC]^T, 3xTF32; issued by one thread
+__device__ __forceinline__ void gemm3(uint32_t tmem_d, const unsigned char* a_hi, const unsigned char* a_lo, const unsigned char* b_hi,
+                                      const unsigned char* b_lo, int KC, int N) {
+    const uint32_t idesc = make_idesc(N);
+    const uint32_t sbo_b = (uint32_t)KC * 32;
+    for (int s = 0; s < KC / 8; ++s) {
+        const uint64_t ah = make_desc(smem_u32(a_hi) + s * 4096, 512, 2048, 1);
+        const uint64_t al = make_desc(smem_u32(a_lo) + s * 4096, 512, 2048, 1);
+        const uint64_t bh = make_desc(smem_u32(b_hi) + s * 256, 128, sbo_b, 0);
+        const uint64_t bl = make_desc(smem_u32(b_lo) + s * 256, 128, sbo_b, 0);
+        mma_tf32(tmem_d, al, bh, idesc, s > 0);
+        mma_tf32(tmem_d, ah, bl, idesc, 1);
+        mma_tf32(tmem_d, ah, bh, idesc, 1);
+    }
+}
+
+__device__ __forceinline__ void commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// 32 consecutive TMEM columns of this thread's lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// all threads have written an A operand (generic proxy): make it visible to the tensor core, then meet
+__device__ __forceinline__ void publish_and_sync() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+__device__ __forceinline__ float gelu_exact(float h) {
+    // Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7), same evaluation as csrc/fz_block_glue.cu
+    const float z = fabsf(h) * 0.70710678118654752f;
+    const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+    const float e = exp2f(h * h * -0.72134752044448170f);
+    float p = fmaf(t, 1.061405429f, -1.453152027f);
+    p = fmaf(t, p, 1.421413741f);
+    p = fmaf(t, p, -0.284496736f);
+    p = fmaf(t, p, 0.254829592f);
+    const float erf_abs = fmaf(-(p * t), e, 1.f);
+    return h * fmaf(copysignf(0.5f, h), erf_abs, 0.5f);
+}
+
+__global__ void __launch_bounds__(kTM, 2) mixer_mlp_fwd_tc(const float* __restrict__ x, const float* __restrict__ m,
+                                                           const float* __restrict__ Wout, const float* __restrict__ bout,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const float* __restrict__ W1, const float* __restrict__ b1,
+                                                           const float* __restrict__ W2, const float* __restrict__ b2,
+                                                           float* __restrict__ x1_out, float* __restrict__ out, int HID,
+                                                           long long vox, int tiles_per_sample, long long total_tiles, float eps) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* a_hi = smem;                       // 128 voxels x up to 64 channels
+    unsigned char* a_lo = a_hi + kTM * kMaxHid * 4;
+    unsigned char* wo_hi = a_lo + kTM * kMaxHid * 4;  // (32, 32)
+    unsigned char* wo_lo = wo_hi + kC * kC * 4;
+    unsigned char* w1_hi = wo_lo + kC * kC * 4;       // (HID, 32)
+    unsigned char* w1_lo = w1_hi + kMaxHid * kC * 4;
+    unsigned char* w2_hi = w1_lo + kMaxHid * kC * 4;  // (32, HID)
+    unsigned char* w2_lo = w2_hi + kC * kMaxHid * 4;
+    float* par = reinterpret_cast<float*>(w2_lo + kC * kMaxHid * 4);     // bout | b2 | gamma | beta | b1
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    for (int e = tid; e < kC * kC; e += kTM) {
+        const int n = e / kC, k = e % kC;
+        const float v = Wout[e];
+        *reinterpret_cast<float*>(wo_hi + b_off(n, k, kC)) = v;
+        *reinterpret_cast<float*>(wo_lo + b_off(n, k, kC)) = v - tf32_hi(v);
+    }
+    for (int e = tid; e < HID * kC; e += kTM) {
+        {
+            const int n = e / kC, k = e % kC;            // W1 (HID, 32)
+            const float v = W1[e];
+            *reinterpret_cast<float*>(w1_hi + b_off(n, k, kC)) = v;
+            *reinterpret_cast<float*>(w1_lo + b_off(n, k, kC)) = v - tf32_hi(v);
+        }
+        {
+            const int n = e / HID, k = e % HID;          // W2 (32, HID)
+            const float v = W2[e];
+            *reinterpret_cast<float*>(w2_hi + b_off(n, k, HID)) = v;
+            *reinterpret_cast<float*>(w2_lo + b_off(n, k, HID)) = v - tf32_hi(v);
+        }
+    }
+    for (int c = tid; c < kC; c += kTM) {
+        par[c] = bout ? bout[c] : 0.f; par[kC + c] = b2 ? b2[c] : 0.f;
+        par[2 * kC + c] = gamma ? gamma[c] : 1.f; par[3 * kC + c] = beta ? beta[c] : 0.f;
+    }
+    for (int j = tid; j < HID; j += kTM) par[4 * kC + j] = b1 ? b1[j] : 0.f;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" :: "r"(smem_u32(&tmem_base)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    publish_and_sync();
+    const uint32_t tmem = tmem_base;
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);     // this thread's TMEM lane, column 0
+    // TMEM columns: [0, 32) x1 projection | [32, 32 + HID) hidden | [96, 128) output projection
+    uint32_t parity = 0;
+
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const long long b = tile / tiles_per_sample;
+        const long long v0 = (tile - b * tiles_per_sample) * kTM + tid;
+        const bool valid = v0 < vox;
+        const long long base = b * kC * vox + v0;
+        // ---- A <- m ----
+#pragma unroll 8
+        for (int c = 0; c < kC; ++c) put_a(a_hi, a_lo, tid, c, valid ? __ldg(m + base + c * vox) : 0.f);
+        publish_and_sync();
+        if (tid == 0) { gemm3(tmem, a_hi, a_lo, wo_hi, wo_lo, kC, kC); commit(&bar); }
+        // x arrives while the tensor core works
+        float x1[kC];
+#pragma unroll
+        for (int c = 0; c < kC; ++c) x1[c] = valid ? __ldg(x + base + c * vox) : 0.f;
+        wait_bar(&bar, parity); parity ^= 1;
+        {
+            float d[32];
+            tmem_ld32(lane_addr, d);
+#pragma unroll
+            for (int c = 0; c < kC; ++c) x1[c] += d[c] + par[c];
+        }
+        if (x1_out && valid) {
+#pragma unroll
+            for (int c = 0; c < kC; ++c) x1_out[base + c * vox] = x1[c];
+        }
+        // ---- A <- LN(x1) ----
+        {
+            float mean = 0.f;
+#pragma unroll
+            for (int c = 0; c < kC; ++c) mean += x1[c];
+            mean *= (1.f / kC);
+            float var = 0.f;
+#pragma unroll
+            for (int c = 0; c < kC; ++c) { const float dlt = x1[c] - mean; var = fmaf(dlt, dlt, var); }
+            const float rstd = rsqrtf(var * (1.f / kC) + eps);
+#pragma unroll
+            for (int c = 0; c < kC; ++c)
+                put_a(a_hi, a_lo, tid, c, fmaf((x1[c] - mean) * rstd, par[2 * kC + c], par[3 * kC + c]));
+        }
+        publish_and_sync();
+        if (tid == 0) { gemm3(tmem + 32, a_hi, a_lo, w1_hi, w1_lo, kC, HID); commit(&bar); }
+        wait_bar(&bar, parity); parity ^= 1;
+        // ---- A <- gelu(h) ----
+        for (int j0 = 0; j0 < HID; j0 += 32) {
+            float h[32];
+            tmem_ld32(lane_addr + 32 + j0, h);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j0 + j < HID) put_a(a_hi, a_lo, tid, j0 + j, gelu_exact(h[j] + par[4 * kC + j0 + j]));
+        }
+        publish_and_sync();
+        if (tid == 0) { gemm3(tmem + 96, a_hi, a_lo, w2_hi, w2_lo, HID, kC); commit(&bar); }
+        wait_bar(&bar, parity); parity ^= 1;
+        {
+            float d[32];
+            tmem_ld32(lane_addr + 96, d);
+            if (valid) {
+#pragma unroll
+                for (int c = 0; c < kC; ++c) out[base + c * vox] = x1[c] + d[c] + par[kC + c];
+            }
+        }
+        // the next tile overwrites the A region and TMEM columns [0, 32): every thread is past its TMEM loads
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" :: "r"(tmem) : "memory");
+}
+
+size_t tc_smem_bytes() { return (size_t)2 * kTM * kMaxHid * 4 + 2 * kC * kC * 4 + 4 * kMaxHid * kC * 4 + (4 * kC + kMaxHid) * 4 + 1024; }
+
+int tc_sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+}  // namespace
+
+// hidden width: a multiple of 16 (UMMA N) up to 64 (TMEM columns / shared memory of this version)
+bool mixer_mlp_tc_supported(int hidden) { return hidden >= 16 && hidden <= kMaxHid && hidden % 16 == 0; }
+
+int mixer_mlp_tc_launch(const float* x, const float* m, const float* Wout, const float* bout, const float* gamma, const float* beta,
+                        const float* W1, const float* b1, const float* W2, const float* b2, float* x1, float* out, long long batch,
+                        int hidden, long long voxels, float eps, cudaStream_t st) {
+    const size_t smem = tc_smem_bytes();
+    static SmemConfig cfg;
+    FZ_CUDA_CHECK(cfg.ensure(mixer_mlp_fwd_tc, smem));
+    const int tps = (int)((voxels + kTM - 1) / kTM);
+    const long long tiles = batch * tps;
+    const long long cap = 2LL * tc_sm_count();
+    const unsigned blocks = (unsigned)(tiles < cap ? tiles : cap);
+    mixer_mlp_fwd_tc<<<blocks, kTM, smem, st>>>(x, m, Wout, bout, gamma, beta, W1, b1, W2, b2, x1, out, hidden, voxels, tps, tiles, eps);
+    FZ_LAUNCH_CHECK();
+    return FZ_OK;
+}
+
+}  // namespace fz

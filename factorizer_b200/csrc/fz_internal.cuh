@@ -58,6 +58,12 @@ int phase_forward(const float* x, const float* v0, float* y, void* saved, void* 
 int phase_backward(const float* x, const float* gy, const float* v0, const void* saved, float* gx,
                    void* workspace, const DevGeom& G, const fz_solver& s, int K, cudaStream_t st);
 
+// fz_block_glue_tc.cu: tcgen05 / TMEM version of the out_proj + norm2 + MLP forward kernel (3xTF32)
+bool mixer_mlp_tc_supported(int hidden);
+int mixer_mlp_tc_launch(const float* x, const float* m, const float* Wout, const float* bout, const float* gamma, const float* beta,
+                        const float* W1, const float* b1, const float* W2, const float* b2, float* x1, float* out, long long batch,
+                        int hidden, long long voxels, float eps, cudaStream_t st);
+
 // fz_nmf_big.cu: rank-1 MU / HALS on matrices too large for one CTA (global Matricize: M channels x all voxels), one
 // grid-wide pass per sweep
 bool big_supported(int M, long long N, const fz_solver& s);
