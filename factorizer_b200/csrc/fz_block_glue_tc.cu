@@ -56,13 +56,6 @@ __device__ __forceinline__ uint32_t b_off(int n, int k, int KC) {
 }
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
 
-__device__ __forceinline__ void put_a(unsigned char* hi, unsigned char* lo, int m, int k, float v) {
-    const uint32_t o = a_off(m, k);
-    const float h = tf32_hi(v);
-    *reinterpret_cast<float*>(hi + o) = v;
-    *reinterpret_cast<float*>(lo + o) = v - h;
-}
-
 // D[tmem_d .. +N) (+)= A[128 x KC] W[N x KC]^T, 3xTF32; issued by one thread
 __device__ __forceinline__ void gemm3(uint32_t tmem_d, const unsigned char* a_hi, const unsigned char* a_lo, const unsigned char* b_hi,
                                       const unsigned char* b_lo, int KC, int N) {
@@ -128,12 +121,23 @@ __device__ __forceinline__ float gelu_exact(float h) {
     return h * fmaf(copysignf(0.5f, h), erf_abs, 0.5f);
 }
 
+// store value v of (this thread's voxel, channel k) into the hi / lo A buffers; ab[r] = swizzled byte offset of the
+// voxel inside a K group for channel k % 4 = r, so that k's own part is a compile-time immediate
+#define FZ_PUT_A(k, v)                                                                          \
+    do {                                                                                        \
+        const float v_ = (v);                                                                   \
+        const uint32_t o_ = ab[(k) & 3] + (uint32_t)((k) >> 2) * 2048u;                         \
+        *reinterpret_cast<float*>(a_hi + o_) = v_;                                              \
+        *reinterpret_cast<float*>(a_lo + o_) = v_ - tf32_hi(v_);                                \
+    } while (0)
+
+template <int HID>
 __global__ void __launch_bounds__(kTM, 2) mixer_mlp_fwd_tc(const float* __restrict__ x, const float* __restrict__ m,
                                                            const float* __restrict__ Wout, const float* __restrict__ bout,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ W1, const float* __restrict__ b1,
                                                            const float* __restrict__ W2, const float* __restrict__ b2,
-                                                           float* __restrict__ x1_out, float* __restrict__ out, int HID,
+                                                           float* __restrict__ x1_out, float* __restrict__ out,
                                                            long long vox, int tiles_per_sample, long long total_tiles, float eps) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* a_hi = smem;                       // 128 voxels x up to 64 channels
@@ -187,15 +191,30 @@ __global__ void __launch_bounds__(kTM, 2) mixer_mlp_fwd_tc(const float* __restri
     const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);     // this thread's TMEM lane, column 0
     // TMEM columns: [0, 32) x1 projection | [32, 32 + HID) hidden | [96, 128) output projection
     uint32_t parity = 0;
+    uint32_t ab[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) ab[r] = a_off(tid, r);
 
+    // the first tile's m; every later tile's m is fetched while the previous tile is in its GELU phase
+    float mreg[kC];
+    {
+        const long long tile = blockIdx.x;
+        if (tile < total_tiles) {
+            const long long b = tile / tiles_per_sample;
+            const long long v0 = (tile - b * tiles_per_sample) * kTM + tid;
+            const long long base = b * kC * vox + v0;
+#pragma unroll
+            for (int c = 0; c < kC; ++c) mreg[c] = v0 < vox ? __ldg(m + base + c * vox) : 0.f;
+        }
+    }
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const long long b = tile / tiles_per_sample;
         const long long v0 = (tile - b * tiles_per_sample) * kTM + tid;
         const bool valid = v0 < vox;
         const long long base = b * kC * vox + v0;
         // ---- A <- m ----
-#pragma unroll 8
-        for (int c = 0; c < kC; ++c) put_a(a_hi, a_lo, tid, c, valid ? __ldg(m + base + c * vox) : 0.f);
+#pragma unroll
+        for (int c = 0; c < kC; ++c) FZ_PUT_A(c, mreg[c]);
         publish_and_sync();
         if (tid == 0) { gemm3(tmem, a_hi, a_lo, wo_hi, wo_lo, kC, kC); commit(&bar); }
         // x arrives while the tensor core works
@@ -224,19 +243,29 @@ __global__ void __launch_bounds__(kTM, 2) mixer_mlp_fwd_tc(const float* __restri
             for (int c = 0; c < kC; ++c) { const float dlt = x1[c] - mean; var = fmaf(dlt, dlt, var); }
             const float rstd = rsqrtf(var * (1.f / kC) + eps);
 #pragma unroll
-            for (int c = 0; c < kC; ++c)
-                put_a(a_hi, a_lo, tid, c, fmaf((x1[c] - mean) * rstd, par[2 * kC + c], par[3 * kC + c]));
+            for (int c = 0; c < kC; ++c) FZ_PUT_A(c, fmaf((x1[c] - mean) * rstd, par[2 * kC + c], par[3 * kC + c]));
         }
         publish_and_sync();
         if (tid == 0) { gemm3(tmem + 32, a_hi, a_lo, w1_hi, w1_lo, kC, HID); commit(&bar); }
+        // next tile's m: in flight during this tile's GELU and output phases
+        {
+            const long long nt = tile + gridDim.x;
+            if (nt < total_tiles) {
+                const long long nb = nt / tiles_per_sample;
+                const long long nv = (nt - nb * tiles_per_sample) * kTM + tid;
+                const long long nbase = nb * kC * vox + nv;
+#pragma unroll
+                for (int c = 0; c < kC; ++c) mreg[c] = nv < vox ? __ldg(m + nbase + c * vox) : 0.f;
+            }
+        }
         wait_bar(&bar, parity); parity ^= 1;
         // ---- A <- gelu(h) ----
+#pragma unroll
         for (int j0 = 0; j0 < HID; j0 += 32) {
             float h[32];
             tmem_ld32(lane_addr + 32 + j0, h);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (j0 + j < HID) put_a(a_hi, a_lo, tid, j0 + j, gelu_exact(h[j] + par[4 * kC + j0 + j]));
+            for (int j = 0; j < 32; ++j) FZ_PUT_A(j0 + j, gelu_exact(h[j] + par[4 * kC + j0 + j]));
         }
         publish_and_sync();
         if (tid == 0) { gemm3(tmem + 96, a_hi, a_lo, w2_hi, w2_lo, HID, kC); commit(&bar); }
@@ -274,20 +303,24 @@ int tc_sm_count() {
 
 }  // namespace
 
-// hidden width: a multiple of 16 (UMMA N) up to 64 (TMEM columns / shared memory of this version)
-bool mixer_mlp_tc_supported(int hidden) { return hidden >= 16 && hidden <= kMaxHid && hidden % 16 == 0; }
+// hidden width 32 or 64 (mlp_ratio 1 or 2 at 32 channels): TMEM columns / shared memory of this version
+bool mixer_mlp_tc_supported(int hidden) { return hidden == 32 || hidden == 64; }
 
 int mixer_mlp_tc_launch(const float* x, const float* m, const float* Wout, const float* bout, const float* gamma, const float* beta,
                         const float* W1, const float* b1, const float* W2, const float* b2, float* x1, float* out, long long batch,
                         int hidden, long long voxels, float eps, cudaStream_t st) {
     const size_t smem = tc_smem_bytes();
-    static SmemConfig cfg;
-    FZ_CUDA_CHECK(cfg.ensure(mixer_mlp_fwd_tc, smem));
+    static SmemConfig cfg32, cfg64;
+    FZ_CUDA_CHECK(cfg32.ensure(mixer_mlp_fwd_tc<32>, smem));
+    FZ_CUDA_CHECK(cfg64.ensure(mixer_mlp_fwd_tc<64>, smem));
     const int tps = (int)((voxels + kTM - 1) / kTM);
     const long long tiles = batch * tps;
     const long long cap = 2LL * tc_sm_count();
     const unsigned blocks = (unsigned)(tiles < cap ? tiles : cap);
-    mixer_mlp_fwd_tc<<<blocks, kTM, smem, st>>>(x, m, Wout, bout, gamma, beta, W1, b1, W2, b2, x1, out, hidden, voxels, tps, tiles, eps);
+    if (hidden == 64)
+        mixer_mlp_fwd_tc<64><<<blocks, kTM, smem, st>>>(x, m, Wout, bout, gamma, beta, W1, b1, W2, b2, x1, out, voxels, tps, tiles, eps);
+    else
+        mixer_mlp_fwd_tc<32><<<blocks, kTM, smem, st>>>(x, m, Wout, bout, gamma, beta, W1, b1, W2, b2, x1, out, voxels, tps, tiles, eps);
     FZ_LAUNCH_CHECK();
     return FZ_OK;
 }
