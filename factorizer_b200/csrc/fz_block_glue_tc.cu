@@ -108,17 +108,25 @@ __device__ __forceinline__ void publish_and_sync() {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
-__device__ __forceinline__ float gelu_exact(float h) {
-    // Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7), same evaluation as csrc/fz_block_glue.cu
-    const float z = fabsf(h) * 0.70710678118654752f;
-    const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-    const float e = exp2f(h * h * -0.72134752044448170f);
-    float p = fmaf(t, 1.061405429f, -1.453152027f);
-    p = fmaf(t, p, 1.421413741f);
-    p = fmaf(t, p, -0.284496736f);
-    p = fmaf(t, p, 0.254829592f);
-    const float erf_abs = fmaf(-(p * t), e, 1.f);
-    return h * fmaf(copysignf(0.5f, h), erf_abs, 0.5f);
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// exact-erf GELU of two values (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7; same formula as csrc/fz_block_glue.cu),
+// polynomial in packed FFMA2, one MUFU.RCP + one MUFU.EX2 per value
+__device__ __forceinline__ float2 gelu_exact2(float2 h) {
+    const float2 z = make_float2(fabsf(h.x) * 0.70710678118654752f, fabsf(h.y) * 0.70710678118654752f);
+    const float2 d = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), z, make_float2(1.f, 1.f));
+    const float2 t = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+    const float2 hh = __fmul2_rn(h, h);
+    const float2 e = make_float2(ex2_approx(hh.x * -0.72134752044448170f), ex2_approx(hh.y * -0.72134752044448170f));
+    float2 p = __ffma2_rn(t, make_float2(1.061405429f, 1.061405429f), make_float2(-1.453152027f, -1.453152027f));
+    p = __ffma2_rn(t, p, make_float2(1.421413741f, 1.421413741f));
+    p = __ffma2_rn(t, p, make_float2(-0.284496736f, -0.284496736f));
+    p = __ffma2_rn(t, p, make_float2(0.254829592f, 0.254829592f));
+    const float2 pt = __fmul2_rn(p, t);
+    const float2 erf_abs = __ffma2_rn(make_float2(-pt.x, -pt.y), e, make_float2(1.f, 1.f));
+    const float2 cdf = __ffma2_rn(make_float2(copysignf(0.5f, h.x), copysignf(0.5f, h.y)), erf_abs, make_float2(0.5f, 0.5f));
+    return __fmul2_rn(h, cdf);
 }
 
 // store value v of (this thread's voxel, channel k) into the hi / lo A buffers; ab[r] = swizzled byte offset of the
@@ -195,8 +203,8 @@ __global__ void __launch_bounds__(kTM, 2) mixer_mlp_fwd_tc(const float* __restri
 #pragma unroll
     for (int r = 0; r < 4; ++r) ab[r] = a_off(tid, r);
 
-    // the first tile's m; every later tile's m is fetched while the previous tile is in its GELU phase
-    float mreg[kC];
+    // the first tile's m and x; every later tile's are fetched while the previous tile is in its GELU phase
+    float mreg[kC], xreg[kC];
     {
         const long long tile = blockIdx.x;
         if (tile < total_tiles) {
@@ -205,6 +213,8 @@ __global__ void __launch_bounds__(kTM, 2) mixer_mlp_fwd_tc(const float* __restri
             const long long base = b * kC * vox + v0;
 #pragma unroll
             for (int c = 0; c < kC; ++c) mreg[c] = v0 < vox ? __ldg(m + base + c * vox) : 0.f;
+#pragma unroll
+            for (int c = 0; c < kC; ++c) xreg[c] = v0 < vox ? __ldg(x + base + c * vox) : 0.f;
         }
     }
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -217,10 +227,9 @@ __global__ void __launch_bounds__(kTM, 2) mixer_mlp_fwd_tc(const float* __restri
         for (int c = 0; c < kC; ++c) FZ_PUT_A(c, mreg[c]);
         publish_and_sync();
         if (tid == 0) { gemm3(tmem, a_hi, a_lo, wo_hi, wo_lo, kC, kC); commit(&bar); }
-        // x arrives while the tensor core works
         float x1[kC];
 #pragma unroll
-        for (int c = 0; c < kC; ++c) x1[c] = valid ? __ldg(x + base + c * vox) : 0.f;
+        for (int c = 0; c < kC; ++c) x1[c] = xreg[c];
         wait_bar(&bar, parity); parity ^= 1;
         {
             float d[32];
@@ -247,7 +256,7 @@ __global__ void __launch_bounds__(kTM, 2) mixer_mlp_fwd_tc(const float* __restri
         }
         publish_and_sync();
         if (tid == 0) { gemm3(tmem + 32, a_hi, a_lo, w1_hi, w1_lo, kC, HID); commit(&bar); }
-        // next tile's m: in flight during this tile's GELU and output phases
+        // next tile's m and x: in flight during this tile's GELU and output phases
         {
             const long long nt = tile + gridDim.x;
             if (nt < total_tiles) {
@@ -256,6 +265,8 @@ __global__ void __launch_bounds__(kTM, 2) mixer_mlp_fwd_tc(const float* __restri
                 const long long nbase = nb * kC * vox + nv;
 #pragma unroll
                 for (int c = 0; c < kC; ++c) mreg[c] = nv < vox ? __ldg(m + nbase + c * vox) : 0.f;
+#pragma unroll
+                for (int c = 0; c < kC; ++c) xreg[c] = nv < vox ? __ldg(x + nbase + c * vox) : 0.f;
             }
         }
         wait_bar(&bar, parity); parity ^= 1;
@@ -265,7 +276,12 @@ __global__ void __launch_bounds__(kTM, 2) mixer_mlp_fwd_tc(const float* __restri
             float h[32];
             tmem_ld32(lane_addr + 32 + j0, h);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) FZ_PUT_A(j0 + j, gelu_exact(h[j] + par[4 * kC + j0 + j]));
+            for (int j = 0; j < 32; j += 2) {
+                const float2 bj = *reinterpret_cast<const float2*>(par + 4 * kC + j0 + j);
+                const float2 g = gelu_exact2(make_float2(h[j] + bj.x, h[j + 1] + bj.y));
+                FZ_PUT_A(j0 + j, g.x);
+                FZ_PUT_A(j0 + j + 1, g.y);
+            }
         }
         publish_and_sync();
         if (tid == 0) { gemm3(tmem + 96, a_hi, a_lo, w2_hi, w2_lo, HID, kC); commit(&bar); }
