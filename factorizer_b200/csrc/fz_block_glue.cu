@@ -129,28 +129,34 @@ __device__ __forceinline__ float warp_vec_sum(float (&v)[N], int lane) {
 // Exact (erf) GELU through Abramowitz-Stegun 7.1.26: erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1/(1 + p z),
 // |error| <= 1.5e-7 for z >= 0, odd extension below.  With z = |h|/sqrt(2) the exponential is exp(-h^2/2), which is
 // also the density the derivative needs; two MUFU ops (RCP, EX2) and ~12 FP32 ops instead of erff + expf (~45).
-// Returns Phi(h) = (1 + erf(h/sqrt 2))/2 and e = exp(-h^2/2).
-__device__ __forceinline__ float gauss_cdf(float h, float& e) {
-    const float z = fabsf(h) * 0.70710678118654752f;
-    const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-    e = exp2f(h * h * -0.72134752044448170f);            // exp(-h^2/2) = 2^(-h^2 / (2 ln 2))
-    float p = fmaf(t, 1.061405429f, -1.453152027f);
-    p = fmaf(t, p, 1.421413741f);
-    p = fmaf(t, p, -0.284496736f);
-    p = fmaf(t, p, 0.254829592f);
-    const float erf_abs = fmaf(-(p * t), e, 1.f);
-    return fmaf(copysignf(0.5f, h), erf_abs, 0.5f);
+// gauss_cdf2 returns Phi(h) = (1 + erf(h/sqrt 2))/2 and e = exp(-h^2/2).
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// two values at a time: the polynomial in packed FFMA2, one MUFU.RCP + one MUFU.EX2 per value
+__device__ __forceinline__ f2 gauss_cdf2(f2 h, f2& e) {
+    const f2 z = make_float2(fabsf(h.x) * 0.70710678118654752f, fabsf(h.y) * 0.70710678118654752f);
+    const f2 d = fma2(dup(0.3275911f), z, dup(1.f));
+    const f2 t = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+    const f2 hh = __fmul2_rn(h, h);
+    e = make_float2(ex2_approx(hh.x * -0.72134752044448170f), ex2_approx(hh.y * -0.72134752044448170f));   // exp(-h^2/2)
+    f2 p = fma2(t, dup(1.061405429f), dup(-1.453152027f));
+    p = fma2(t, p, dup(1.421413741f));
+    p = fma2(t, p, dup(-0.284496736f));
+    p = fma2(t, p, dup(0.254829592f));
+    const f2 pt = __fmul2_rn(p, t);
+    const f2 erf_abs = fma2(make_float2(-pt.x, -pt.y), e, dup(1.f));
+    return fma2(make_float2(copysignf(0.5f, h.x), copysignf(0.5f, h.y)), erf_abs, dup(0.5f));
 }
-__device__ __forceinline__ float gelu(float h) {
-    float e;
-    return h * gauss_cdf(h, e);
+__device__ __forceinline__ f2 gelu2(f2 h) {
+    f2 e;
+    return __fmul2_rn(h, gauss_cdf2(h, e));
 }
 // gelu(h) and its derivative Phi(h) + h phi(h)  (torch: GeluBackward, approximate='none')
-__device__ __forceinline__ void gelu_grad(float h, float& g, float& gp) {
-    float e;
-    const float cdf = gauss_cdf(h, e);
-    g = h * cdf;
-    gp = fmaf(h * 0.39894228040143268f, e, cdf);
+__device__ __forceinline__ void gelu_grad2(f2 h, f2& g, f2& gp) {
+    f2 e;
+    const f2 cdf = gauss_cdf2(h, e);
+    g = __fmul2_rn(h, cdf);
+    gp = fma2(__fmul2_rn(h, dup(0.39894228040143268f)), e, cdf);
 }
 
 template <int C>
@@ -258,8 +264,9 @@ __global__ void __launch_bounds__(128, 2) mixer_mlp_fwd(const float* __restrict_
             f2 g[8];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                g[2 * k] = make_float2(gelu(h0[k].x), gelu(h1[k].x));
-                g[2 * k + 1] = make_float2(gelu(h0[k].y), gelu(h1[k].y));
+                const f2 ga = gelu2(h0[k]), gb = gelu2(h1[k]);          // (hidden 2k, 2k+1) of voxel 0 / voxel 1
+                g[2 * k] = make_float2(ga.x, gb.x);
+                g[2 * k + 1] = make_float2(ga.y, gb.y);
             }
             matvec<8, C>(W2T + j0 * C, C, g, o0, o1);
         }
@@ -546,12 +553,12 @@ __global__ void __launch_bounds__(kTT, 1) mlp_bwd(const float* __restrict__ x1, 
             float sb[8];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                float g, gp;
-                f2 ga, gb;
-                gelu_grad(h0[k].x, g, gp); ga.x = g; dh[2 * k].x = q0[k].x * gp;
-                gelu_grad(h1[k].x, g, gp); ga.y = g; dh[2 * k].y = q1[k].x * gp;
-                gelu_grad(h0[k].y, g, gp); gb.x = g; dh[2 * k + 1].x = q0[k].y * gp;
-                gelu_grad(h1[k].y, g, gp); gb.y = g; dh[2 * k + 1].y = q1[k].y * gp;
+                f2 g0, gp0, g1, gp1;                                     // (hidden 2k, 2k+1) of voxel 0 / voxel 1
+                gelu_grad2(h0[k], g0, gp0);
+                gelu_grad2(h1[k], g1, gp1);
+                const f2 ga = make_float2(g0.x, g1.x), gb = make_float2(g0.y, g1.y);
+                dh[2 * k] = make_float2(q0[k].x * gp0.x, q1[k].x * gp1.x);
+                dh[2 * k + 1] = make_float2(q0[k].y * gp0.y, q1[k].y * gp1.y);
                 *reinterpret_cast<f2*>(Sg + (2 * k) * kRS + 2 * tid) = ga;
                 *reinterpret_cast<f2*>(Sg + (2 * k + 1) * kRS + 2 * tid) = gb;
                 *reinterpret_cast<f2*>(Sdh + (2 * k) * kRS + 2 * tid) = dh[2 * k];
