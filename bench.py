@@ -333,7 +333,7 @@ def run_ours(args):
         bms = b0.elapsed_time(b1) / nb
         block = {"workload": "FactorizerBlock(32,128^3,LayerNorm,SWMatricize,HALS r1,mlp_ratio=2,dropout=0) fwd+bwd incl. "
                              "parameter gradients, B=1/GPU, fp32",
-                 "path": "hand-written glue kernels (fz_block_glue.cu) + fused core: 3 launches fwd, 4 bwd" if block_fused
+                 "path": "hand-written glue kernels (fz_block_glue.cu on the FP32 pipe; forward out_proj+norm2+MLP on tcgen05/TMEM, 3xTF32, fz_block_glue_tc.cu) + fused core: 3 launches fwd, 4 bwd" if block_fused
                          else "layer by layer (library GEMMs) around the fused core",
                  "ms_per_step": bms, "voxels_per_s_per_gpu": N ** 3 / (bms * 1e-3)}
 
