@@ -282,7 +282,7 @@ def _glue_call(fn, *args):
     L.check(fn(*[a.data_ptr() if isinstance(a, torch.Tensor) else a for a in args]))
 
 
-@pytest.mark.parametrize("HID", [48, 136])
+@pytest.mark.parametrize("HID", [32, 48, 64, 136])
 @pytest.mark.parametrize("shape", [(1, 32, 8, 8, 8), (2, 32, 6, 10, 7), (3, 32, 1030)])
 def test_glue_kernels_against_torch_fp64(ft, dev, shape, HID):
     """Each kernel of csrc/fz_block_glue.cu through the C ABI against fp64 torch autograd of the same
