@@ -736,6 +736,13 @@ int fz_linear_backward(const float* dy, const float* a, const float* gamma, cons
     if (dgamma) FZ_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, kC * sizeof(float), st));
     if (dbeta) FZ_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, kC * sizeof(float), st));
     if (batch == 0 || voxels == 0) return FZ_OK;
+    {
+        // weight gradient on the tensor core (tcgen05, 3xTF32) unless FZ_GLUE_TC=0
+        static int use_tc = -1;
+        if (use_tc < 0) { const char* e = getenv("FZ_GLUE_TC"); use_tc = !(e && e[0] == '0'); }
+        if (use_tc)
+            return linear_bwd_tc_launch(dy, a, gamma, beta, W, resid, da, dW, db, dgamma, dbeta, batch, voxels, eps, layernorm, st);
+    }
     const size_t smem = linear_bwd_smem();
     static SmemConfig cfg_ln, cfg_plain;
     FZ_CUDA_CHECK(cfg_ln.ensure(linear_bwd<kC, true>, smem));

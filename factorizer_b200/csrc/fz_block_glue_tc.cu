@@ -304,6 +304,221 @@ __global__ void __launch_bounds__(kTM, 2) mixer_mlp_fwd_tc(const float* __restri
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" :: "r"(tmem) : "memory");
 }
 
+// =====================================================================================================================
+// linear_bwd with the weight gradient on the tensor core:
+//   da = W^T dy  [through LayerNorm, plus a residual gradient]  -- per voxel, FP32 pipe (1 024 FMA per voxel)
+//   dW = sum_v dy n(a)^T                                        -- tcgen05: a contraction over voxels
+// Operands of the contraction are K-major = voxel-contiguous rows, no swizzle, 8 x 16-byte core matrices 144 B apart
+// along K (a voxel-owning warp's stores then hit 32 distinct banks).  A = [dy ; dy_lo] (64 rows: the smallest tcgen05 M,
+// and exactly the two left factors of 3xTF32), B = n(a) and then n(a)_lo: two MMAs per 8 voxels give
+//   rows 0..31  = dy (b_hi + b_lo),   rows 32..63 = dy_lo (b_hi + b_lo),   dW = their sum,
+// accumulated in TMEM across ALL tiles of the CTA and flushed once at the end (row r sits in lane 32 (r/16) + r%16).
+// Layout facts pinned by bench_probes/tcgen05_wgrad_probe.cu.
+// =====================================================================================================================
+constexpr int kKP = 144;                       // pitch of the core matrices along K (bytes)
+constexpr int kKS = (kTM / 4) * kKP;           // 8 rows of 128 voxels: 4608 B
+__device__ __forceinline__ uint32_t k_off(int row, int v) {
+    return (uint32_t)((row >> 3) * kKS + (v >> 2) * kKP + (row & 7) * 16 + (v & 3) * 4);
+}
+__device__ __forceinline__ void mma_tf32_kk(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    mma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
+}
+__device__ __forceinline__ float warp_sum_tc(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// transposing warp reduction of 32 values: returns the warp total of element `lane`
+__device__ __forceinline__ float warp_vec_sum32(float (&v)[32], int lane) {
+    int off = 16;
+#pragma unroll
+    for (int n = 32; n > 1; n >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float keep = up ? v[i + n / 2] : v[i];
+            const float send = up ? v[i] : v[i + n / 2];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+        off >>= 1;
+    }
+    return v[0];
+}
+
+template <bool LN>
+__global__ void __launch_bounds__(kTM, 2) linear_bwd_tc(const float* __restrict__ dy, const float* __restrict__ a,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        const float* __restrict__ W, const float* __restrict__ resid,
+                                                        float* __restrict__ da, float* __restrict__ dW, float* __restrict__ db,
+                                                        float* __restrict__ dgamma, float* __restrict__ dbeta, long long vox,
+                                                        int tiles_per_sample, long long total_tiles, float eps) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* KA = smem;                         // [dy ; dy_lo], 64 rows
+    unsigned char* KBh = KA + 8 * kKS;                // n(a), 32 rows
+    unsigned char* KBl = KBh + 4 * kKS;               // n(a)_lo
+    float* Ws = reinterpret_cast<float*>(KBl + 4 * kKS);   // W [o][c] as stored
+    float* gs = Ws + kC * kC;
+    float* bs = gs + kC;
+    float* accv = bs + kC;                            // db | dgamma | dbeta
+    float* scr = accv + 3 * kC;                       // [warp][3 * kC]
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < kC * kC; i += kTM) Ws[i] = W[i];
+    for (int c = tid; c < kC; c += kTM) { gs[c] = gamma ? gamma[c] : 1.f; bs[c] = beta ? beta[c] : 0.f; }
+    for (int c = tid; c < 3 * kC; c += kTM) accv[c] = 0.f;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" :: "r"(smem_u32(&tmem_base)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    publish_and_sync();
+    const uint32_t tmem = tmem_base;
+    // D = F32, A = B = TF32, both K-major, N = 32, M = 64
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kC >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+    uint32_t parity = 0;
+    bool pending = false;          // MMAs of the previous tile still read KA / KB
+    uint32_t kb[8];                // this voxel's byte offset inside a row group, per row % 8
+#pragma unroll
+    for (int r = 0; r < 8; ++r) kb[r] = k_off(r, tid);
+
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const long long b = tile / tiles_per_sample;
+        const long long v0 = (tile - b * tiles_per_sample) * kTM + tid;
+        const bool valid = v0 < vox;
+        const long long base = b * kC * vox + v0;
+        float g[kC], av[kC];
+#pragma unroll
+        for (int o = 0; o < kC; ++o) g[o] = valid ? __ldg(dy + base + o * vox) : 0.f;
+#pragma unroll
+        for (int c = 0; c < kC; ++c) av[c] = valid ? __ldg(a + base + c * vox) : 0.f;
+        if (pending) { wait_bar(&bar, parity); parity ^= 1; pending = false; }
+        // ---- stage [dy ; dy_lo] ----
+#pragma unroll
+        for (int o = 0; o < kC; ++o) {
+            const uint32_t off = kb[o & 7] + (uint32_t)(o >> 3) * kKS;
+            *reinterpret_cast<float*>(KA + off) = g[o];
+            *reinterpret_cast<float*>(KA + off + 4 * kKS) = g[o] - tf32_hi(g[o]);
+        }
+        float r_db;
+        {
+            float sv[kC];
+#pragma unroll
+            for (int o = 0; o < kC; ++o) sv[o] = g[o];
+            r_db = warp_vec_sum32(sv, lane);
+        }
+        // ---- da = W^T dy on the FP32 pipe: packed FFMA2 on output pairs, broadcast LDS.128 of the weights ----
+        float2 d2[kC / 2];
+#pragma unroll
+        for (int k = 0; k < kC / 2; ++k) d2[k] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int o = 0; o < kC; ++o) {
+            const float2 go = make_float2(g[o], g[o]);
+#pragma unroll
+            for (int q = 0; q < kC / 4; ++q) {
+                const float4 w = *reinterpret_cast<const float4*>(Ws + o * kC + 4 * q);
+                d2[2 * q] = __ffma2_rn(make_float2(w.x, w.y), go, d2[2 * q]);
+                d2[2 * q + 1] = __ffma2_rn(make_float2(w.z, w.w), go, d2[2 * q + 1]);
+            }
+        }
+        // ---- n(a): stage it, and run the LayerNorm backward ----
+        float r_dg = 0.f, r_dbeta = 0.f;
+        if (LN) {
+            float mean = 0.f;
+#pragma unroll
+            for (int c = 0; c < kC; ++c) mean += av[c];
+            mean *= (1.f / kC);
+            float var = 0.f;
+#pragma unroll
+            for (int c = 0; c < kC; ++c) { av[c] -= mean; var = fmaf(av[c], av[c], var); }
+            const float rstd = rsqrtf(var * (1.f / kC) + eps);
+            float m1 = 0.f, m2 = 0.f;
+            float sg[kC], sb[kC];
+#pragma unroll
+            for (int c = 0; c < kC; ++c) {
+                av[c] *= rstd;                                            // a_hat
+                const float n2 = fmaf(av[c], gs[c], bs[c]);
+                const uint32_t off = kb[c & 7] + (uint32_t)(c >> 3) * kKS;
+                *reinterpret_cast<float*>(KBh + off) = n2;
+                *reinterpret_cast<float*>(KBl + off) = n2 - tf32_hi(n2);
+                const float d = (c & 1) ? d2[c >> 1].y : d2[c >> 1].x;
+                sg[c] = d * av[c];
+                sb[c] = d;
+                const float t = d * gs[c];
+                m1 += t;
+                m2 = fmaf(t, av[c], m2);
+            }
+            m1 *= (1.f / kC); m2 *= (1.f / kC);
+            if (valid) {
+#pragma unroll
+                for (int c = 0; c < kC; ++c) {
+                    const float d = (c & 1) ? d2[c >> 1].y : d2[c >> 1].x;
+                    float o = rstd * (d * gs[c] - m1 - av[c] * m2);
+                    if (resid) o += __ldg(resid + base + c * vox);
+                    da[base + c * vox] = o;
+                }
+            }
+            r_dg = warp_vec_sum32(sg, lane);
+            r_dbeta = warp_vec_sum32(sb, lane);
+        } else {
+#pragma unroll
+            for (int c = 0; c < kC; ++c) {
+                const uint32_t off = kb[c & 7] + (uint32_t)(c >> 3) * kKS;
+                *reinterpret_cast<float*>(KBh + off) = av[c];
+                *reinterpret_cast<float*>(KBl + off) = av[c] - tf32_hi(av[c]);
+                if (valid) da[base + c * vox] = (c & 1) ? d2[c >> 1].y : d2[c >> 1].x;
+            }
+        }
+        scr[warp * 3 * kC + lane] = r_db;
+        scr[warp * 3 * kC + kC + lane] = r_dg;
+        scr[warp * 3 * kC + 2 * kC + lane] = r_dbeta;
+        publish_and_sync();
+        if (tid == 0) {
+            const bool first = tile == (long long)blockIdx.x;
+            for (int s = 0; s < kTM / 8; ++s) {
+                const uint64_t ad = make_desc(smem_u32(KA) + s * 2 * kKP, kKP, kKS, 0);
+                const uint64_t bh = make_desc(smem_u32(KBh) + s * 2 * kKP, kKP, kKS, 0);
+                const uint64_t bl = make_desc(smem_u32(KBl) + s * 2 * kKP, kKP, kKS, 0);
+                mma_tf32_kk(tmem, ad, bh, idesc, !(first && s == 0));
+                mma_tf32_kk(tmem, ad, bl, idesc, 1);
+            }
+            commit(&bar);
+        }
+        pending = true;
+        if (tid < 3 * kC) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < kTM / 32; ++w) t += scr[w * 3 * kC + tid];
+            accv[tid] += t;
+        }
+        __syncthreads();            // scr is rewritten by the next tile
+    }
+    if (pending) { wait_bar(&bar, parity); parity ^= 1; }
+    // ---- flush: row r of the accumulator sits in TMEM lane 32 (r / 16) + r % 16; rows r and 32 + r add up to dW[r] ----
+    if (blockIdx.x < total_tiles) {
+        float d[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), d);
+        if (lane < 16) {
+            const int o = (warp * 16 + lane) & 31;
+#pragma unroll
+            for (int c = 0; c < kC; ++c) atomicAdd(dW + o * kC + c, d[c]);
+        }
+    }
+    for (int c = tid; c < kC; c += kTM) {
+        if (db) atomicAdd(db + c, accv[c]);
+        if (LN && dgamma) atomicAdd(dgamma + c, accv[kC + c]);
+        if (LN && dbeta) atomicAdd(dbeta + c, accv[2 * kC + c]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" :: "r"(tmem) : "memory");
+}
+
+size_t lbw_tc_smem_bytes() { return (size_t)16 * kKS + (kC * kC + 2 * kC + 3 * kC + (kTM / 32) * 3 * kC) * 4 + 1024; }
+
 size_t tc_smem_bytes() { return (size_t)2 * kTM * kMaxHid * 4 + 2 * kC * kC * 4 + 4 * kMaxHid * kC * 4 + (4 * kC + kMaxHid) * 4 + 1024; }
 
 int tc_sm_count() {
@@ -337,6 +552,25 @@ int mixer_mlp_tc_launch(const float* x, const float* m, const float* Wout, const
         mixer_mlp_fwd_tc<64><<<blocks, kTM, smem, st>>>(x, m, Wout, bout, gamma, beta, W1, b1, W2, b2, x1, out, voxels, tps, tiles, eps);
     else
         mixer_mlp_fwd_tc<32><<<blocks, kTM, smem, st>>>(x, m, Wout, bout, gamma, beta, W1, b1, W2, b2, x1, out, voxels, tps, tiles, eps);
+    FZ_LAUNCH_CHECK();
+    return FZ_OK;
+}
+
+int linear_bwd_tc_launch(const float* dy, const float* a, const float* gamma, const float* beta, const float* W, const float* resid,
+                         float* da, float* dW, float* db, float* dgamma, float* dbeta, long long batch, long long voxels, float eps,
+                         int layernorm, cudaStream_t st) {
+    const size_t smem = lbw_tc_smem_bytes();
+    static SmemConfig cfg_ln, cfg_plain;
+    FZ_CUDA_CHECK(cfg_ln.ensure(linear_bwd_tc<true>, smem));
+    FZ_CUDA_CHECK(cfg_plain.ensure(linear_bwd_tc<false>, smem));
+    const int tps = (int)((voxels + kTM - 1) / kTM);
+    const long long tiles = batch * tps;
+    const long long cap = 2LL * tc_sm_count();
+    const unsigned blocks = (unsigned)(tiles < cap ? tiles : cap);
+    if (layernorm)
+        linear_bwd_tc<true><<<blocks, kTM, smem, st>>>(dy, a, gamma, beta, W, resid, da, dW, db, dgamma, dbeta, voxels, tps, tiles, eps);
+    else
+        linear_bwd_tc<false><<<blocks, kTM, smem, st>>>(dy, a, nullptr, nullptr, W, nullptr, da, dW, db, nullptr, nullptr, voxels, tps, tiles, eps);
     FZ_LAUNCH_CHECK();
     return FZ_OK;
 }
