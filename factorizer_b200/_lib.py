@@ -59,6 +59,8 @@ _SIGNATURES = {
     "fz_layernorm_cf_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_float, c_void_p]),
     "fz_layernorm_cf_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                                          c_int64, c_float, c_void_p]),
+    "fz_set_glue_mode": (None, [c_int32]),
+    "fz_get_glue_mode": (c_int, []),
     "fz_glue_supported": (c_int, [c_int32, c_int32, c_int64]),
     "fz_ln_linear_forward": (c_int, [c_void_p] * 5 + [c_int64, c_int32, c_int64, c_float, c_void_p]),
     "fz_mixer_mlp_forward": (c_int, [c_void_p] * 12 + [c_int64, c_int32, c_int32, c_int64, c_float, c_void_p]),

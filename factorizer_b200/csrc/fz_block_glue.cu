@@ -640,6 +640,17 @@ __global__ void __launch_bounds__(kTT, 1) mlp_bwd(const float* __restrict__ x1, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// bit 0: forward out_proj + norm2 + MLP on tcgen05 (default on); bit 1: weight gradient of linear_bwd on tcgen05 (default
+// off).  FZ_GLUE_TC=<n> sets the initial value, fz_set_glue_mode() changes it.
+volatile int g_glue_mode = -1;
+int glue_mode() {
+    if (g_glue_mode < 0) {
+        const char* e = getenv("FZ_GLUE_TC");
+        g_glue_mode = e ? atoi(e) & 3 : 1;
+    }
+    return g_glue_mode;
+}
+
 int sm_count() {
     static int sms = 0;
     if (!sms) {
@@ -672,6 +683,9 @@ using namespace fz;
 
 extern "C" {
 
+void fz_set_glue_mode(int32_t mode) { g_glue_mode = mode & 3; }
+int fz_get_glue_mode(void) { return glue_mode(); }
+
 int fz_glue_supported(int32_t channels, int32_t hidden, int64_t voxels) {
     return channels == kC && voxels > 0 && voxels % 2 == 0 && hidden >= 8 && hidden % 8 == 0 && hidden <= 256;
 }
@@ -702,10 +716,8 @@ int fz_mixer_mlp_forward(const float* x, const float* m, const float* Wout, cons
     if (!x || !m || !Wout || !W1 || !W2 || !out) return fail(FZ_ERR_INVALID, "null buffer");
     if (misaligned(x) || misaligned(m) || misaligned(out) || misaligned(x1)) return fail(FZ_ERR_INVALID, "buffers must be 8-byte aligned");
     {
-        // tensor-core path (tcgen05, 3xTF32) unless FZ_GLUE_TC=0 asks for the FP32-pipe kernel
-        static int use_tc = -1;
-        if (use_tc < 0) { const char* e = getenv("FZ_GLUE_TC"); use_tc = !(e && e[0] == '0'); }
-        if (use_tc && mixer_mlp_tc_supported(hidden))
+        // tensor-core path (tcgen05, 3xTF32) unless the glue mode asks for the FP32-pipe kernel
+        if ((glue_mode() & 1) && mixer_mlp_tc_supported(hidden))
             return mixer_mlp_tc_launch(x, m, Wout, bout, gamma, beta, W1, b1, W2, b2, x1, out, batch, hidden, voxels, eps,
                                        (cudaStream_t)stream);
     }
@@ -737,10 +749,9 @@ int fz_linear_backward(const float* dy, const float* a, const float* gamma, cons
     if (dbeta) FZ_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, kC * sizeof(float), st));
     if (batch == 0 || voxels == 0) return FZ_OK;
     {
-        // weight gradient on the tensor core (tcgen05, 3xTF32) unless FZ_GLUE_TC=0
-        static int use_tc = -1;
-        if (use_tc < 0) { const char* e = getenv("FZ_GLUE_TC"); use_tc = !(e && e[0] == '0'); }
-        if (use_tc)
+        // weight gradient on the tensor core (tcgen05, 3xTF32): opt-in, measured slower than the FP32-pipe kernel as long as
+        // the per-voxel dgrad stays on the FP32 pipe (452 / 418 us against 354 / 284 us, profiles/r01g_tc_glue_ncu.md)
+        if (glue_mode() & 2)
             return linear_bwd_tc_launch(dy, a, gamma, beta, W, resid, da, dW, db, dgamma, dbeta, batch, voxels, eps, layernorm, st);
     }
     const size_t smem = linear_bwd_smem();

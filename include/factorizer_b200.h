@@ -138,6 +138,12 @@ int fz_layernorm_cf_backward(const float* x, const float* gamma, const float* dy
  * multiple of 8 up to 256 (the backward runs in slices of 64 hidden units). */
 int fz_glue_supported(int32_t channels, int32_t hidden, int64_t voxels);
 
+/* Which glue kernels run on the tensor cores (tcgen05 / TMEM, 3xTF32): bit 0 = fz_mixer_mlp_forward (hidden width 32 or
+ * 64; default on), bit 1 = the weight gradient inside fz_linear_backward (default off: measured slower).  The environment
+ * variable FZ_GLUE_TC=<mode> sets the initial value.  Both paths meet the same parity bounds. */
+void fz_set_glue_mode(int32_t mode);
+int fz_get_glue_mode(void);
+
 /* z = W LN(x): norm1 + bias-free in_proj (factorizer/factorizer.py:26,38,75; layers/norm.py:29-34). */
 int fz_ln_linear_forward(const float* x, const float* gamma, const float* beta, const float* W, float* z, int64_t batch,
                          int32_t channels, int64_t voxels, float eps, void* stream);

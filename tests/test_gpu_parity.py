@@ -282,9 +282,20 @@ def _glue_call(fn, *args):
     L.check(fn(*[a.data_ptr() if isinstance(a, torch.Tensor) else a for a in args]))
 
 
+@pytest.fixture(params=[0, 1, 3], ids=["fp32-pipe", "tc-forward", "tc-forward+wgrad"])
+def glue_mode(request):
+    """0 = every glue kernel on the FP32 pipe, 1 = forward MLP kernel on tcgen05 (default), 3 = also linear_bwd's wgrad."""
+    from factorizer_b200 import _lib as L
+    lib = L.lib()
+    before = lib.fz_get_glue_mode()
+    lib.fz_set_glue_mode(request.param)
+    yield request.param
+    lib.fz_set_glue_mode(before)
+
+
 @pytest.mark.parametrize("HID", [32, 48, 64, 136])
 @pytest.mark.parametrize("shape", [(1, 32, 8, 8, 8), (2, 32, 6, 10, 7), (3, 32, 1030)])
-def test_glue_kernels_against_torch_fp64(ft, dev, shape, HID):
+def test_glue_kernels_against_torch_fp64(ft, dev, shape, HID, glue_mode):
     """Each kernel of csrc/fz_block_glue.cu through the C ABI against fp64 torch autograd of the same
     layers (LayerNorm over channels, k=1 Conv1d, exact GELU: the reference's factorizer/layers/*)."""
     from factorizer_b200 import _lib as L
