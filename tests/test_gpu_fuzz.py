@@ -48,10 +48,12 @@ def test_fused_core_against_oracle(case):
     reshape = getattr(ft, cls)((None, *xs[1:]), **kw)
     M, N = reshape.output_size[2:]
     nmf = ft.NMF((M, N), rank=1, num_iters=T, num_grad_steps=K, init="uniform", solver=solver).to(dev)
-    dist = rng.standard_normal if (relu or solver == "hals") and solver != "mu" else rng.random
-    x_np = (dist(xs) if dist is rng.random else dist(xs)).astype(np.float32)
-    if solver == "mu":
-        x_np = np.abs(x_np) + 0.05          # MU needs non-negative, well-conditioned input
+    x_np = rng.standard_normal(xs).astype(np.float32)
+    if solver == "mu" or not relu:
+        # MU needs non-negative input; HALS on signed data without the ReLU is ill-conditioned (a row of X v can
+        # change sign, u collapses to 0 and the next sweep divides by eps: SURVEY App. C), which no fp32
+        # implementation reproduces bit-stably -- the reference's FactMixer always applies the ReLU
+        x_np = np.abs(x_np) + np.float32(0.05)
     gy_np = rng.standard_normal(xs).astype(np.float32)
     x = torch.from_numpy(x_np).to(dev).requires_grad_(True)
     y = _ops.SWNMF.apply(x, nmf.init.u0, nmf.init.v0, reshape._geom, nmf.solver_spec(), relu)
