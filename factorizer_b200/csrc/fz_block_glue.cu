@@ -14,12 +14,14 @@
 // The small matrix-vector products read the weights from shared memory as broadcast LDS.128 (4 weights
 // per load, stored input-major so 4 consecutive OUTPUTS are contiguous) and issue packed FFMA2 on output
 // pairs: 8 LDS.128 + 32 FFMA2 per input channel and voxel pair, i.e. FP32-pipe bound, not LDS bound.
-// Weight gradients are contractions over voxels: the two operands of a 512-voxel tile are staged in shared
-// memory as [row][voxel] (row stride 516 floats, so consecutive rows start 4 banks apart), every thread then
-// accumulates a small register tile of dW over a slice of the voxels, adds it to a per-CTA shared
-// accumulator, and the CTA adds its total to the global gradient once at the end (fp32 atomics).
-// Per-channel sums (bias / LayerNorm parameter gradients) use a transposing warp reduction (31 shuffles
-// for 32 values).
+// Weight gradients are contractions over voxels: the two operands of a 512-voxel (256 for linear_bwd) tile are staged in
+// shared memory as [row][voxel] (row stride 516 / 260 floats, so consecutive rows start 4 banks apart), every thread then
+// accumulates a small register tile of dW over a slice of the voxels and writes it to its warp's scratch slice; owner
+// threads add the slices into the per-CTA accumulator (fp32 atomics on shared memory are CAS loops on sm_100a), and the
+// CTA adds its total to the global gradient once at the end (global fp32 atomics).
+// Per-channel sums (bias / LayerNorm parameter gradients) use a transposing warp reduction (31 shuffles for 32 values).
+// mixer_mlp_fwd has a tensor-core twin in fz_block_glue_tc.cu (tcgen05 / TMEM, 3xTF32), which is the default for hidden
+// widths 32 and 64; fz_set_glue_mode() / FZ_GLUE_TC choose.
 #include <stdlib.h>
 
 #include "fz_common.cuh"
