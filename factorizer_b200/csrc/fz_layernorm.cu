@@ -122,6 +122,110 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_cf_bwd(const float* __re
     }
 }
 
+// ---- any channel count up to kLnMaxC: channels are looped, not held in registers ------------------------------------
+// Statistics come from shifted sums (shift = the voxel's first channel), so x is read twice (the second time from
+// L1 / L2) instead of three times; the backward keeps per-warp rows of d(gamma), d(beta) partials in shared memory.
+constexpr int kLnMaxC = 512;
+
+__device__ __forceinline__ void ln_stats(const float2* __restrict__ xp, long long pps, int C, float eps, float2& mean, float2& rstd) {
+    const float2 k = __ldg(xp);
+    float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+    for (int c = 0; c < C; ++c) {
+        const float2 v = __ldg(xp + (long long)c * pps);
+        const float dx = v.x - k.x, dy = v.y - k.y;
+        s1.x += dx; s1.y += dy;
+        s2.x = fmaf(dx, dx, s2.x); s2.y = fmaf(dy, dy, s2.y);
+    }
+    const float inv = 1.f / (float)C;
+    const float mx = s1.x * inv, my = s1.y * inv;
+    mean = make_float2(k.x + mx, k.y + my);
+    rstd = make_float2(rsqrtf(fmaxf(s2.x * inv - mx * mx, 0.f) + eps), rsqrtf(fmaxf(s2.y * inv - my * my, 0.f) + eps));
+}
+
+__global__ void __launch_bounds__(kLnThreads) layernorm_cf_fwd_any(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta, float* __restrict__ y, int C,
+                                                                   long long pairs_per_sample, long long total_pairs, float eps) {
+    __shared__ float gs[kLnMaxC], bs[kLnMaxC];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { gs[c] = gamma ? gamma[c] : 1.f; bs[c] = beta ? beta[c] : 0.f; }
+    __syncthreads();
+    const long long vox = 2 * pairs_per_sample;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total_pairs; p += (long long)gridDim.x * blockDim.x) {
+        const long long b = p / pairs_per_sample, v = p - b * pairs_per_sample;
+        const float2* xp = reinterpret_cast<const float2*>(x + b * C * vox) + v;
+        float2* yp = reinterpret_cast<float2*>(y + b * C * vox) + v;
+        float2 mean, rstd;
+        ln_stats(xp, pairs_per_sample, C, eps, mean, rstd);
+        for (int c = 0; c < C; ++c) {
+            const float2 val = __ldg(xp + (long long)c * pairs_per_sample);
+            yp[(long long)c * pairs_per_sample] = make_float2(fmaf((val.x - mean.x) * rstd.x, gs[c], bs[c]),
+                                                              fmaf((val.y - mean.y) * rstd.y, gs[c], bs[c]));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kLnThreads) layernorm_cf_bwd_any(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                   const float* __restrict__ dy, float* __restrict__ dx,
+                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta, int C,
+                                                                   long long pairs_per_sample, long long total_pairs, float eps) {
+    extern __shared__ float lsm[];
+    float* gs = lsm;                                   // [C]
+    float* part = lsm + C;                             // [warps][2 C]: d(gamma) | d(beta) partials of each warp
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) gs[c] = gamma ? gamma[c] : 1.f;
+    for (int i = threadIdx.x; i < (kLnThreads / 32) * 2 * C; i += blockDim.x) part[i] = 0.f;
+    __syncthreads();
+    float* mine = part + warp * 2 * C;
+    const long long vox = 2 * pairs_per_sample;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // whole warps iterate together (the per-channel warp sums need every lane)
+    for (long long p0 = first - lane; p0 < total_pairs; p0 += stride) {
+        const long long p = p0 + lane;
+        const bool valid = p < total_pairs;
+        const long long pc = valid ? p : 0;
+        const long long b = pc / pairs_per_sample, v = pc - b * pairs_per_sample;
+        const float2* xp = reinterpret_cast<const float2*>(x + b * C * vox) + v;
+        const float2* gp = reinterpret_cast<const float2*>(dy + b * C * vox) + v;
+        float2* op = reinterpret_cast<float2*>(dx + b * C * vox) + v;
+        float2 mean, rstd;
+        ln_stats(xp, pairs_per_sample, C, eps, mean, rstd);
+        float2 m1 = make_float2(0.f, 0.f), m2 = make_float2(0.f, 0.f);
+        for (int c = 0; c < C; ++c) {
+            const float2 xv = __ldg(xp + (long long)c * pairs_per_sample);
+            float2 g = __ldg(gp + (long long)c * pairs_per_sample);
+            if (!valid) g = make_float2(0.f, 0.f);
+            const float hx = (xv.x - mean.x) * rstd.x, hy = (xv.y - mean.y) * rstd.y;
+            if (dgamma || dbeta) {
+                const float sg = warp_sum(fmaf(g.x, hx, g.y * hy));
+                const float sb = warp_sum(g.x + g.y);
+                if (lane == 0) { mine[c] += sg; mine[C + c] += sb; }
+            }
+            const float tx = g.x * gs[c], ty = g.y * gs[c];
+            m1.x += tx; m1.y += ty;
+            m2.x = fmaf(tx, hx, m2.x); m2.y = fmaf(ty, hy, m2.y);
+        }
+        const float inv = 1.f / (float)C;
+        m1.x *= inv; m1.y *= inv; m2.x *= inv; m2.y *= inv;
+        if (valid) {
+            for (int c = 0; c < C; ++c) {
+                const float2 xv = __ldg(xp + (long long)c * pairs_per_sample);
+                const float2 g = __ldg(gp + (long long)c * pairs_per_sample);
+                const float hx = (xv.x - mean.x) * rstd.x, hy = (xv.y - mean.y) * rstd.y;
+                op[(long long)c * pairs_per_sample] = make_float2(rstd.x * (g.x * gs[c] - m1.x - hx * m2.x),
+                                                                  rstd.y * (g.y * gs[c] - m1.y - hy * m2.y));
+            }
+        }
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < 2 * C; q += blockDim.x) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < kLnThreads / 32; ++w) t += part[w * 2 * C + q];
+        float* dst = q < C ? dgamma : dbeta;
+        if (dst) atomicAdd(dst + (q < C ? q : q - C), t);
+    }
+}
+
 int sm_count() {
     static int sms = 0;
     if (!sms) {
@@ -160,8 +264,8 @@ int launch_bwd(const float* x, const float* gamma, const float* dy, float* dx, f
 int check_args(const void* a, const void* b, long long batch, int channels, long long voxels) {
     if (!a || !b) return fail(FZ_ERR_INVALID, "null buffer");
     if (batch < 0 || voxels < 0) return fail(FZ_ERR_INVALID, "negative size");
-    if (channels != 8 && channels != 16 && channels != 32)
-        return fail(FZ_ERR_UNSUPPORTED, "channels-first LayerNorm kernel handles 8, 16 or 32 channels, got %d", channels);
+    if (channels < 1 || channels > kLnMaxC)
+        return fail(FZ_ERR_UNSUPPORTED, "channels-first LayerNorm kernel handles 1..%d channels, got %d", kLnMaxC, channels);
     if (voxels % 2) return fail(FZ_ERR_UNSUPPORTED, "channels-first LayerNorm kernel needs an even number of voxels, got %lld", voxels);
     if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 7) return fail(FZ_ERR_INVALID, "buffers must be 8-byte aligned");
     return FZ_OK;
@@ -175,7 +279,7 @@ using namespace fz;
 extern "C" {
 
 int fz_layernorm_cf_supported(int32_t channels, int64_t voxels) {
-    return (channels == 8 || channels == 16 || channels == 32) && voxels % 2 == 0;
+    return channels >= 1 && channels <= kLnMaxC && voxels % 2 == 0;
 }
 
 int fz_layernorm_cf_forward(const float* x, const float* gamma, const float* beta, float* y, int64_t batch,
@@ -187,7 +291,17 @@ int fz_layernorm_cf_forward(const float* x, const float* gamma, const float* bet
     switch (channels) {
         case 8: return launch_fwd<8>(x, gamma, beta, y, batch, voxels, eps, st);
         case 16: return launch_fwd<16>(x, gamma, beta, y, batch, voxels, eps, st);
-        default: return launch_fwd<32>(x, gamma, beta, y, batch, voxels, eps, st);
+        case 32: return launch_fwd<32>(x, gamma, beta, y, batch, voxels, eps, st);
+        default: break;
+    }
+    {
+        const long long pps = voxels / 2, total = batch * pps;
+        long long blocks = (total + kLnThreads - 1) / kLnThreads;
+        const long long cap = 8LL * sm_count();
+        if (blocks > cap) blocks = cap;
+        layernorm_cf_fwd_any<<<(unsigned)blocks, kLnThreads, 0, st>>>(x, gamma, beta, y, channels, pps, total, eps);
+        FZ_LAUNCH_CHECK();
+        return FZ_OK;
     }
 }
 
@@ -205,7 +319,22 @@ int fz_layernorm_cf_backward(const float* x, const float* gamma, const float* dy
     switch (channels) {
         case 8: return launch_bwd<8>(x, gamma, dy, dx, dgamma, dbeta, batch, voxels, eps, st);
         case 16: return launch_bwd<16>(x, gamma, dy, dx, dgamma, dbeta, batch, voxels, eps, st);
-        default: return launch_bwd<32>(x, gamma, dy, dx, dgamma, dbeta, batch, voxels, eps, st);
+        case 32: return launch_bwd<32>(x, gamma, dy, dx, dgamma, dbeta, batch, voxels, eps, st);
+        default: break;
+    }
+    {
+        const long long pps = voxels / 2, total = batch * pps;
+        long long blocks = (total + kLnThreads - 1) / kLnThreads;
+        const long long cap = 4LL * sm_count();
+        if (blocks > cap) blocks = cap;
+        if (dgamma) FZ_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, channels * sizeof(float), st));
+        if (dbeta) FZ_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, channels * sizeof(float), st));
+        const size_t smem = sizeof(float) * ((size_t)channels + (kLnThreads / 32) * 2 * (size_t)channels);
+        static SmemConfig cfg;
+        FZ_CUDA_CHECK(cfg.ensure(layernorm_cf_bwd_any, smem));
+        layernorm_cf_bwd_any<<<(unsigned)blocks, kLnThreads, smem, st>>>(x, gamma, dy, dx, dgamma, dbeta, channels, pps, total, eps);
+        FZ_LAUNCH_CHECK();
+        return FZ_OK;
     }
 }
 

@@ -121,8 +121,9 @@ int fz_swnmf_backward(const float* x, const float* gy, const float* u0, const fl
 
 /* LayerNorm over the channel axis of a (batch, channels, voxels) tensor
  * (factorizer/layers/norm.py:25-34: movedim -> nn.LayerNorm(channels) -> movedim; biased variance, eps
- * inside the square root).  gamma / beta may be NULL (no affine).  Kernels exist for 8, 16 and 32
- * channels and an even number of voxels; fz_layernorm_cf_supported() tells. */
+ * inside the square root).  gamma / beta may be NULL (no affine).  Any channel count up to 512 (8, 16, 32 keep
+ * all channels of a voxel in registers, the others loop) and an even number of voxels;
+ * fz_layernorm_cf_supported() tells. */
 int fz_layernorm_cf_supported(int32_t channels, int64_t voxels);
 int fz_layernorm_cf_forward(const float* x, const float* gamma, const float* beta, float* y, int64_t batch,
                             int32_t channels, int64_t voxels, float eps, void* stream);

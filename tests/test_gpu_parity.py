@@ -452,7 +452,9 @@ def test_full_size_properties(ft, dev):
     assert torch.allclose(y1, x1, rtol=1e-4, atol=1e-5)
 
 
-@pytest.mark.parametrize("shape", [(2, 32, 8, 8, 8), (1, 16, 6, 10, 4), (3, 8, 50), (1, 32, 16, 16, 16)])
+@pytest.mark.parametrize("shape", [(2, 32, 8, 8, 8), (1, 16, 6, 10, 4), (3, 8, 50), (1, 32, 16, 16, 16),
+                                   (2, 64, 16, 16, 16), (1, 24, 6, 10, 4), (2, 128, 8, 8, 8), (3, 512, 4, 4, 4), (1, 5, 7, 6),
+                                   (1, 256, 2, 33, 1)])
 def test_layernorm_channels_first(ft, dev, shape):
     """ft.LayerNorm (hand-written channels-first kernel) against torch's own layer_norm on the permuted
     tensor, which is literally what the reference does (factorizer/layers/norm.py:25-34): output, input
@@ -484,8 +486,9 @@ def test_layernorm_channels_first(ft, dev, shape):
 def test_layernorm_fallback_shapes(ft, dev):
     """Channel counts / voxel counts without a kernel take the reference's own permute + nn.LayerNorm route."""
     from factorizer_b200 import _ops
-    x = torch.randn(2, 24, 5, 3, device=dev)
+    x = torch.randn(2, 24, 5, 3, device=dev)          # odd number of voxels
     assert not _ops.layernorm_cf_supported(x)
+    assert not _ops.layernorm_cf_supported(torch.randn(1, 600, 4, 4, device=dev))
     ln = ft.LayerNorm(24).to(dev)
     ref = torch.nn.functional.layer_norm(x.movedim(1, -1), (24,), ln.norm.weight, ln.norm.bias, ln.norm.eps).movedim(-1, 1)
     assert torch.allclose(ln(x), ref)
