@@ -8,6 +8,7 @@ import factorizer_b200 as ft
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "train"
 dev = torch.device('cuda:0')
+torch.backends.cudnn.benchmark = True
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 n = 128

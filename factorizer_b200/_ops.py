@@ -409,3 +409,46 @@ class LayerNormCF(torch.autograd.Function):
             _call(lib.fz_layernorm_cf_backward, L.ptr(x), L.ptr(w), L.ptr(gy), L.ptr(gx), L.ptr(gw), L.ptr(gb), B, C, vox,
                   ctx.eps, L.stream_ptr(x.device))
         return gx, gw, gb, None
+
+
+# ---- pointwise channel map (k = 1 Conv1d) with a hand-written weight gradient -------------------
+def linear_wgrad_supported(x: torch.Tensor, out_channels: int) -> bool:
+    """The contraction over voxels is worth a kernel of its own when it is long (library SGEMMs take their slow
+    large-K route there); short ones stay with cuBLAS."""
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() >= 3):
+        return False
+    vox = x.numel() // max(x.shape[0] * x.shape[1], 1)
+    if x.shape[0] * vox < 16384:
+        return False
+    return bool(L.lib().fz_linear_wgrad_supported(int(out_channels), x.shape[1], vox))
+
+
+class LinearCF(torch.autograd.Function):
+    """y = W x (+ b) over the channel axis of a (B, C_in, voxels) tensor (reference factorizer/layers/linear.py:53-58).
+    Forward and input gradient are cuBLAS GEMMs; the weight / bias gradients come from csrc/fz_linear.cu."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        B = x.shape[0]
+        wb = weight.unsqueeze(0).expand(B, -1, -1)
+        y = torch.bmm(wb, x) if bias is None else torch.baddbmm(bias[None, :, None], wb, x)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        lib = L.lib()
+        gy = L.require_cuda_f32(gy, "grad")
+        B, cin, vox = x.shape
+        cout = weight.shape[0]
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.bmm(weight.t().unsqueeze(0).expand(B, -1, -1), gy)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            gw = torch.empty_like(weight)
+            gb = torch.empty(cout, device=x.device, dtype=torch.float32) if ctx.has_bias else None
+            with torch.cuda.device(x.device):
+                _call(lib.fz_linear_wgrad, L.ptr(gy), L.ptr(x), L.ptr(gw), L.ptr(gb), B, cout, cin, vox, L.stream_ptr(x.device))
+        return gx, gw, gb

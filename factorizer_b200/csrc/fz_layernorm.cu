@@ -130,6 +130,7 @@ constexpr int kLnMaxC = 512;
 __device__ __forceinline__ void ln_stats(const float2* __restrict__ xp, long long pps, int C, float eps, float2& mean, float2& rstd) {
     const float2 k = __ldg(xp);
     float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+#pragma unroll 8
     for (int c = 0; c < C; ++c) {
         const float2 v = __ldg(xp + (long long)c * pps);
         const float dx = v.x - k.x, dy = v.y - k.y;
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_cf_fwd_any(const float* 
         float2* yp = reinterpret_cast<float2*>(y + b * C * vox) + v;
         float2 mean, rstd;
         ln_stats(xp, pairs_per_sample, C, eps, mean, rstd);
+#pragma unroll 8
         for (int c = 0; c < C; ++c) {
             const float2 val = __ldg(xp + (long long)c * pairs_per_sample);
             yp[(long long)c * pairs_per_sample] = make_float2(fmaf((val.x - mean.x) * rstd.x, gs[c], bs[c]),
@@ -163,22 +165,41 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_cf_fwd_any(const float* 
     }
 }
 
+// Transposing warp reduction of 32 values per lane: lane l ends up with the warp-wide total of element l (31 shuffles
+// instead of 160 for 32 separate butterfly sums).
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
+    int off = 16;
+#pragma unroll
+    for (int n = 32; n > 1; n >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float keep = up ? v[i + n / 2] : v[i];
+            const float send = up ? v[i] : v[i + n / 2];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+        off >>= 1;
+    }
+    return v[0];
+}
+
 __global__ void __launch_bounds__(kLnThreads) layernorm_cf_bwd_any(const float* __restrict__ x, const float* __restrict__ gamma,
                                                                    const float* __restrict__ dy, float* __restrict__ dx,
                                                                    float* __restrict__ dgamma, float* __restrict__ dbeta, int C,
                                                                    long long pairs_per_sample, long long total_pairs, float eps) {
     extern __shared__ float lsm[];
-    float* gs = lsm;                                   // [C]
-    float* part = lsm + C;                             // [warps][2 C]: d(gamma) | d(beta) partials of each warp
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) gs[c] = gamma ? gamma[c] : 1.f;
-    for (int i = threadIdx.x; i < (kLnThreads / 32) * 2 * C; i += blockDim.x) part[i] = 0.f;
+    const int CP = (C + 31) & ~31;                     // channels rounded up to whole chunks of 32
+    float* gs = lsm;                                   // [CP]
+    float* part = lsm + CP;                            // [warps][2 CP]: d(gamma) | d(beta) partials of each warp
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+    for (int c = threadIdx.x; c < CP; c += blockDim.x) gs[c] = (c < C && gamma) ? gamma[c] : (c < C ? 1.f : 0.f);
+    for (int i = threadIdx.x; i < warps * 2 * CP; i += blockDim.x) part[i] = 0.f;
     __syncthreads();
-    float* mine = part + warp * 2 * C;
+    float* mine = part + warp * 2 * CP;
     const long long vox = 2 * pairs_per_sample;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    // whole warps iterate together (the per-channel warp sums need every lane)
+    // whole warps iterate together (the per-channel sums over voxels are warp reductions)
     for (long long p0 = first - lane; p0 < total_pairs; p0 += stride) {
         const long long p = p0 + lane;
         const bool valid = p < total_pairs;
@@ -190,23 +211,31 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_cf_bwd_any(const float* 
         float2 mean, rstd;
         ln_stats(xp, pairs_per_sample, C, eps, mean, rstd);
         float2 m1 = make_float2(0.f, 0.f), m2 = make_float2(0.f, 0.f);
-        for (int c = 0; c < C; ++c) {
-            const float2 xv = __ldg(xp + (long long)c * pairs_per_sample);
-            float2 g = __ldg(gp + (long long)c * pairs_per_sample);
-            if (!valid) g = make_float2(0.f, 0.f);
-            const float hx = (xv.x - mean.x) * rstd.x, hy = (xv.y - mean.y) * rstd.y;
-            if (dgamma || dbeta) {
-                const float sg = warp_sum(fmaf(g.x, hx, g.y * hy));
-                const float sb = warp_sum(g.x + g.y);
-                if (lane == 0) { mine[c] += sg; mine[C + c] += sb; }
+        for (int c0 = 0; c0 < C; c0 += 32) {
+            float sg[32], sb[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int c = min(c0 + j, C - 1);                  // the tail chunk re-reads the last channel, weighted 0
+                const float2 xv = __ldg(xp + (long long)c * pairs_per_sample);
+                float2 g = __ldg(gp + (long long)c * pairs_per_sample);
+                if (!valid || c0 + j >= C) g = make_float2(0.f, 0.f);
+                const float hx = (xv.x - mean.x) * rstd.x, hy = (xv.y - mean.y) * rstd.y;
+                sg[j] = fmaf(g.x, hx, g.y * hy);
+                sb[j] = g.x + g.y;
+                const float w = gs[c0 + j];
+                const float tx = g.x * w, ty = g.y * w;
+                m1.x += tx; m1.y += ty;
+                m2.x = fmaf(tx, hx, m2.x); m2.y = fmaf(ty, hy, m2.y);
             }
-            const float tx = g.x * gs[c], ty = g.y * gs[c];
-            m1.x += tx; m1.y += ty;
-            m2.x = fmaf(tx, hx, m2.x); m2.y = fmaf(ty, hy, m2.y);
+            if (dgamma || dbeta) {
+                mine[c0 + lane] += warp_transpose_sum32(sg, lane);
+                mine[CP + c0 + lane] += warp_transpose_sum32(sb, lane);
+            }
         }
         const float inv = 1.f / (float)C;
         m1.x *= inv; m1.y *= inv; m2.x *= inv; m2.y *= inv;
         if (valid) {
+#pragma unroll 8
             for (int c = 0; c < C; ++c) {
                 const float2 xv = __ldg(xp + (long long)c * pairs_per_sample);
                 const float2 g = __ldg(gp + (long long)c * pairs_per_sample);
@@ -217,12 +246,13 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_cf_bwd_any(const float* 
         }
     }
     __syncthreads();
-    for (int q = threadIdx.x; q < 2 * C; q += blockDim.x) {
+    for (int q = threadIdx.x; q < 2 * CP; q += blockDim.x) {
+        const int c = q < CP ? q : q - CP;
+        if (c >= C) continue;
         float t = 0.f;
-#pragma unroll
-        for (int w = 0; w < kLnThreads / 32; ++w) t += part[w * 2 * C + q];
-        float* dst = q < C ? dgamma : dbeta;
-        if (dst) atomicAdd(dst + (q < C ? q : q - C), t);
+        for (int w = 0; w < warps; ++w) t += part[w * 2 * CP + q];
+        float* dst = q < CP ? dgamma : dbeta;
+        if (dst) atomicAdd(dst + c, t);
     }
 }
 
@@ -296,10 +326,11 @@ int fz_layernorm_cf_forward(const float* x, const float* gamma, const float* bet
     }
     {
         const long long pps = voxels / 2, total = batch * pps;
-        long long blocks = (total + kLnThreads - 1) / kLnThreads;
+        const int threads = total >= 256LL * sm_count() ? kLnThreads : 64;   // few voxels: spread them over more SMs
+        long long blocks = (total + threads - 1) / threads;
         const long long cap = 8LL * sm_count();
         if (blocks > cap) blocks = cap;
-        layernorm_cf_fwd_any<<<(unsigned)blocks, kLnThreads, 0, st>>>(x, gamma, beta, y, channels, pps, total, eps);
+        layernorm_cf_fwd_any<<<(unsigned)blocks, threads, 0, st>>>(x, gamma, beta, y, channels, pps, total, eps);
         FZ_LAUNCH_CHECK();
         return FZ_OK;
     }
@@ -324,15 +355,17 @@ int fz_layernorm_cf_backward(const float* x, const float* gamma, const float* dy
     }
     {
         const long long pps = voxels / 2, total = batch * pps;
-        long long blocks = (total + kLnThreads - 1) / kLnThreads;
+        const int threads = total >= 256LL * sm_count() ? kLnThreads : 64;
+        long long blocks = (total + threads - 1) / threads;
         const long long cap = 4LL * sm_count();
         if (blocks > cap) blocks = cap;
         if (dgamma) FZ_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, channels * sizeof(float), st));
         if (dbeta) FZ_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, channels * sizeof(float), st));
-        const size_t smem = sizeof(float) * ((size_t)channels + (kLnThreads / 32) * 2 * (size_t)channels);
+        const size_t cp = ((size_t)channels + 31) & ~(size_t)31;
+        const size_t smem = sizeof(float) * (cp + (threads / 32) * 2 * cp);
         static SmemConfig cfg;
-        FZ_CUDA_CHECK(cfg.ensure(layernorm_cf_bwd_any, smem));
-        layernorm_cf_bwd_any<<<(unsigned)blocks, kLnThreads, smem, st>>>(x, gamma, dy, dx, dgamma, dbeta, channels, pps, total, eps);
+        FZ_CUDA_CHECK(cfg.ensure(layernorm_cf_bwd_any, sizeof(float) * (kLnMaxC + (kLnThreads / 32) * 2 * kLnMaxC)));
+        layernorm_cf_bwd_any<<<(unsigned)blocks, threads, smem, st>>>(x, gamma, dy, dx, dgamma, dbeta, channels, pps, total, eps);
         FZ_LAUNCH_CHECK();
         return FZ_OK;
     }

@@ -1,6 +1,7 @@
 """Channels-first glue layers around the hot path.  LayerNorm runs a
 hand-written channels-first kernel (csrc/fz_layernorm.cu) where it applies; Linear is a cuBLAS GEMM on the
-(C_out, C_in) x (C_in, voxels) view instead of a k=1 cuDNN convolution; GELU / residual adds are ATen.  Module and parameter names match the reference so its checkpoints load:
+(C_out, C_in) x (C_in, voxels) view instead of a k=1 cuDNN convolution, with its own weight-gradient kernel
+(csrc/fz_linear.cu) when the contraction over voxels is long; GELU / residual adds are ATen.  Module and parameter names match the reference so its checkpoints load:
 ``Linear.linear`` (factorizer/layers/linear.py:43-58), ``LayerNorm.norm`` (layers/norm.py:25-34),
 ``MLP.block.{0,3}`` (layers/mlp.py:40-63), ``PositionalEmbedding.pos`` (layers/pos_embed.py:70-89).
 """
@@ -29,6 +30,10 @@ class Linear(nn.Module):
         shape = x.shape
         w = self.linear.weight.squeeze(-1)
         xf = self.flatten(x)                                  # (B, C_in, voxels): a view, no copy
+        from . import _ops
+        if torch.is_grad_enabled() and w.requires_grad and xf.is_contiguous() and _ops.linear_wgrad_supported(xf, w.shape[0]):
+            # long contractions over voxels: hand-written weight-gradient kernel (csrc/fz_linear.cu)
+            return _ops.LinearCF.apply(xf, w, self.linear.bias).view(shape[0], -1, *shape[2:])
         if self.linear.bias is not None:
             y = torch.baddbmm(self.linear.bias[None, :, None], w.unsqueeze(0).expand(shape[0], -1, -1), xf)
         else:

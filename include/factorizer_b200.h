@@ -131,6 +131,16 @@ int fz_layernorm_cf_forward(const float* x, const float* gamma, const float* bet
 int fz_layernorm_cf_backward(const float* x, const float* gamma, const float* dy, float* dx, float* dgamma,
                              float* dbeta, int64_t batch, int32_t channels, int64_t voxels, float eps, void* stream);
 
+/* ---- weight gradient of the pointwise channel map (reference factorizer/layers/linear.py:53-58, a k=1 Conv1d) ----
+ * dW[o][i] = sum over batch and voxels of dy[b][o][v] x[b][i][v]   (cout x cin floats, OVERWRITTEN)
+ * db[o]    = sum over batch and voxels of dy[b][o][v]              (cout floats, OVERWRITTEN; may be NULL)
+ * dy is (batch, cout, voxels), x is (batch, cin, voxels), fp32 contiguous.  Channel counts must be multiples of 32
+ * and voxels a multiple of 4; fz_linear_wgrad_supported() tells.  Replaces the large-K library SGEMM autograd picks
+ * for the 64..512-channel stages of the Swin Factorizer. */
+int fz_linear_wgrad_supported(int32_t cout, int32_t cin, int64_t voxels);
+int fz_linear_wgrad(const float* dy, const float* x, float* dW, float* db, int64_t batch, int32_t cout, int32_t cin,
+                    int64_t voxels, void* stream);
+
 /* ---- FactMixer / FactorizerBlock pointwise glue, 32-channel blocks --------
  * All tensors are (batch, channels, voxels) fp32 = flattened NCDHW; weights are the reference's Conv1d(k=1)
  * weights squeezed to (out, in) (factorizer/layers/linear.py:43-50).  Gradient outputs are OVERWRITTEN. */

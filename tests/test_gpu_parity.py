@@ -483,6 +483,35 @@ def test_layernorm_channels_first(ft, dev, shape):
     assert_close(_np(gb) / scale, _np(rb) / scale, what="gb")
 
 
+@pytest.mark.parametrize("shape,cout,bias", [((1, 64, 32, 32, 32), 128, True), ((2, 96, 8200), 64, True),
+                                             ((1, 32, 40, 40, 12), 32, False), ((3, 128, 24, 24, 24), 256, True)])
+def test_linear_weight_gradient_kernel(ft, dev, shape, cout, bias):
+    """ft.Linear on long voxel axes: output and input gradient are library GEMMs, the weight / bias gradients come
+    from csrc/fz_linear.cu; all four against the reference's formulation (a k=1 Conv1d, layers/linear.py:53-58) in
+    fp64."""
+    from factorizer_b200 import _ops
+    torch.manual_seed(3)
+    lin = ft.Linear(shape[1], cout, bias=bias).to(dev)
+    x = torch.randn(shape, device=dev, requires_grad=True)
+    gy = torch.randn(shape[0], cout, *shape[2:], device=dev)
+    assert _ops.linear_wgrad_supported(x.flatten(2), cout)
+    y = lin(x)
+    params = [lin.linear.weight] + ([lin.linear.bias] if bias else [])
+    grads = torch.autograd.grad((y * gy).sum(), [x] + params)
+    x64 = x.detach().double().requires_grad_(True)
+    p64 = [p.detach().double().requires_grad_(True) for p in params]
+    y64 = torch.nn.functional.conv1d(x64.flatten(2), p64[0], p64[1] if bias else None).view(gy.shape)
+    refs = torch.autograd.grad((y64 * gy.double()).sum(), [x64] + p64)
+    assert_close(_np(y), _np(y64), what="y")
+    for name, g, r in zip(["gx", "gw", "gb"], grads, refs):
+        assert g.shape == r.shape
+        scale = max(1.0, float(r.abs().max()))
+        assert_close(_np(g) / scale, _np(r) / scale, what=name)
+    # short voxel axes and odd channel counts stay with the library path
+    assert not _ops.linear_wgrad_supported(torch.randn(1, 64, 8, 8, 8, device=dev).flatten(2), 64)
+    assert not _ops.linear_wgrad_supported(torch.randn(1, 48, 32, 32, 32, device=dev).flatten(2), 40)
+
+
 def test_layernorm_fallback_shapes(ft, dev):
     """Channel counts / voxel counts without a kernel take the reference's own permute + nn.LayerNorm route."""
     from factorizer_b200 import _ops
