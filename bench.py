@@ -8,7 +8,7 @@ ft.NMF(rank 1, 5 HALS sweeps) + inverse, forward + backward on one (1, 32, 128^3
 i.e. the fused FactMixer core that FactorizerBlock runs between its two 1x1 projections.  A "step" is
 one forward + one backward through the C ABI (fz_swnmf_forward / fz_swnmf_backward).  The same line
 also carries the whole FactorizerBlock (BASELINE config 3: fused glue kernels around the fused core) in
-`block`.
+`block`, and the whole Swin Factorizer (configs 4-5: inference pass and single-rank training step) in `model`.
 
 value      voxels/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks); the K steps are
            timed twice, as plain stream launches (which also gives the fwd / bwd split) and replayed from one CUDA graph
@@ -166,6 +166,75 @@ class ClockSampler:
         os.unlink(self.path)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def model_leg(dev, n=128, steps=3):
+    """Configs 4 and 5: the README Swin Factorizer on this package's kernels, one 128^3 volume per GPU --
+    an inference pass and a training step (forward, sigmoid-BCE + soft-Dice, backward, AdamW), fp32, cuDNN / cuBLAS for
+    the convolutions and the wide stages' GEMMs.  Side measurement; never raises."""
+    import torch
+    import factorizer_b200 as ft
+    from torch import nn
+    keep = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        torch.backends.cudnn.benchmark = True       # the heuristic choice for the 4->32 stem's fp32 wgrad is 10x slower
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.manual_seed(1234)
+        net = ft.Factorizer(in_channels=4, out_channels=3, spatial_size=(n, n, n), encoder_depth=(1, 1, 1, 1, 1),
+                            encoder_width=(32, 64, 128, 256, 512), strides=(1, 2, 2, 2, 2), decoder_depth=(1, 1, 1, 1),
+                            norm=ft.LayerNorm, reshape=(ft.SWMatricize, {"head_dim": HEAD_DIM, "patch_size": PATCH}),
+                            act=nn.ReLU, factorize=ft.NMF, rank=1, num_iters=T_ITERS, init="uniform", solver="hals",
+                            mlp_ratio=2, dropout=0.1).to(dev)
+        x = torch.rand(1, 4, n, n, n, device=dev)
+        target = torch.randint(0, 2, (1, 3, n, n, n), device=dev).float()
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+
+        def timed(fn):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize(dev)
+            a, b = ev(), ev()
+            a.record()
+            for _ in range(steps):
+                fn()
+            b.record()
+            torch.cuda.synchronize(dev)
+            return a.elapsed_time(b) / steps
+
+        net.eval()
+        with torch.no_grad():
+            infer_ms = timed(lambda: net(x))
+        net.train()
+        opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-5)
+
+        def train_step():
+            opt.zero_grad(set_to_none=True)
+            logits = net(x)
+            p = torch.sigmoid(logits)
+            dice = 1 - (2 * (p * target).sum((2, 3, 4)) + 1e-5) / (p.sum((2, 3, 4)) + target.sum((2, 3, 4)) + 1e-5)
+            loss = nn.functional.binary_cross_entropy_with_logits(logits, target) + dice.mean()
+            loss.backward()
+            opt.step()
+
+        train_ms = timed(train_step)
+        out = {"workload": f"Swin Factorizer (README 78-96) 4->3 ch, {n}^3, widths (32,64,128,256,512), HALS r1, B=1/GPU, fp32, "
+                           "cudnn.benchmark; convolutions and wide-stage GEMMs are cuDNN / cuBLAS",
+               "params": sum(q.numel() for q in net.parameters()),
+               "infer_ms": infer_ms, "infer_voxels_per_s_per_gpu": n ** 3 / (infer_ms * 1e-3),
+               "train_step_ms": train_ms, "train_voxels_per_s_per_gpu": n ** 3 / (train_ms * 1e-3),
+               "train_step": "forward, sigmoid-BCE + soft-Dice, backward, AdamW; no gradient all-reduce (single-rank step)"}
+        del net, opt, x, target
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:                              # a side measurement must not cost the bench line
+        try:
+            torch.cuda.synchronize(dev)
+        except Exception:
+            pass
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = keep
 
 
 def run_ours(args):
@@ -365,6 +434,7 @@ def run_ours(args):
         barrier()
         bms = b0.elapsed_time(b1) / nb
         block_launch = "stream launches from autograd"
+        bgraph = None
         try:        # the same step replayed from one CUDA graph (forward, autograd backward, gradient accumulation)
             for p_ in blk.parameters():
                 p_.grad = None
@@ -400,6 +470,15 @@ def run_ours(args):
                  "path": "hand-written glue kernels (fz_block_glue.cu on the FP32 pipe; forward out_proj+norm2+MLP on tcgen05/TMEM, 3xTF32, fz_block_glue_tc.cu) + fused core: 3 launches fwd, 4 bwd" if block_fused
                          else "layer by layer (library GEMMs) around the fused core",
                  "launch": block_launch, "ms_per_step": bms, "voxels_per_s_per_gpu": N ** 3 / (bms * 1e-3)}
+
+    # ---------------- whole model (configs 4 and 5), every rank its own replica ----------------
+    model = None
+    if not args.no_model:
+        if block is not None:
+            blk = xb = bgraph = None                # release the block leg's tensors and graph pool
+        torch.cuda.empty_cache()
+        model = model_leg(dev)
+        barrier()
 
     # ---------------- reduce over ranks ----------------
     dom_us = passes_us["phase_bwd_apply"] if passes_us else bwd_us
@@ -455,6 +534,8 @@ def run_ours(args):
             block["hbm_frac_of_absolute_floor"] = 5 * n_el * 4 / (block_ms * 1e-3) / 1e9 / peak
             block.pop("voxels_per_s_per_gpu", None)
             line["block"] = block
+        if model:
+            line["model"] = model
         if world == 1 and not args.no_cpu:
             os.sched_setaffinity(0, all_cpus)       # the CPU baseline gets every core again
             rate, times, threads = cpu_reference_rate(64, 3)
@@ -473,6 +554,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-block", action="store_true", help="skip the FactorizerBlock (config 3) side measurement")
+    ap.add_argument("--no-model", action="store_true", help="skip the whole-model (configs 4-5) side measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
