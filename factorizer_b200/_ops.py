@@ -418,7 +418,7 @@ def linear_wgrad_supported(x: torch.Tensor, out_channels: int) -> bool:
     if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() >= 3):
         return False
     vox = x.numel() // max(x.shape[0] * x.shape[1], 1)
-    if x.shape[0] * vox < 16384:
+    if x.shape[0] * vox < 4096:
         return False
     return bool(L.lib().fz_linear_wgrad_supported(int(out_channels), x.shape[1], vox))
 

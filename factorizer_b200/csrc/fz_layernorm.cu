@@ -256,6 +256,161 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_cf_bwd_any(const float* 
     }
 }
 
+int sm_count();
+int sm_count_cached() { return sm_count(); }
+
+// ---- few voxels, many channels (the deep stages: 128 ch at 32^3 ... 512 ch at 8^3) -------------------------------------
+// A thread walking all C channels of its voxel pair is one long latency chain there and the grid is a handful of CTAs.
+// Sliced form: blockDim = (32 voxel pairs, SL channel slices); every warp owns C / SL channels of the CTA's 32 pairs,
+// the per-voxel statistics are combined across slices through shared memory.
+constexpr int kLnMaxSlices = 8;
+
+__device__ __forceinline__ void slice_range(int C, int& cbeg, int& cend) {
+    const int per = (C + blockDim.y - 1) / blockDim.y;
+    cbeg = min((int)threadIdx.y * per, C);
+    cend = min(cbeg + per, C);
+}
+
+// partial shifted sums of this slice -> totals over all slices (every thread of a pair column gets the same values)
+__device__ __forceinline__ void sliced_stats(const float2* __restrict__ xp, long long pps, int C, int cbeg, int cend, float eps,
+                                             float2 (*sa)[32], float2 (*sb)[32], float2& mean, float2& rstd) {
+    const int lane = threadIdx.x;
+    const float2 k = __ldg(xp);
+    float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+#pragma unroll 8
+    for (int c = cbeg; c < cend; ++c) {
+        const float2 v = __ldg(xp + (long long)c * pps);
+        const float dx = v.x - k.x, dy = v.y - k.y;
+        s1.x += dx; s1.y += dy;
+        s2.x = fmaf(dx, dx, s2.x); s2.y = fmaf(dy, dy, s2.y);
+    }
+    sa[threadIdx.y][lane] = s1;
+    sb[threadIdx.y][lane] = s2;
+    __syncthreads();
+    s1 = make_float2(0.f, 0.f); s2 = make_float2(0.f, 0.f);
+    for (int w = 0; w < (int)blockDim.y; ++w) {
+        const float2 a = sa[w][lane], b = sb[w][lane];
+        s1.x += a.x; s1.y += a.y; s2.x += b.x; s2.y += b.y;
+    }
+    const float inv = 1.f / (float)C;
+    const float mx = s1.x * inv, my = s1.y * inv;
+    mean = make_float2(k.x + mx, k.y + my);
+    rstd = make_float2(rsqrtf(fmaxf(s2.x * inv - mx * mx, 0.f) + eps), rsqrtf(fmaxf(s2.y * inv - my * my, 0.f) + eps));
+}
+
+__global__ void __launch_bounds__(32 * kLnMaxSlices) layernorm_cf_fwd_sliced(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                             const float* __restrict__ beta, float* __restrict__ y, int C,
+                                                                             long long pairs_per_sample, long long total_pairs, float eps) {
+    __shared__ float2 sa[kLnMaxSlices][32], sb[kLnMaxSlices][32];
+    const int lane = threadIdx.x;
+    int cbeg, cend;
+    slice_range(C, cbeg, cend);
+    const long long vox = 2 * pairs_per_sample;
+    for (long long p0 = 32LL * blockIdx.x; p0 < total_pairs; p0 += 32LL * gridDim.x) {
+        const long long p = p0 + lane;
+        const bool valid = p < total_pairs;
+        const long long pc = valid ? p : 0;
+        const long long b = pc / pairs_per_sample, v = pc - b * pairs_per_sample;
+        const float2* xp = reinterpret_cast<const float2*>(x + b * C * vox) + v;
+        float2* yp = reinterpret_cast<float2*>(y + b * C * vox) + v;
+        float2 mean, rstd;
+        sliced_stats(xp, pairs_per_sample, C, cbeg, cend, eps, sa, sb, mean, rstd);
+        if (valid) {
+#pragma unroll 8
+            for (int c = cbeg; c < cend; ++c) {
+                const float2 val = __ldg(xp + (long long)c * pairs_per_sample);
+                const float g = gamma ? __ldg(gamma + c) : 1.f, bb = beta ? __ldg(beta + c) : 0.f;
+                yp[(long long)c * pairs_per_sample] = make_float2(fmaf((val.x - mean.x) * rstd.x, g, bb), fmaf((val.y - mean.y) * rstd.y, g, bb));
+            }
+        }
+        __syncthreads();          // sa / sb are rewritten by the next group
+    }
+}
+
+__global__ void __launch_bounds__(32 * kLnMaxSlices, 2) layernorm_cf_bwd_sliced(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                             const float* __restrict__ dy, float* __restrict__ dx,
+                                                                             float* __restrict__ dgamma, float* __restrict__ dbeta, int C,
+                                                                             long long pairs_per_sample, long long total_pairs, float eps) {
+    extern __shared__ float lsm[];
+    __shared__ float2 sa[kLnMaxSlices][32], sb[kLnMaxSlices][32];
+    float* part = lsm;                                 // d(gamma) [C] | d(beta) [C]; every slice touches its own channels only
+    float* gs = lsm + 2 * C;                           // gamma [C]
+    const int lane = threadIdx.x, tid = threadIdx.y * 32 + lane, nthr = 32 * blockDim.y;
+    for (int i = tid; i < 2 * C; i += nthr) part[i] = 0.f;
+    for (int i = tid; i < C; i += nthr) gs[i] = gamma ? gamma[i] : 1.f;
+    __syncthreads();
+    int cbeg, cend;
+    slice_range(C, cbeg, cend);
+    const long long vox = 2 * pairs_per_sample;
+    for (long long p0 = 32LL * blockIdx.x; p0 < total_pairs; p0 += 32LL * gridDim.x) {
+        const long long p = p0 + lane;
+        const bool valid = p < total_pairs;
+        const long long pc = valid ? p : 0;
+        const long long b = pc / pairs_per_sample, v = pc - b * pairs_per_sample;
+        const float2* xp = reinterpret_cast<const float2*>(x + b * C * vox) + v;
+        const float2* gp = reinterpret_cast<const float2*>(dy + b * C * vox) + v;
+        float2* op = reinterpret_cast<float2*>(dx + b * C * vox) + v;
+        float2 mean, rstd;
+        sliced_stats(xp, pairs_per_sample, C, cbeg, cend, eps, sa, sb, mean, rstd);
+        float2 m1 = make_float2(0.f, 0.f), m2 = make_float2(0.f, 0.f);
+        for (int c0 = cbeg; c0 < cend; c0 += 32) {
+            float sg[32], sbv[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const bool live = c0 + j < cend;
+                const int c = live ? c0 + j : cend - 1;            // the tail chunk re-reads the last channel, weighted 0
+                const float2 xv = __ldg(xp + (long long)c * pairs_per_sample);
+                float2 g = __ldg(gp + (long long)c * pairs_per_sample);
+                if (!valid || !live) g = make_float2(0.f, 0.f);
+                const float hx = (xv.x - mean.x) * rstd.x, hy = (xv.y - mean.y) * rstd.y;
+                sg[j] = fmaf(g.x, hx, g.y * hy);
+                sbv[j] = g.x + g.y;
+                const float w = gs[c];
+                const float tx = g.x * w, ty = g.y * w;
+                m1.x += tx; m1.y += ty;
+                m2.x = fmaf(tx, hx, m2.x); m2.y = fmaf(ty, hy, m2.y);
+            }
+            if (dgamma || dbeta) {
+                const float rg = warp_transpose_sum32(sg, lane), rb = warp_transpose_sum32(sbv, lane);
+                if (c0 + lane < cend) { part[c0 + lane] += rg; part[C + c0 + lane] += rb; }
+            }
+        }
+        __syncthreads();          // everyone has read the statistics partials
+        sa[threadIdx.y][lane] = m1;
+        sb[threadIdx.y][lane] = m2;
+        __syncthreads();
+        m1 = make_float2(0.f, 0.f); m2 = make_float2(0.f, 0.f);
+        for (int w = 0; w < (int)blockDim.y; ++w) {
+            const float2 a = sa[w][lane], bq = sb[w][lane];
+            m1.x += a.x; m1.y += a.y; m2.x += bq.x; m2.y += bq.y;
+        }
+        const float inv = 1.f / (float)C;
+        m1.x *= inv; m1.y *= inv; m2.x *= inv; m2.y *= inv;
+        if (valid) {
+#pragma unroll 8
+            for (int c = cbeg; c < cend; ++c) {
+                const float2 xv = __ldg(xp + (long long)c * pairs_per_sample);
+                const float2 g = __ldg(gp + (long long)c * pairs_per_sample);
+                const float w = gs[c];
+                const float hx = (xv.x - mean.x) * rstd.x, hy = (xv.y - mean.y) * rstd.y;
+                op[(long long)c * pairs_per_sample] = make_float2(rstd.x * (g.x * w - m1.x - hx * m2.x), rstd.y * (g.y * w - m1.y - hy * m2.y));
+            }
+        }
+        __syncthreads();          // sa / sb are rewritten by the next group
+    }
+    __syncthreads();
+    for (int q = tid; q < 2 * C; q += nthr) {
+        float* dst = q < C ? dgamma : dbeta;
+        if (dst) atomicAdd(dst + (q < C ? q : q - C), part[q]);
+    }
+}
+
+// slices for the sliced kernels: 0 = use the one-thread-per-voxel-pair kernels
+int ln_slices(int channels, long long total_pairs) {
+    if (channels < 64 || total_pairs >= 256LL * sm_count_cached()) return 0;
+    return channels >= 256 ? 8 : (channels >= 128 ? 4 : 2);
+}
+
 int sm_count() {
     static int sms = 0;
     if (!sms) {
@@ -326,6 +481,13 @@ int fz_layernorm_cf_forward(const float* x, const float* gamma, const float* bet
     }
     {
         const long long pps = voxels / 2, total = batch * pps;
+        if (const int sl = ln_slices(channels, total)) {
+            long long groups = (total + 31) / 32;
+            if (groups > 8LL * sm_count()) groups = 8LL * sm_count();
+            layernorm_cf_fwd_sliced<<<(unsigned)groups, dim3(32, sl), 0, st>>>(x, gamma, beta, y, channels, pps, total, eps);
+            FZ_LAUNCH_CHECK();
+            return FZ_OK;
+        }
         const int threads = total >= 256LL * sm_count() ? kLnThreads : 64;   // few voxels: spread them over more SMs
         long long blocks = (total + threads - 1) / threads;
         const long long cap = 8LL * sm_count();
@@ -361,6 +523,14 @@ int fz_layernorm_cf_backward(const float* x, const float* gamma, const float* dy
         if (blocks > cap) blocks = cap;
         if (dgamma) FZ_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, channels * sizeof(float), st));
         if (dbeta) FZ_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, channels * sizeof(float), st));
+        if (const int sl = ln_slices(channels, total)) {
+            long long groups = (total + 31) / 32;
+            if (groups > 4LL * sm_count()) groups = 4LL * sm_count();
+            layernorm_cf_bwd_sliced<<<(unsigned)groups, dim3(32, sl), sizeof(float) * 3 * channels, st>>>(x, gamma, dy, dx, dgamma, dbeta,
+                                                                                                         channels, pps, total, eps);
+            FZ_LAUNCH_CHECK();
+            return FZ_OK;
+        }
         const size_t cp = ((size_t)channels + 31) & ~(size_t)31;
         const size_t smem = sizeof(float) * (cp + (threads / 32) * 2 * cp);
         static SmemConfig cfg;

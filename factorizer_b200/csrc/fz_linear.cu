@@ -21,19 +21,21 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     return __ffma2_rn(a, b, c);
 }
 
-// rows [r0, r0+32) x voxels [v0, v0+256) of a (rows_total, vox) matrix -> S[32][kWRS]; past-the-end voxels read as 0
-__device__ __forceinline__ void stage_rows(const float* __restrict__ g, long long vox, long long v0, float* __restrict__ S, int tid,
-                                           float (&rowsum)[16], bool want_sums) {
+// rows [r0, r0+32) x voxels [v0, v0+256) of a (rows_total, vox) matrix -> S[32][kWRS]; past-the-end voxels and rows
+// (rows_left = rows_total - r0 may be below 32) read as 0
+__device__ __forceinline__ void stage_rows(const float* __restrict__ g, long long vox, long long v0, int rows_left, float* __restrict__ S,
+                                           int tid, float (&rowsum)[16], bool want_sums) {
     const int col4 = tid & 63, rbase = tid >> 6;
     const long long v = v0 + 4 * col4;
-    const bool in = v < vox;                      // vox % 4 == 0: a float4 is wholly inside or outside
+    const bool in_v = v < vox;                    // vox % 4 == 0: a float4 is wholly inside or outside
 #pragma unroll
     for (int h = 0; h < 2; ++h) {                 // 8 rows in flight at a time (register budget of 3 CTAs per SM)
         float4 val[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-            val[i] = in ? __ldg(reinterpret_cast<const float4*>(g + (long long)(rbase + 2 * (8 * h + i)) * vox + v))
-                        : make_float4(0.f, 0.f, 0.f, 0.f);
+            val[i] = (in_v && rbase + 2 * (8 * h + i) < rows_left)
+                         ? __ldg(reinterpret_cast<const float4*>(g + (long long)(rbase + 2 * (8 * h + i)) * vox + v))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             *reinterpret_cast<float4*>(S + (rbase + 2 * (8 * h + i)) * kWRS + 4 * col4) = val[i];
@@ -63,8 +65,8 @@ __global__ void __launch_bounds__(kWT, 3) linear_wgrad(const float* __restrict__
         const long long b = tile / tiles_per_sample;
         const long long v0 = (tile - b * tiles_per_sample) * kWV;
         __syncthreads();                // the previous tile has been consumed
-        stage_rows(dy + (b * cout + o0) * vox, vox, v0, SA, tid, rowsum, sums);
-        stage_rows(x + (b * cin + i0) * vox, vox, v0, SB, tid, unused, false);
+        stage_rows(dy + (b * cout + o0) * vox, vox, v0, cout - o0, SA, tid, rowsum, sums);
+        stage_rows(x + (b * cin + i0) * vox, vox, v0, cin - i0, SB, tid, unused, false);
         __syncthreads();
 #pragma unroll 2
         for (int it = 0; it < kWV / 4 / kWWarps; ++it) {
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(kWT, 3) linear_wgrad(const float* __restrict__
         float t = 0.f;
 #pragma unroll
         for (int w = 0; w < kWWarps; ++w) t += scr[w * 1024 + e];
-        atomicAdd(dW + (long long)(o0 + (e >> 5)) * cin + i0 + (e & 31), t);
+        if (o0 + (e >> 5) < cout && i0 + (e & 31) < cin) atomicAdd(dW + (long long)(o0 + (e >> 5)) * cin + i0 + (e & 31), t);
     }
     if (sums) {
 #pragma unroll
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(kWT, 3) linear_wgrad(const float* __restrict__
             if (lane == 0) atomicAdd(rs + (tid >> 6) + 2 * i, t);      // once per kernel: the CAS loop does not matter here
         }
         __syncthreads();
-        if (tid < 32) atomicAdd(db + o0 + tid, rs[tid]);
+        if (tid < 32 && o0 + tid < cout) atomicAdd(db + o0 + tid, rs[tid]);
     }
 }
 
@@ -118,15 +120,15 @@ using namespace fz;
 extern "C" {
 
 int fz_linear_wgrad_supported(int32_t cout, int32_t cin, int64_t voxels) {
-    return cout > 0 && cin > 0 && cout % 32 == 0 && cin % 32 == 0 && voxels > 0 && voxels % 4 == 0;
+    return cout > 0 && cin > 0 && cout <= 32 * 65535 && cin <= 32 * 65535 && voxels > 0 && voxels % 4 == 0;
 }
 
 int fz_linear_wgrad(const float* dy, const float* x, float* dW, float* db, int64_t batch, int32_t cout, int32_t cin, int64_t voxels,
                     void* stream) {
     if (batch < 0 || cout <= 0 || cin <= 0 || voxels <= 0) return fail(FZ_ERR_INVALID, "linear wgrad: bad sizes");
     if (!fz_linear_wgrad_supported(cout, cin, voxels))
-        return fail(FZ_ERR_UNSUPPORTED, "linear wgrad kernel needs channel counts divisible by 32 and voxels divisible by 4 (got %d x %d x %lld)",
-                    cout, cin, (long long)voxels);
+        return fail(FZ_ERR_UNSUPPORTED, "linear wgrad kernel needs a voxel count divisible by 4 (got %d x %d x %lld)", cout, cin,
+                    (long long)voxels);
     if (!dW) return fail(FZ_ERR_INVALID, "linear wgrad: null dW");
     cudaStream_t st = (cudaStream_t)stream;
     FZ_CUDA_CHECK(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)cout * cin, st));
@@ -135,7 +137,8 @@ int fz_linear_wgrad(const float* dy, const float* x, float* dW, float* db, int64
     if (!dy || !x) return fail(FZ_ERR_INVALID, "linear wgrad: null buffer");
     const int tps = (int)((voxels + kWV - 1) / kWV);
     const long long tiles = batch * tps;
-    const int blocks = (cout / 32) * (cin / 32);
+    const int bo = (cout + 31) / 32, bi = (cin + 31) / 32;       // channel counts are padded with zero rows inside the kernel
+    const int blocks = bo * bi;
     int dev = 0, sms = 148;
     FZ_CUDA_CHECK(cudaGetDevice(&dev));
     FZ_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -145,7 +148,7 @@ int fz_linear_wgrad(const float* dy, const float* x, float* dW, float* db, int64
     const size_t smem = sizeof(float) * 2 * 32 * kWRS;          // 66.5 KB >= the 16.1 KB epilogue scratch
     static SmemConfig cfg;
     FZ_CUDA_CHECK(cfg.ensure(linear_wgrad, smem));
-    linear_wgrad<<<dim3((unsigned)gx, cout / 32, cin / 32), kWT, smem, st>>>(dy, x, dW, db, cout, cin, voxels, tps, tiles);
+    linear_wgrad<<<dim3((unsigned)gx, bo, bi), kWT, smem, st>>>(dy, x, dW, db, cout, cin, voxels, tps, tiles);
     FZ_LAUNCH_CHECK();
     return FZ_OK;
 }

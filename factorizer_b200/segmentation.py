@@ -17,6 +17,7 @@ from torch import nn
 
 from .factorizer import FactorizerStage
 from .helpers import as_tuple, partialize
+from . import layers
 from .layers import PositionalEmbedding
 
 __all__ = ["UNet", "Factorizer"]
@@ -76,7 +77,7 @@ class UNet(nn.Module):
             raise NotImplementedError("factorizer_b200.UNet needs `block` (per-level stage specs); the reference's "
                                       "default DoubleConv U-Net is not part of this package")
         self.spatial_dims, self.spatial_size = spatial_dims, spatial_size
-        conv = getattr(nn, f"Conv{spatial_dims}d")
+        conv = getattr(layers, f"Conv{spatial_dims}d")     # nn.ConvNd with a patch (kernel == stride) fast path
         tconv = getattr(nn, f"ConvTranspose{spatial_dims}d")
         downsample = downsample or (conv, {"kernel_size": 2})
         upsample = upsample or (tconv, {"kernel_size": 2})

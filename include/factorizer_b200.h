@@ -134,8 +134,8 @@ int fz_layernorm_cf_backward(const float* x, const float* gamma, const float* dy
 /* ---- weight gradient of the pointwise channel map (reference factorizer/layers/linear.py:53-58, a k=1 Conv1d) ----
  * dW[o][i] = sum over batch and voxels of dy[b][o][v] x[b][i][v]   (cout x cin floats, OVERWRITTEN)
  * db[o]    = sum over batch and voxels of dy[b][o][v]              (cout floats, OVERWRITTEN; may be NULL)
- * dy is (batch, cout, voxels), x is (batch, cin, voxels), fp32 contiguous.  Channel counts must be multiples of 32
- * and voxels a multiple of 4; fz_linear_wgrad_supported() tells.  Replaces the large-K library SGEMM autograd picks
+ * dy is (batch, cout, voxels), x is (batch, cin, voxels), fp32 contiguous.  voxels must be a multiple of 4 (channel
+ * counts are free: blocks of 32 x 32 are zero-padded); fz_linear_wgrad_supported() tells.  Replaces the large-K library SGEMM autograd picks
  * for the 64..512-channel stages of the Swin Factorizer. */
 int fz_linear_wgrad_supported(int32_t cout, int32_t cin, int64_t voxels);
 int fz_linear_wgrad(const float* dy, const float* x, float* dW, float* db, int64_t batch, int32_t cout, int32_t cin,

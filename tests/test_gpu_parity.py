@@ -454,7 +454,7 @@ def test_full_size_properties(ft, dev):
 
 @pytest.mark.parametrize("shape", [(2, 32, 8, 8, 8), (1, 16, 6, 10, 4), (3, 8, 50), (1, 32, 16, 16, 16),
                                    (2, 64, 16, 16, 16), (1, 24, 6, 10, 4), (2, 128, 8, 8, 8), (3, 512, 4, 4, 4), (1, 5, 7, 6),
-                                   (1, 256, 2, 33, 1)])
+                                   (1, 256, 2, 33, 1), (1, 200, 6, 6, 6), (2, 72, 10, 10, 2), (1, 64, 64, 64, 32)])
 def test_layernorm_channels_first(ft, dev, shape):
     """ft.LayerNorm (hand-written channels-first kernel) against torch's own layer_norm on the permuted
     tensor, which is literally what the reference does (factorizer/layers/norm.py:25-34): output, input
@@ -509,7 +509,42 @@ def test_linear_weight_gradient_kernel(ft, dev, shape, cout, bias):
         assert_close(_np(g) / scale, _np(r) / scale, what=name)
     # short voxel axes and odd channel counts stay with the library path
     assert not _ops.linear_wgrad_supported(torch.randn(1, 64, 8, 8, 8, device=dev).flatten(2), 64)
-    assert not _ops.linear_wgrad_supported(torch.randn(1, 48, 32, 32, 32, device=dev).flatten(2), 40)
+    assert not _ops.linear_wgrad_supported(torch.randn(1, 48, 31, 31, 31, device=dev).flatten(2), 40)
+
+
+@pytest.mark.parametrize("nd,cin,cout,k,size,bias", [(3, 32, 64, 2, (32, 32, 32), True), (3, 4, 3, 1, (32, 32, 16), True),
+                                                     (3, 24, 40, 2, (16, 32, 64), False), (2, 32, 64, 2, (128, 128), True),
+                                                     (3, 8, 16, (2, 1, 2), (32, 16, 32), True)])
+def test_patch_convolution_as_channel_map(ft, dev, nd, cin, cout, k, size, bias):
+    """ft.layers.ConvNd with kernel_size == stride (the reference U-Net's down-samplers and 1x1 head, unet.py:53,247)
+    runs as a pointwise map on the space-to-depth view with the weight gradient from csrc/fz_linear.cu: output and
+    all gradients against torch's own convolution in fp64; other shapes are the stock convolution."""
+    from factorizer_b200 import layers
+    torch.manual_seed(5)
+    cls = getattr(layers, f"Conv{nd}d")
+    conv = cls(cin, cout, kernel_size=k, stride=k, bias=bias).to(dev)
+    x = torch.randn(2, cin, *size, device=dev, requires_grad=True)
+    assert conv._patch_view(x) is not None
+    y = conv(x)
+    gy = torch.randn_like(y)
+    params = [conv.weight] + ([conv.bias] if bias else [])
+    grads = torch.autograd.grad((y * gy).sum(), [x] + params)
+    fn = getattr(torch.nn.functional, f"conv{nd}d")
+    x64 = x.detach().double().requires_grad_(True)
+    p64 = [p.detach().double().requires_grad_(True) for p in params]
+    y64 = fn(x64, p64[0], p64[1] if bias else None, stride=k)
+    refs = torch.autograd.grad((y64 * gy.double()).sum(), [x64] + p64)
+    assert y.shape == y64.shape
+    assert_close(_np(y), _np(y64), what="y")
+    for name, g, r in zip(["gx", "gw", "gb"], grads, refs):
+        assert g.shape == r.shape
+        scale = max(1.0, float(r.abs().max()))
+        assert_close(_np(g) / scale, _np(r) / scale, what=name)
+    # overlapping / padded convolutions and no-grad calls are the library's
+    assert cls(cin, cout, kernel_size=3, padding=1).to(dev)._patch_view(x) is None
+    with torch.no_grad():
+        assert conv._patch_view(x) is None
+        assert torch.allclose(conv(x), y, rtol=1e-4, atol=1e-5)
 
 
 def test_layernorm_fallback_shapes(ft, dev):
