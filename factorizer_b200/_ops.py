@@ -447,8 +447,46 @@ class LinearCF(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = torch.bmm(weight.t().unsqueeze(0).expand(B, -1, -1), gy)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            gw = torch.empty_like(weight)
+            gw = torch.empty(weight.shape, device=x.device, dtype=torch.float32)     # row-major whatever the weight's strides
             gb = torch.empty(cout, device=x.device, dtype=torch.float32) if ctx.has_bias else None
             with torch.cuda.device(x.device):
                 _call(lib.fz_linear_wgrad, L.ptr(gy), L.ptr(x), L.ptr(gw), L.ptr(gb), B, cout, cin, vox, L.stream_ptr(x.device))
         return gx, gw, gb
+
+
+class ConvWgradCF(torch.autograd.Function):
+    """Stride-1 convolution with few input rows (C_in * prod(kernel) <= 256: the 4 -> 32 channel 3x3x3 stem of the
+    Swin Factorizer, reference factorizer/factorizer.py:139-140).  Forward and input gradient are the library's; the
+    weight gradient is the channel-map kernel (csrc/fz_linear.cu) on the unfolded input, rebuilt in the backward --
+    cuDNN's fp32 wgrad for that shape takes 2-4 ms at 128^3."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, padding):
+        nd = weight.dim() - 2
+        y = getattr(torch.nn.functional, f"conv{nd}d")(x, weight, bias, padding=padding)
+        ctx.save_for_backward(x, weight)
+        ctx.padding, ctx.has_bias = tuple(padding), bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        import itertools
+        x, weight = ctx.saved_tensors
+        lib = L.lib()
+        nd = weight.dim() - 2
+        gy = L.require_cuda_f32(gy, "grad")
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = getattr(torch.nn.grad, f"conv{nd}d_input")(x.shape, weight, gy, padding=ctx.padding)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            B, cout, k, out_sp = x.shape[0], weight.shape[0], weight.shape[2:], gy.shape[2:]
+            xp = torch.nn.functional.pad(x, [q for p in reversed(ctx.padding) for q in (p, p)])
+            cols = torch.stack([xp[(slice(None), slice(None)) + tuple(slice(o, o + n) for o, n in zip(off, out_sp))]
+                                for off in itertools.product(*[range(q) for q in k])], dim=2)   # (B, C_in, K, *out)
+            rows = cols.shape[1] * cols.shape[2]
+            gw = torch.empty(weight.shape, device=x.device, dtype=torch.float32)
+            gb = torch.empty(cout, device=x.device, dtype=torch.float32) if ctx.has_bias else None
+            with torch.cuda.device(x.device):
+                _call(lib.fz_linear_wgrad, L.ptr(gy), L.ptr(cols), L.ptr(gw), L.ptr(gb), B, cout, rows, gy[0, 0].numel(),
+                      L.stream_ptr(x.device))
+        return gx, gw, gb, None

@@ -112,6 +112,113 @@ __global__ void __launch_bounds__(kWT, 3) linear_wgrad(const float* __restrict__
     }
 }
 
+
+// ---- both channel counts >= 64: 64 x 64 blocks, cp.async double buffering -------------------------------------------
+// The 32 x 32 kernel above re-reads dy cin/32 times and x cout/32 times and exposes the load latency of every tile; for
+// the wide layers (64 x 256 over 262144 voxels moves 1.07 GB that way) this one halves the re-reads and overlaps them:
+// 256 threads, stages of 128 voxels x (64 dy rows + 64 x rows) filled by cp.async (zero-filled past the end), warp w
+// owns the 32 x 32 sub-block (w & 3) of every second float4 column (w >> 2).
+constexpr int kW2T = 256, kW2V = 128, kW2RS = kW2V + 4, kW2Stage = 128 * kW2RS;
+
+__device__ __forceinline__ void cp_async16(float* dst, const float* src, bool real) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int n = real ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+
+__global__ void __launch_bounds__(kW2T, 1) linear_wgrad64(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dW,
+                                                          float* __restrict__ db, int cout, int cin, long long vox, int tiles_per_sample,
+                                                          long long total_tiles) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, ro = lane & 3, co = lane >> 2;
+    const int kh = w >> 2, sr = (w >> 1) & 1, sc = w & 1;
+    const int o0 = blockIdx.y * 64, i0 = blockIdx.z * 64;
+    const bool sums = db != nullptr && blockIdx.z == 0 && sc == 0;
+    float2 acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[i][k] = make_float2(0.f, 0.f);
+    float rs[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rs[i] = 0.f;
+
+    auto issue = [&](long long tile, int stage) {
+        const long long b = tile / tiles_per_sample;
+        const long long v = (tile - b * tiles_per_sample) * kW2V + 4 * (tid & 31);
+        const bool in_v = v < vox;
+        float* S = sm + stage * kW2Stage + 4 * (tid & 31);
+        const float* gdy = dy + b * cout * vox;
+        const float* gx = x + b * cin * vox;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int r = (tid >> 5) + 8 * i;              // 0..127: dy rows, then x rows
+            const bool isx = r >= 64;
+            const int ch = isx ? i0 + r - 64 : o0 + r;
+            const bool real = in_v && ch < (isx ? cin : cout);
+            const float* src = real ? (isx ? gx : gdy) + (long long)ch * vox + v : dy;
+            cp_async16(S + r * kW2RS, src, real);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    long long tile = blockIdx.x;
+    int stage = 0;
+    if (tile < total_tiles) issue(tile, 0);
+    for (; tile < total_tiles; tile += gridDim.x, stage ^= 1) {
+        if (tile + gridDim.x < total_tiles) {
+            issue(tile + gridDim.x, stage ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const float* SA = sm + stage * kW2Stage + (32 * sr) * kW2RS;
+        const float* SB = sm + stage * kW2Stage + (64 + 32 * sc) * kW2RS;
+#pragma unroll 2
+        for (int it = 0; it < kW2V / 4 / 2; ++it) {
+            const int v = (2 * it + kh) * 4;
+            float4 B[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) B[k] = *reinterpret_cast<const float4*>(SB + (co + 8 * k) * kW2RS + v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 A = *reinterpret_cast<const float4*>(SA + (ro + 4 * i) * kW2RS + v);
+                if (sums) rs[i] += (A.x + A.y) + (A.z + A.w);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    acc[i][k] = ffma2(make_float2(A.x, A.y), make_float2(B[k].x, B[k].y), acc[i][k]);
+                    acc[i][k] = ffma2(make_float2(A.z, A.w), make_float2(B[k].z, B[k].w), acc[i][k]);
+                }
+            }
+        }
+        __syncthreads();            // the stage is rewritten by the copy issued in the next iteration
+    }
+    // partial blocks of the 8 warps -> shared memory -> one atomicAdd per element and CTA
+    float* scr = sm;                // [warp][32*32]
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) scr[w * 1024 + (ro + 4 * i) * 32 + co + 8 * k] = acc[i][k].x + acc[i][k].y;
+    float* rsum = sm + 8 * 1024;    // [64] row sums of dy
+    if (tid < 64) rsum[tid] = 0.f;
+    __syncthreads();
+    for (int e = tid; e < 4096; e += kW2T) {
+        const int sub = e >> 10, q = e & 1023;                    // sub = 2 sr + sc
+        const float t = scr[sub * 1024 + q] + scr[(sub + 4) * 1024 + q];
+        const int o = o0 + 32 * (sub >> 1) + (q >> 5), c = i0 + 32 * (sub & 1) + (q & 31);
+        if (o < cout && c < cin) atomicAdd(dW + (long long)o * cin + c, t);
+    }
+    if (db != nullptr && blockIdx.z == 0) {
+        if (sc == 0 && co == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) atomicAdd(rsum + 32 * sr + ro + 4 * i, rs[i]);   // once per kernel
+        }
+        __syncthreads();
+        if (tid < 64 && o0 + tid < cout) atomicAdd(db + o0 + tid, rsum[tid]);
+    }
+}
+
 }  // namespace
 }  // namespace fz
 
@@ -135,13 +242,27 @@ int fz_linear_wgrad(const float* dy, const float* x, float* dW, float* db, int64
     if (db) FZ_CUDA_CHECK(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)cout, st));
     if (batch == 0) return FZ_OK;
     if (!dy || !x) return fail(FZ_ERR_INVALID, "linear wgrad: null buffer");
+    int dev = 0, sms = 148;
+    FZ_CUDA_CHECK(cudaGetDevice(&dev));
+    FZ_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (cout >= 64 && cin >= 64 && batch * voxels >= 32768) {      // fewer voxels: the smaller CTAs spread better
+        const int tps = (int)((voxels + kW2V - 1) / kW2V);
+        const long long tiles = batch * tps;
+        const int bo = (cout + 63) / 64, bi = (cin + 63) / 64;
+        long long gx = (2LL * sms + bo * bi - 1) / (bo * bi);
+        if (gx > tiles) gx = tiles;
+        if (gx < 1) gx = 1;
+        const size_t smem = sizeof(float) * 2 * kW2Stage;       // 132 KB: two stages; the epilogue scratch (32.3 KB) aliases them
+        static SmemConfig cfg64;
+        FZ_CUDA_CHECK(cfg64.ensure(linear_wgrad64, smem));
+        linear_wgrad64<<<dim3((unsigned)gx, bo, bi), kW2T, smem, st>>>(dy, x, dW, db, cout, cin, voxels, tps, tiles);
+        FZ_LAUNCH_CHECK();
+        return FZ_OK;
+    }
     const int tps = (int)((voxels + kWV - 1) / kWV);
     const long long tiles = batch * tps;
     const int bo = (cout + 31) / 32, bi = (cin + 31) / 32;       // channel counts are padded with zero rows inside the kernel
     const int blocks = bo * bi;
-    int dev = 0, sms = 148;
-    FZ_CUDA_CHECK(cudaGetDevice(&dev));
-    FZ_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     long long gx = (3LL * sms + blocks - 1) / blocks;
     if (gx > tiles) gx = tiles;
     if (gx < 1) gx = 1;

@@ -13,7 +13,8 @@ from typing import Optional, Sequence
 import torch
 from torch import nn
 
-__all__ = ["Linear", "LayerNorm", "MLP", "PositionalEmbedding", "PosEmbed", "Conv1d", "Conv2d", "Conv3d"]
+__all__ = ["Linear", "LayerNorm", "MLP", "PositionalEmbedding", "PosEmbed", "Conv1d", "Conv2d", "Conv3d",
+           "ConvTranspose1d", "ConvTranspose2d", "ConvTranspose3d"]
 
 
 class Linear(nn.Module):
@@ -71,9 +72,28 @@ class _PatchConv:
             return None
         return xf, out_sp
 
+    def _unfold_ok(self, x: torch.Tensor) -> bool:
+        """Stride-1 convolution whose unfolded input has few rows (the 4 -> 32 channel stem): library forward,
+        weight gradient from csrc/fz_linear.cu on the unfolded input (see _ops.ConvWgradCF)."""
+        k = self.kernel_size
+        if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == len(k) + 2 and torch.is_grad_enabled()
+                and self.weight.requires_grad and self.groups == 1 and all(q == 1 for q in self.stride)
+                and all(d == 1 for d in self.dilation) and not isinstance(self.padding, str)
+                and self.padding_mode == "zeros" and math.prod(k) > 1 and x.is_contiguous()):
+            return False
+        rows = self.in_channels * math.prod(k)
+        out_sp = [n + 2 * p - q + 1 for n, p, q in zip(x.shape[2:], self.padding, k)]
+        vox = math.prod(out_sp)
+        # the unfolded copy is rows * voxels floats: keep it under 2 GiB
+        return (rows <= 256 and min(out_sp) > 0 and vox % 4 == 0 and x.shape[0] * vox >= 4096
+                and x.shape[0] * rows * vox * 4 <= 2 ** 31)
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         pv = self._patch_view(x)
         if pv is None:
+            if self._unfold_ok(x):
+                from . import _ops
+                return _ops.ConvWgradCF.apply(x, self.weight, self.bias, tuple(self.padding))
             return super().forward(x)
         from . import _ops
         xf, out_sp = pv
@@ -90,6 +110,48 @@ class Conv2d(_PatchConv, nn.Conv2d):
 
 
 class Conv3d(_PatchConv, nn.Conv3d):
+    pass
+
+
+class _PatchConvTranspose:
+    """Mixin for nn.ConvTransposeNd: with kernel_size == stride and no padding (the reference U-Net's up-samplers,
+    factorizer/unet.py:97-99) every input voxel writes its own output patch, i.e. the layer is a pointwise channel map
+    C_in -> C_out * prod(kernel) followed by a depth-to-space permutation.  Same conditions and purpose as _PatchConv."""
+
+    def _patch_ok(self, x: torch.Tensor) -> bool:
+        k = self.kernel_size
+        if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == len(k) + 2 and torch.is_grad_enabled()
+                and self.weight.requires_grad and self.groups == 1 and tuple(self.stride) == tuple(k)
+                and all(d == 1 for d in self.dilation) and all(p == 0 for p in self.padding)
+                and all(p == 0 for p in self.output_padding) and x.is_contiguous()):
+            return False
+        from . import _ops
+        return _ops.linear_wgrad_supported(x.flatten(2), self.out_channels * math.prod(k))
+
+    def forward(self, x: torch.Tensor, output_size=None) -> torch.Tensor:
+        if output_size is not None or not self._patch_ok(x):
+            return super().forward(x, output_size)
+        from . import _ops
+        k, nd = self.kernel_size, len(self.kernel_size)
+        B, co, K = x.shape[0], self.out_channels, math.prod(self.kernel_size)
+        w = self.weight.reshape(self.in_channels, co * K).t()                   # rows (co, k...), a view
+        b = None if self.bias is None else self.bias.repeat_interleave(K)
+        y = _ops.LinearCF.apply(x.flatten(2), w, b)                             # (B, co * K, voxels)
+        sp = x.shape[2:]
+        perm = [0, 1] + [d for i in range(nd) for d in (2 + nd + i, 2 + i)]
+        y = y.view(B, co, *k, *sp).permute(perm)                                # (B, co, n0, k0, n1, k1, ...)
+        return y.reshape(B, co, *[n * q for n, q in zip(sp, k)])                # one copy
+
+
+class ConvTranspose1d(_PatchConvTranspose, nn.ConvTranspose1d):
+    pass
+
+
+class ConvTranspose2d(_PatchConvTranspose, nn.ConvTranspose2d):
+    pass
+
+
+class ConvTranspose3d(_PatchConvTranspose, nn.ConvTranspose3d):
     pass
 
 

@@ -78,7 +78,7 @@ class UNet(nn.Module):
                                       "default DoubleConv U-Net is not part of this package")
         self.spatial_dims, self.spatial_size = spatial_dims, spatial_size
         conv = getattr(layers, f"Conv{spatial_dims}d")     # nn.ConvNd with a patch (kernel == stride) fast path
-        tconv = getattr(nn, f"ConvTranspose{spatial_dims}d")
+        tconv = getattr(layers, f"ConvTranspose{spatial_dims}d")
         downsample = downsample or (conv, {"kernel_size": 2})
         upsample = upsample or (tconv, {"kernel_size": 2})
         head = partialize(head or (conv, {"kernel_size": 1}))
@@ -138,7 +138,7 @@ class Factorizer(UNet):
                  num_deep_supr=False, **kwargs):
         nd = len(spatial_size)
         if stem is None:
-            stem = (getattr(nn, f"Conv{nd}d"), {"kernel_size": 3, "padding": 1, "bias": False})
+            stem = (getattr(layers, f"Conv{nd}d"), {"kernel_size": 3, "padding": 1, "bias": False})
         plain = (FactorizerStage, kwargs)
         bottleneck = (FactorizerStage, {"pos_embed": pos_embed, **kwargs})
         blocks = [plain] * (len(encoder_depth) - 1) + [bottleneck] + [plain] * len(decoder_depth)

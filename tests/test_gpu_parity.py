@@ -542,9 +542,79 @@ def test_patch_convolution_as_channel_map(ft, dev, nd, cin, cout, k, size, bias)
         assert_close(_np(g) / scale, _np(r) / scale, what=name)
     # overlapping / padded convolutions and no-grad calls are the library's
     assert cls(cin, cout, kernel_size=3, padding=1).to(dev)._patch_view(x) is None
-    with torch.no_grad():
-        assert conv._patch_view(x) is None
-        assert torch.allclose(conv(x), y, rtol=1e-4, atol=1e-5)
+    keep = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            assert conv._patch_view(x) is None
+            assert_close(_np(conv(x)), _np(y64), what="library path")
+    finally:
+        torch.backends.cudnn.allow_tf32 = keep
+
+
+@pytest.mark.parametrize("nd,cin,cout,k,size,bias", [(3, 64, 32, 2, (16, 16, 16), True), (3, 40, 24, 2, (8, 16, 32), False),
+                                                     (2, 64, 32, 2, (64, 64), True), (3, 16, 8, (2, 1, 2), (16, 16, 16), True)])
+def test_patch_transposed_convolution_as_channel_map(ft, dev, nd, cin, cout, k, size, bias):
+    """ft.layers.ConvTransposeNd with kernel_size == stride (the reference U-Net's up-samplers, unet.py:97-99) as a
+    pointwise map + depth-to-space: output and all gradients against torch's own transposed convolution in fp64."""
+    from factorizer_b200 import layers
+    torch.manual_seed(6)
+    cls = getattr(layers, f"ConvTranspose{nd}d")
+    conv = cls(cin, cout, kernel_size=k, stride=k, bias=bias).to(dev)
+    x = torch.randn(2, cin, *size, device=dev, requires_grad=True)
+    assert conv._patch_ok(x)
+    y = conv(x)
+    gy = torch.randn_like(y)
+    params = [conv.weight] + ([conv.bias] if bias else [])
+    grads = torch.autograd.grad((y * gy).sum(), [x] + params)
+    fn = getattr(torch.nn.functional, f"conv_transpose{nd}d")
+    x64 = x.detach().double().requires_grad_(True)
+    p64 = [p.detach().double().requires_grad_(True) for p in params]
+    y64 = fn(x64, p64[0], p64[1] if bias else None, stride=k)
+    refs = torch.autograd.grad((y64 * gy.double()).sum(), [x64] + p64)
+    assert y.shape == y64.shape
+    assert_close(_np(y), _np(y64), what="y")
+    for name, g, r in zip(["gx", "gw", "gb"], grads, refs):
+        assert g.shape == r.shape
+        scale = max(1.0, float(r.abs().max()))
+        assert_close(_np(g) / scale, _np(r) / scale, what=name)
+    assert not cls(cin, cout, kernel_size=3, stride=2).to(dev)._patch_ok(x)
+
+
+@pytest.mark.parametrize("nd,cin,cout,k,pad,size,bias,xgrad", [(3, 4, 32, 3, 1, (32, 32, 32), False, False),
+                                                               (3, 5, 12, (3, 1, 3), (1, 0, 1), (16, 16, 16), True, True),
+                                                               (2, 3, 16, 5, 2, (64, 64), True, True),
+                                                               (3, 2, 8, 3, 0, (18, 18, 18), True, False)])
+def test_stem_convolution_weight_gradient(ft, dev, nd, cin, cout, k, pad, size, bias, xgrad):
+    """ft.layers.ConvNd, stride 1 with few unfolded rows (the reference's 3x3x3 stem, factorizer.py:139-140): library
+    forward / input gradient, weight gradient from csrc/fz_linear.cu on the unfolded input; against fp64 torch."""
+    from factorizer_b200 import layers
+    torch.manual_seed(7)
+    cls = getattr(layers, f"Conv{nd}d")
+    conv = cls(cin, cout, kernel_size=k, padding=pad, bias=bias).to(dev)
+    x = torch.randn(2, cin, *size, device=dev, requires_grad=xgrad)
+    assert conv._patch_view(x) is None and conv._unfold_ok(x)
+    keep = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        y = conv(x)
+        gy = torch.randn_like(y)
+        params = [conv.weight] + ([conv.bias] if bias else [])
+        wrt = ([x] if xgrad else []) + params
+        grads = torch.autograd.grad((y * gy).sum(), wrt)
+    finally:
+        torch.backends.cudnn.allow_tf32 = keep
+    fn = getattr(torch.nn.functional, f"conv{nd}d")
+    x64 = x.detach().double().requires_grad_(xgrad)
+    p64 = [p.detach().double().requires_grad_(True) for p in params]
+    y64 = fn(x64, p64[0], p64[1] if bias else None, padding=pad)
+    refs = torch.autograd.grad((y64 * gy.double()).sum(), ([x64] if xgrad else []) + p64)
+    assert_close(_np(y), _np(y64), what="y")
+    for i, (g, r) in enumerate(zip(grads, refs)):
+        assert g.shape == r.shape
+        scale = max(1.0, float(r.abs().max()))
+        assert_close(_np(g) / scale, _np(r) / scale, what=f"grad {i}")
+    assert not cls(64, 64, kernel_size=3, padding=1).to(dev)._unfold_ok(torch.randn(1, 64, 16, 16, 16, device=dev))
 
 
 def test_layernorm_fallback_shapes(ft, dev):
