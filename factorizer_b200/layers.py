@@ -46,17 +46,18 @@ class Linear(nn.Module):
 class _PatchConv:
     """Mixin for nn.ConvNd: a convolution over non-overlapping patches (kernel_size == stride, no padding -- the
     reference U-Net's strided down-samplers, factorizer/unet.py:53, and its 1x1 head, unet.py:247) is a pointwise
-    channel map on the space-to-depth view of the input.  On CUDA fp32 tensors with gradients enabled it runs as
-    one, so that its weight gradient comes from csrc/fz_linear.cu instead of cuDNN's fp32 wgrad (1.7 ms per layer at
-    128^3); everything else, and every other convolution shape, is the stock nn.ConvNd.  Parameters and state_dict
+    channel map on the space-to-depth view of the input.  On CUDA fp32 tensors it runs as one (a library GEMM
+    forward, 0.3 ms instead of cuDNN's 0.54 ms for the first down-sampler), so that its weight gradient comes from
+    csrc/fz_linear.cu instead of cuDNN's fp32 wgrad (1.7 ms per layer at 128^3); every other convolution shape is the
+    stock nn.ConvNd.  Parameters and state_dict
     keys are those of nn.ConvNd."""
 
     def _patch_view(self, x: torch.Tensor):
         k = self.kernel_size
-        if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == len(k) + 2 and torch.is_grad_enabled()
-                and self.weight.requires_grad and self.groups == 1 and tuple(self.stride) == tuple(k)
-                and all(d == 1 for d in self.dilation) and not isinstance(self.padding, str)
-                and all(p == 0 for p in self.padding) and all(n % q == 0 for n, q in zip(x.shape[2:], k))):
+        if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == len(k) + 2 and self.groups == 1
+                and tuple(self.stride) == tuple(k) and all(d == 1 for d in self.dilation)
+                and not isinstance(self.padding, str) and all(p == 0 for p in self.padding)
+                and all(n % q == 0 for n, q in zip(x.shape[2:], k))):
             return None
         B, C = x.shape[:2]
         out_sp = [n // q for n, q in zip(x.shape[2:], k)]
