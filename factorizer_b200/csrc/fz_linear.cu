@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kWT, 3) linear_wgrad(const float* __restrict__
 // The 32 x 32 kernel above re-reads dy cin/32 times and x cout/32 times and exposes the load latency of every tile; for
 // the wide layers (64 x 256 over 262144 voxels moves 1.07 GB that way) this one halves the re-reads and overlaps them:
 // 256 threads, stages of 128 voxels x (64 dy rows + 64 x rows) filled by cp.async (zero-filled past the end), warp w
-// owns the 32 x 32 sub-block (w & 3) of every second float4 column (w >> 2).
+// owns 32 dy rows (w & 1) x all 64 x rows of every fourth float4 column (w >> 1).
 constexpr int kW2T = 256, kW2V = 128, kW2RS = kW2V + 4, kW2Stage = 128 * kW2RS;
 
 __device__ __forceinline__ void cp_async16(float* dst, const float* src, bool real) {
@@ -131,14 +131,16 @@ __global__ void __launch_bounds__(kW2T, 1) linear_wgrad64(const float* __restric
                                                           long long total_tiles) {
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, ro = lane & 3, co = lane >> 2;
-    const int kh = w >> 2, sr = (w >> 1) & 1, sc = w & 1;
+    const int kq = w >> 1, sr = w & 1;            // warp: float4 columns kq, kq+4, ... of dy rows [32 sr, 32 sr + 32) x all 64 x rows
     const int o0 = blockIdx.y * 64, i0 = blockIdx.z * 64;
-    const bool sums = db != nullptr && blockIdx.z == 0 && sc == 0;
-    float2 acc[8][4];
+    const bool sums = db != nullptr && blockIdx.z == 0;
+    // an 8 x 8 register tile per lane: 16 LDS.128 per 128 FFMA2 (a 128-bit shared load holds the LSU for four cycles
+    // whatever the broadcast, so the 8 x 4 tile of the kernel above is LSU-bound at two thirds of the FP32 pipe)
+    float2 acc[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) acc[i][k] = make_float2(0.f, 0.f);
+        for (int k = 0; k < 8; ++k) acc[i][k] = make_float2(0.f, 0.f);
     float rs[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) rs[i] = 0.f;
@@ -174,19 +176,19 @@ __global__ void __launch_bounds__(kW2T, 1) linear_wgrad64(const float* __restric
         }
         __syncthreads();
         const float* SA = sm + stage * kW2Stage + (32 * sr) * kW2RS;
-        const float* SB = sm + stage * kW2Stage + (64 + 32 * sc) * kW2RS;
-#pragma unroll 2
-        for (int it = 0; it < kW2V / 4 / 2; ++it) {
-            const int v = (2 * it + kh) * 4;
-            float4 B[4];
+        const float* SB = sm + stage * kW2Stage + 64 * kW2RS;
+#pragma unroll 1
+        for (int it = 0; it < kW2V / 4 / 4; ++it) {
+            const int v = (4 * it + kq) * 4;
+            float4 B[8];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) B[k] = *reinterpret_cast<const float4*>(SB + (co + 8 * k) * kW2RS + v);
+            for (int k = 0; k < 8; ++k) B[k] = *reinterpret_cast<const float4*>(SB + (co + 8 * k) * kW2RS + v);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float4 A = *reinterpret_cast<const float4*>(SA + (ro + 4 * i) * kW2RS + v);
                 if (sums) rs[i] += (A.x + A.y) + (A.z + A.w);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < 8; ++k) {
                     acc[i][k] = ffma2(make_float2(A.x, A.y), make_float2(B[k].x, B[k].y), acc[i][k]);
                     acc[i][k] = ffma2(make_float2(A.z, A.w), make_float2(B[k].z, B[k].w), acc[i][k]);
                 }
@@ -195,22 +197,24 @@ __global__ void __launch_bounds__(kW2T, 1) linear_wgrad64(const float* __restric
         __syncthreads();            // the stage is rewritten by the copy issued in the next iteration
     }
     // partial blocks of the 8 warps -> shared memory -> one atomicAdd per element and CTA
-    float* scr = sm;                // [warp][32*32]
+    float* scr = sm;                // [warp][32 * 64]
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) scr[w * 1024 + (ro + 4 * i) * 32 + co + 8 * k] = acc[i][k].x + acc[i][k].y;
-    float* rsum = sm + 8 * 1024;    // [64] row sums of dy
+        for (int k = 0; k < 8; ++k) scr[w * 2048 + (ro + 4 * i) * 64 + co + 8 * k] = acc[i][k].x + acc[i][k].y;
+    float* rsum = sm + 8 * 2048;    // [64] row sums of dy
     if (tid < 64) rsum[tid] = 0.f;
     __syncthreads();
     for (int e = tid; e < 4096; e += kW2T) {
-        const int sub = e >> 10, q = e & 1023;                    // sub = 2 sr + sc
-        const float t = scr[sub * 1024 + q] + scr[(sub + 4) * 1024 + q];
-        const int o = o0 + 32 * (sub >> 1) + (q >> 5), c = i0 + 32 * (sub & 1) + (q & 31);
+        const int half = e >> 11, q = e & 2047;
+        float t = 0.f;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) t += scr[(2 * g + half) * 2048 + q];
+        const int o = o0 + 32 * half + (q >> 6), c = i0 + (q & 63);
         if (o < cout && c < cin) atomicAdd(dW + (long long)o * cin + c, t);
     }
-    if (db != nullptr && blockIdx.z == 0) {
-        if (sc == 0 && co == 0) {
+    if (sums) {
+        if (co == 0) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) atomicAdd(rsum + 32 * sr + ro + 4 * i, rs[i]);   // once per kernel
         }
@@ -252,7 +256,7 @@ int fz_linear_wgrad(const float* dy, const float* x, float* dW, float* db, int64
         long long gx = (2LL * sms + bo * bi - 1) / (bo * bi);
         if (gx > tiles) gx = tiles;
         if (gx < 1) gx = 1;
-        const size_t smem = sizeof(float) * 2 * kW2Stage;       // 132 KB: two stages; the epilogue scratch (32.3 KB) aliases them
+        const size_t smem = sizeof(float) * 2 * kW2Stage;       // 132 KB: two stages; the epilogue scratch (64.3 KB) aliases them
         static SmemConfig cfg64;
         FZ_CUDA_CHECK(cfg64.ensure(linear_wgrad64, smem));
         linear_wgrad64<<<dim3((unsigned)gx, bo, bi), kW2T, smem, st>>>(dy, x, dW, db, cout, cin, voxels, tps, tiles);
