@@ -412,13 +412,47 @@ class LayerNormCF(torch.autograd.Function):
 
 
 # ---- pointwise channel map (k = 1 Conv1d) with a hand-written weight gradient -------------------
-def linear_wgrad_supported(x: torch.Tensor, out_channels: int) -> bool:
+def space_depth2_supported(x: torch.Tensor) -> bool:
+    return (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and x.is_contiguous()
+            and bool(L.lib().fz_space_depth2_supported(*x.shape[2:])))
+
+
+class SpaceDepth2(torch.autograd.Function):
+    """to_depth: (B, C, D, H, W) -> (B, C*8, D/2*H/2*W/2), rows (c, kd, kh, kw); otherwise the inverse, taking the
+    full-resolution spatial shape.  Each direction is the other's adjoint (a permutation)."""
+
+    @staticmethod
+    def forward(ctx, x, to_depth: bool, full_shape):
+        B, D, H, W = x.shape[0], *full_shape
+        ctx.to_depth, ctx.full_shape = to_depth, tuple(full_shape)
+        return SpaceDepth2._run(x, B, D, H, W, to_depth)
+
+    @staticmethod
+    def _run(x, B, D, H, W, to_depth):
+        x = L.require_cuda_f32(x, "x")
+        if to_depth:
+            C = x.shape[1]
+            out = torch.empty(B, C * 8, (D // 2) * (H // 2) * (W // 2), device=x.device, dtype=torch.float32)
+        else:
+            C = x.shape[1] // 8
+            out = torch.empty(B, C, D, H, W, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _call(L.lib().fz_space_depth2, L.ptr(x), L.ptr(out), B, C, D, H, W, 1 if to_depth else 0, L.stream_ptr(x.device))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        D, H, W = ctx.full_shape
+        return SpaceDepth2._run(g, g.shape[0], D, H, W, not ctx.to_depth), None, None
+
+
+def linear_wgrad_supported(x: torch.Tensor, out_channels: int, min_voxels: int = 4096) -> bool:
     """The contraction over voxels is worth a kernel of its own when it is long (library SGEMMs take their slow
     large-K route there); short ones stay with cuBLAS."""
     if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() >= 3):
         return False
     vox = x.numel() // max(x.shape[0] * x.shape[1], 1)
-    if x.shape[0] * vox < 4096:
+    if x.shape[0] * vox < min_voxels:
         return False
     return bool(L.lib().fz_linear_wgrad_supported(int(out_channels), x.shape[1], vox))
 

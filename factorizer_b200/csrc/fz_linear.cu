@@ -223,6 +223,35 @@ __global__ void __launch_bounds__(kW2T, 1) linear_wgrad64(const float* __restric
     }
 }
 
+
+// ---- space-to-depth / depth-to-space for 2x2x2 patches ---------------------------------------------------------------
+// (B, C, D, H, W) <-> (B, C*8, D/2 * H/2 * W/2), rows ordered (c, kd, kh, kw): the view on which a kernel-2 stride-2
+// convolution (or its transpose) is a channel map.  A thread moves one float4 of the full-resolution tensor = two
+// float2 of the patch rows kw = 0 and kw = 1, so both sides are coalesced (torch's strided permute copy gathers 4-byte
+// elements at stride 2).
+template <bool TO_DEPTH>
+__global__ void __launch_bounds__(256) space_depth2(const float* __restrict__ in, float* __restrict__ out, long long total4, int C, int D,
+                                                    int H, int W4) {
+    const int Hh = H >> 1, Wh = 2 * W4;                         // half-resolution height / width
+    const long long Vh = (long long)(D >> 1) * Hh * Wh;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total4; q += (long long)gridDim.x * blockDim.x) {
+        long long t = q;
+        const int j = (int)(t % W4); t /= W4;
+        const int h = (int)(t % H); t /= H;
+        const int d = (int)(t % D); t /= D;                     // t = b * C + c
+        const long long row = t * 8 + (d & 1) * 4 + (h & 1) * 2;
+        const long long off = row * Vh + ((long long)(d >> 1) * Hh + (h >> 1)) * Wh + 2 * j;
+        if (TO_DEPTH) {
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(in) + q);
+            *reinterpret_cast<float2*>(out + off) = make_float2(v.x, v.z);
+            *reinterpret_cast<float2*>(out + off + Vh) = make_float2(v.y, v.w);
+        } else {
+            const float2 a = __ldcs(reinterpret_cast<const float2*>(in + off)), b = __ldcs(reinterpret_cast<const float2*>(in + off + Vh));
+            reinterpret_cast<float4*>(out)[q] = make_float4(a.x, b.x, a.y, b.y);
+        }
+    }
+}
+
 }  // namespace
 }  // namespace fz
 
@@ -274,6 +303,30 @@ int fz_linear_wgrad(const float* dy, const float* x, float* dW, float* db, int64
     static SmemConfig cfg;
     FZ_CUDA_CHECK(cfg.ensure(linear_wgrad, smem));
     linear_wgrad<<<dim3((unsigned)gx, bo, bi), kWT, smem, st>>>(dy, x, dW, db, cout, cin, voxels, tps, tiles);
+    FZ_LAUNCH_CHECK();
+    return FZ_OK;
+}
+
+int fz_space_depth2_supported(int32_t D, int32_t H, int32_t W) {
+    return D > 0 && H > 0 && W > 0 && D % 2 == 0 && H % 2 == 0 && W % 4 == 0;
+}
+
+int fz_space_depth2(const float* in, float* out, int64_t batch, int32_t channels, int32_t D, int32_t H, int32_t W, int32_t to_depth,
+                    void* stream) {
+    if (batch < 0 || channels <= 0) return fail(FZ_ERR_INVALID, "space/depth: bad sizes");
+    if (!fz_space_depth2_supported(D, H, W))
+        return fail(FZ_ERR_UNSUPPORTED, "space/depth kernel needs even D, H and W divisible by 4 (got %d x %d x %d)", D, H, W);
+    if (batch == 0) return FZ_OK;
+    if (!in || !out) return fail(FZ_ERR_INVALID, "space/depth: null buffer");
+    const long long total4 = (long long)batch * channels * D * H * (W / 4);
+    int dev = 0, sms = 148;
+    FZ_CUDA_CHECK(cudaGetDevice(&dev));
+    FZ_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    long long blocks = (total4 + 255) / 256;
+    if (blocks > 16LL * sms) blocks = 16LL * sms;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (to_depth) space_depth2<true><<<(unsigned)blocks, 256, 0, st>>>(in, out, total4, channels, D, H, W / 4);
+    else space_depth2<false><<<(unsigned)blocks, 256, 0, st>>>(in, out, total4, channels, D, H, W / 4);
     FZ_LAUNCH_CHECK();
     return FZ_OK;
 }

@@ -61,15 +61,17 @@ class _PatchConv:
             return None
         B, C = x.shape[:2]
         out_sp = [n // q for n, q in zip(x.shape[2:], k)]
+        from . import _ops
         if all(q == 1 for q in k):
             xf = x.reshape(B, C, -1)
+        elif tuple(k) == (2, 2, 2) and _ops.space_depth2_supported(x):
+            xf = _ops.SpaceDepth2.apply(x, True, tuple(x.shape[2:]))                         # hand-written permutation
         else:
             split = [d for n, q in zip(out_sp, k) for d in (n, q)]
             nd = len(k)
             perm = [0, 1] + [3 + 2 * i for i in range(nd)] + [2 + 2 * i for i in range(nd)]
             xf = x.reshape(B, C, *split).permute(perm).reshape(B, C * math.prod(k), -1)     # (ci, k...) rows, one copy
-        from . import _ops
-        if not (xf.is_contiguous() and _ops.linear_wgrad_supported(xf, self.out_channels)):
+        if not (xf.is_contiguous() and _ops.linear_wgrad_supported(xf, self.out_channels, min_voxels=64)):
             return None
         return xf, out_sp
 
@@ -121,13 +123,12 @@ class _PatchConvTranspose:
 
     def _patch_ok(self, x: torch.Tensor) -> bool:
         k = self.kernel_size
-        if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == len(k) + 2 and torch.is_grad_enabled()
-                and self.weight.requires_grad and self.groups == 1 and tuple(self.stride) == tuple(k)
-                and all(d == 1 for d in self.dilation) and all(p == 0 for p in self.padding)
-                and all(p == 0 for p in self.output_padding) and x.is_contiguous()):
+        if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == len(k) + 2 and self.groups == 1
+                and tuple(self.stride) == tuple(k) and all(d == 1 for d in self.dilation)
+                and all(p == 0 for p in self.padding) and all(p == 0 for p in self.output_padding) and x.is_contiguous()):
             return False
         from . import _ops
-        return _ops.linear_wgrad_supported(x.flatten(2), self.out_channels * math.prod(k))
+        return _ops.linear_wgrad_supported(x.flatten(2), self.out_channels * math.prod(k), min_voxels=64)
 
     def forward(self, x: torch.Tensor, output_size=None) -> torch.Tensor:
         if output_size is not None or not self._patch_ok(x):
@@ -139,6 +140,9 @@ class _PatchConvTranspose:
         b = None if self.bias is None else self.bias.repeat_interleave(K)
         y = _ops.LinearCF.apply(x.flatten(2), w, b)                             # (B, co * K, voxels)
         sp = x.shape[2:]
+        full = [n * q for n, q in zip(sp, k)]
+        if tuple(k) == (2, 2, 2) and full[2] % 4 == 0:
+            return _ops.SpaceDepth2.apply(y, False, tuple(full))                # hand-written permutation
         perm = [0, 1] + [d for i in range(nd) for d in (2 + nd + i, 2 + i)]
         y = y.view(B, co, *k, *sp).permute(perm)                                # (B, co, n0, k0, n1, k1, ...)
         return y.reshape(B, co, *[n * q for n, q in zip(sp, k)])                # one copy

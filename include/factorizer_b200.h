@@ -141,6 +141,14 @@ int fz_linear_wgrad_supported(int32_t cout, int32_t cin, int64_t voxels);
 int fz_linear_wgrad(const float* dy, const float* x, float* dW, float* db, int64_t batch, int32_t cout, int32_t cin,
                     int64_t voxels, void* stream);
 
+/* (batch, channels, D, H, W) <-> (batch, channels*8, D/2*H/2*W/2) with rows ordered (c, kd, kh, kw): the view on which
+ * the reference U-Net's kernel-2 stride-2 down-sampling convolution (factorizer/unet.py:53) and transposed up-sampling
+ * convolution (unet.py:97-99) are channel maps.  to_depth != 0: full resolution -> patch rows; 0: the inverse.
+ * D, H even and W divisible by 4. */
+int fz_space_depth2_supported(int32_t D, int32_t H, int32_t W);
+int fz_space_depth2(const float* in, float* out, int64_t batch, int32_t channels, int32_t D, int32_t H, int32_t W,
+                    int32_t to_depth, void* stream);
+
 /* ---- FactMixer / FactorizerBlock pointwise glue, 32-channel blocks --------
  * All tensors are (batch, channels, voxels) fp32 = flattened NCDHW; weights are the reference's Conv1d(k=1)
  * weights squeezed to (out, in) (factorizer/layers/linear.py:43-50).  Gradient outputs are OVERWRITTEN. */

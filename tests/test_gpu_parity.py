@@ -514,7 +514,8 @@ def test_linear_weight_gradient_kernel(ft, dev, shape, cout, bias):
 
 @pytest.mark.parametrize("nd,cin,cout,k,size,bias", [(3, 32, 64, 2, (32, 32, 32), True), (3, 4, 3, 1, (32, 32, 16), True),
                                                      (3, 24, 40, 2, (16, 32, 64), False), (2, 32, 64, 2, (128, 128), True),
-                                                     (3, 8, 16, (2, 1, 2), (32, 16, 32), True)])
+                                                     (3, 8, 16, (2, 1, 2), (32, 16, 32), True), (3, 8, 8, 2, (12, 8, 6), True),
+                                                     (3, 256, 512, 2, (16, 16, 16), True)])
 def test_patch_convolution_as_channel_map(ft, dev, nd, cin, cout, k, size, bias):
     """ft.layers.ConvNd with kernel_size == stride (the reference U-Net's down-samplers and 1x1 head, unet.py:53,247)
     runs as a pointwise map on the space-to-depth view with the weight gradient from csrc/fz_linear.cu: output and
@@ -548,7 +549,8 @@ def test_patch_convolution_as_channel_map(ft, dev, nd, cin, cout, k, size, bias)
 
 
 @pytest.mark.parametrize("nd,cin,cout,k,size,bias", [(3, 64, 32, 2, (16, 16, 16), True), (3, 40, 24, 2, (8, 16, 32), False),
-                                                     (2, 64, 32, 2, (64, 64), True), (3, 16, 8, (2, 1, 2), (16, 16, 16), True)])
+                                                     (2, 64, 32, 2, (64, 64), True), (3, 16, 8, (2, 1, 2), (16, 16, 16), True),
+                                                     (3, 8, 8, 2, (6, 4, 3), True), (3, 512, 256, 2, (8, 8, 8), True)])
 def test_patch_transposed_convolution_as_channel_map(ft, dev, nd, cin, cout, k, size, bias):
     """ft.layers.ConvTransposeNd with kernel_size == stride (the reference U-Net's up-samplers, unet.py:97-99) as a
     pointwise map + depth-to-space: output and all gradients against torch's own transposed convolution in fp64."""
@@ -610,6 +612,26 @@ def test_stem_convolution_weight_gradient(ft, dev, nd, cin, cout, k, pad, size, 
         scale = max(1.0, float(r.abs().max()))
         assert_close(_np(g) / scale, _np(r) / scale, what=f"grad {i}")
     assert not cls(64, 64, kernel_size=3, padding=1).to(dev)._unfold_ok(torch.randn(1, 64, 16, 16, 16, device=dev))
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 8, 6, 12), (1, 32, 32, 32, 32), (3, 1, 2, 2, 4)])
+def test_space_to_depth_permutation(ft, dev, shape):
+    """fz_space_depth2 against the einops-style permutation it replaces, both directions, bit-exact."""
+    from factorizer_b200 import _ops
+    torch.manual_seed(8)
+    x = torch.randn(shape, device=dev)
+    B, C, D, H, W = shape
+    assert _ops.space_depth2_supported(x)
+    ref = x.view(B, C, D // 2, 2, H // 2, 2, W // 2, 2).permute(0, 1, 3, 5, 7, 2, 4, 6).reshape(B, C * 8, -1)
+    got = _ops.SpaceDepth2.apply(x, True, (D, H, W))
+    assert torch.equal(got, ref)
+    back = _ops.SpaceDepth2.apply(got, False, (D, H, W))
+    assert torch.equal(back, x)
+    xr = x.clone().requires_grad_(True)
+    g = torch.randn_like(ref)
+    (gx,) = torch.autograd.grad((_ops.SpaceDepth2.apply(xr, True, (D, H, W)) * g).sum(), xr)
+    assert torch.equal(gx, _ops.SpaceDepth2.apply(g, False, (D, H, W)))
+    assert not _ops.space_depth2_supported(torch.randn(1, 2, 4, 4, 6, device=dev))
 
 
 def test_layernorm_fallback_shapes(ft, dev):
