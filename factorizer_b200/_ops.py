@@ -6,6 +6,7 @@ import ctypes
 from typing import Optional, Sequence, Tuple
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _lib as L
 
@@ -102,6 +103,7 @@ class SWMatForward(torch.autograd.Function):
         return _gather(x, geom, divide=False)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gy):
         gy, _ = _check_mat(gy, ctx.geom, "grad")
         return _scatter(gy, ctx.batch, ctx.geom, reference_inverse=False), None
@@ -118,6 +120,7 @@ class SWMatInverse(torch.autograd.Function):
         return _scatter(y, batch, geom, reference_inverse=averaged)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g):
         g = _check_vol(g, ctx.geom, "grad")
         return _gather(g, ctx.geom, divide=ctx.averaged), None, None
@@ -193,6 +196,7 @@ class NMFReconstruct(torch.autograd.Function):
         return y.reshape(x.shape)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gy):
         x3, u0, v0, saved = ctx.saved_tensors
         gy = L.require_cuda_f32(gy, "grad").reshape(x3.shape)
@@ -219,6 +223,7 @@ class NMFDecompose(torch.autograd.Function):
         return u.reshape(*batch, size[0], spec.rank), v.reshape(*batch, size[1], spec.rank)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gu, gv):
         x3, u0, v0 = ctx.saved_tensors
         n, M, N = x3.shape
@@ -287,6 +292,7 @@ class SWNMF(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gy):
         x, u0, v0, saved = ctx.saved_tensors
         gy = _check_vol(gy, ctx.geom, "grad")
@@ -337,6 +343,7 @@ class FactorizerBlockFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gout):
         lib = L.lib()
         x, z, m, x1, saved, g1, b1n, w_in, w_out, g2, b2n, w1, bb1, w2, u0, v0 = ctx.saved_tensors
@@ -396,6 +403,7 @@ class LayerNormCF(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gy):
         lib = L.lib()
         x, w = ctx.saved_tensors
@@ -441,6 +449,7 @@ class SpaceDepth2(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g):
         D, H, W = ctx.full_shape
         return SpaceDepth2._run(g, g.shape[0], D, H, W, not ctx.to_depth), None, None
@@ -471,6 +480,7 @@ class LinearCF(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gy):
         x, weight = ctx.saved_tensors
         lib = L.lib()
@@ -488,6 +498,24 @@ class LinearCF(torch.autograd.Function):
         return gx, gw, gb
 
 
+def stem_conv_supported(x: torch.Tensor, weight: torch.Tensor, padding) -> bool:
+    """3x3x3, stride 1, padding 1, 1..4 -> 32 channels on a contiguous CUDA fp32 volume: csrc/fz_linear.cu has a direct
+    kernel for the forward (the caller checks stride / dilation / groups)."""
+    return (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and x.is_contiguous()
+            and weight.dim() == 5 and tuple(weight.shape[2:]) == (3, 3, 3) and tuple(padding) == (1, 1, 1)
+            and weight.is_contiguous() and weight.dtype == torch.float32
+            and bool(L.lib().fz_conv3d_stem_supported(x.shape[1], weight.shape[0], *x.shape[2:])))
+
+
+def conv3d_stem_forward(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    B, cin, D, H, W = x.shape
+    y = torch.empty(B, weight.shape[0], D, H, W, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _call(L.lib().fz_conv3d_stem_forward, L.ptr(x), L.ptr(weight), L.ptr(bias), L.ptr(y), B, cin, weight.shape[0], D, H, W,
+              L.stream_ptr(x.device))
+    return y
+
+
 class ConvWgradCF(torch.autograd.Function):
     """Stride-1 convolution with few input rows (C_in * prod(kernel) <= 256: the 4 -> 32 channel 3x3x3 stem of the
     Swin Factorizer, reference factorizer/factorizer.py:139-140).  Forward and input gradient are the library's; the
@@ -497,12 +525,16 @@ class ConvWgradCF(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, padding):
         nd = weight.dim() - 2
-        y = getattr(torch.nn.functional, f"conv{nd}d")(x, weight, bias, padding=padding)
+        if stem_conv_supported(x, weight, padding):
+            y = conv3d_stem_forward(x, weight.detach(), None if bias is None else bias.detach())
+        else:
+            y = getattr(torch.nn.functional, f"conv{nd}d")(x, weight, bias, padding=padding)
         ctx.save_for_backward(x, weight)
         ctx.padding, ctx.has_bias = tuple(padding), bias is not None
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gy):
         import itertools
         x, weight = ctx.saved_tensors

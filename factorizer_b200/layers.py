@@ -94,9 +94,14 @@ class _PatchConv:
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         pv = self._patch_view(x)
         if pv is None:
+            from . import _ops
             if self._unfold_ok(x):
-                from . import _ops
                 return _ops.ConvWgradCF.apply(x, self.weight, self.bias, tuple(self.padding))
+            if (not (torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad)) and self.groups == 1
+                    and all(q == 1 for q in self.stride) and all(q == 1 for q in self.dilation)
+                    and not isinstance(self.padding, str) and self.padding_mode == "zeros"
+                    and _ops.stem_conv_supported(x, self.weight, self.padding)):
+                return _ops.conv3d_stem_forward(x, self.weight, self.bias)       # inference: direct stem kernel
             return super().forward(x)
         from . import _ops
         xf, out_sp = pv

@@ -149,6 +149,13 @@ int fz_space_depth2_supported(int32_t D, int32_t H, int32_t W);
 int fz_space_depth2(const float* in, float* out, int64_t batch, int32_t channels, int32_t D, int32_t H, int32_t W,
                     int32_t to_depth, void* stream);
 
+/* 3x3x3 convolution, stride 1, zero padding 1, 1..4 input channels -> 32 output channels: the Swin Factorizer's stem
+ * (reference factorizer/factorizer.py:139-140).  x (batch, cin, D, H, W), weight (32, cin, 3, 3, 3), bias 32 floats or
+ * NULL, y (batch, 32, D, H, W); fp32 contiguous, W divisible by 4. */
+int fz_conv3d_stem_supported(int32_t cin, int32_t cout, int32_t D, int32_t H, int32_t W);
+int fz_conv3d_stem_forward(const float* x, const float* weight, const float* bias, float* y, int64_t batch, int32_t cin,
+                           int32_t cout, int32_t D, int32_t H, int32_t W, void* stream);
+
 /* ---- FactMixer / FactorizerBlock pointwise glue, 32-channel blocks --------
  * All tensors are (batch, channels, voxels) fp32 = flattened NCDHW; weights are the reference's Conv1d(k=1)
  * weights squeezed to (out, in) (factorizer/layers/linear.py:43-50).  Gradient outputs are OVERWRITTEN. */

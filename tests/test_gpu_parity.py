@@ -612,6 +612,25 @@ def test_stem_convolution_weight_gradient(ft, dev, nd, cin, cout, k, pad, size, 
         scale = max(1.0, float(r.abs().max()))
         assert_close(_np(g) / scale, _np(r) / scale, what=f"grad {i}")
     assert not cls(64, 64, kernel_size=3, padding=1).to(dev)._unfold_ok(torch.randn(1, 64, 16, 16, 16, device=dev))
+    with torch.no_grad():        # inference takes the same forward (direct kernel for the 3x3x3 -> 32 stem, library otherwise)
+        assert_close(_np(conv(x)), _np(y64), what="no_grad y")
+
+
+@pytest.mark.parametrize("cin,size,bias", [(4, (16, 12, 32), False), (1, (5, 7, 8), True), (3, (32, 32, 64), True), (2, (1, 1, 4), False)])
+def test_stem_convolution_direct_kernel(ft, dev, cin, size, bias):
+    """fz_conv3d_stem_forward (1..4 -> 32 channels, 3x3x3, padding 1) against torch's convolution in fp64, including
+    volumes thinner than the kernel."""
+    from factorizer_b200 import _ops
+    torch.manual_seed(9)
+    x = torch.randn(2, cin, *size, device=dev)
+    w = torch.randn(32, cin, 3, 3, 3, device=dev) * 0.2
+    b = torch.randn(32, device=dev) if bias else None
+    assert _ops.stem_conv_supported(x, w, (1, 1, 1))
+    y = _ops.conv3d_stem_forward(x, w, b)
+    ref = torch.nn.functional.conv3d(x.double(), w.double(), None if b is None else b.double(), padding=1)
+    assert_close(_np(y), _np(ref), what="y")
+    assert not _ops.stem_conv_supported(torch.randn(1, 4, 8, 8, 6, device=dev), w[:, :4] if cin >= 4 else torch.randn(32, 4, 3, 3, 3, device=dev), (1, 1, 1))
+    assert not _ops.stem_conv_supported(torch.randn(1, 8, 8, 8, 8, device=dev), torch.randn(32, 8, 3, 3, 3, device=dev), (1, 1, 1))
 
 
 @pytest.mark.parametrize("shape", [(2, 3, 8, 6, 12), (1, 32, 32, 32, 32), (3, 1, 2, 2, 4)])
