@@ -219,8 +219,8 @@ def model_leg(dev, n=128, steps=3):
 
         train_ms = timed(train_step)
         out = {"workload": f"Swin Factorizer (README 78-96) 4->3 ch, {n}^3, widths (32,64,128,256,512), HALS r1, B=1/GPU, fp32, "
-                           "cudnn.benchmark; wide-stage GEMMs and the patch (down / up / head) convolutions' forward are cuBLAS, the stem "
-                           "is cuDNN, every weight gradient of those layers is csrc/fz_linear.cu",
+                           "cudnn.benchmark; wide-stage GEMMs and the patch (down / up / head) convolutions' forward are cuBLAS, the stem's "
+                           "forward and every weight gradient of those layers are csrc/fz_linear.cu",
                "params": sum(q.numel() for q in net.parameters()),
                "infer_ms": infer_ms, "infer_voxels_per_s_per_gpu": n ** 3 / (infer_ms * 1e-3),
                "train_step_ms": train_ms, "train_voxels_per_s_per_gpu": n ** 3 / (train_ms * 1e-3),
