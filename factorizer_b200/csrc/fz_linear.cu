@@ -282,14 +282,26 @@ __global__ void __launch_bounds__(128, 2) conv3_stem_fwd(const float* __restrict
 #pragma unroll
         for (int o = 0; o < CO; ++o) acc[o][0] = acc[o][1] = make_float2(bs[o], bs[o]);
         const float* xb = x + t * CIN * vox;
-#pragma unroll 1
-        for (int r = 0; r < CIN * 9; ++r) {
+        // input row r = (ci, kd, kh): float4 of the thread's 4 voxels and the two neighbours; rows outside the volume are zero.
+        // The next row is fetched before the current one is used (the loop is not unrolled: 192 FFMA2 per row).
+        auto fetch = [&](int r, float4& c, float& lft, float& rgt) {
             const int ci = r / 9, kd = (r % 9) / 3, kh = r % 3;
             const int dd = d + kd - 1, hh = h + kh - 1;
-            if (dd < 0 || dd >= D || hh < 0 || hh >= H) continue;
+            if (r >= CIN * 9 || dd < 0 || dd >= D || hh < 0 || hh >= H) {
+                c = make_float4(0.f, 0.f, 0.f, 0.f); lft = rgt = 0.f;
+                return;
+            }
             const float* row = xb + ci * vox + ((long long)dd * H + hh) * W + w0;
-            const float4 c = __ldg(reinterpret_cast<const float4*>(row));
-            const float lft = w0 > 0 ? __ldg(row - 1) : 0.f, rgt = w0 + 4 < W ? __ldg(row + 4) : 0.f;
+            c = __ldg(reinterpret_cast<const float4*>(row));
+            lft = w0 > 0 ? __ldg(row - 1) : 0.f;
+            rgt = w0 + 4 < W ? __ldg(row + 4) : 0.f;
+        };
+        float4 c, cn;
+        float lft, rgt, lftn, rgtn;
+        fetch(0, c, lft, rgt);
+#pragma unroll 1
+        for (int r = 0; r < CIN * 9; ++r) {
+            fetch(r + 1, cn, lftn, rgtn);
             const float2 p[3][2] = {{make_float2(lft, c.x), make_float2(c.y, c.z)},
                                     {make_float2(c.x, c.y), make_float2(c.z, c.w)},
                                     {make_float2(c.y, c.z), make_float2(c.w, rgt)}};
@@ -306,6 +318,7 @@ __global__ void __launch_bounds__(128, 2) conv3_stem_fwd(const float* __restrict
                         acc[4 * o4 + e][1] = ffma2(make_float2(wa[e], wa[e]), p[kw][1], acc[4 * o4 + e][1]);
                     }
                 }
+            c = cn; lft = lftn; rgt = rgtn;
         }
         float* yo = y + t * CO * vox + ((long long)d * H + h) * W + w0;
 #pragma unroll

@@ -612,8 +612,12 @@ def test_stem_convolution_weight_gradient(ft, dev, nd, cin, cout, k, pad, size, 
         scale = max(1.0, float(r.abs().max()))
         assert_close(_np(g) / scale, _np(r) / scale, what=f"grad {i}")
     assert not cls(64, 64, kernel_size=3, padding=1).to(dev)._unfold_ok(torch.randn(1, 64, 16, 16, 16, device=dev))
-    with torch.no_grad():        # inference takes the same forward (direct kernel for the 3x3x3 -> 32 stem, library otherwise)
-        assert_close(_np(conv(x)), _np(y64), what="no_grad y")
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():    # inference takes the same forward (direct kernel for the 3x3x3 -> 32 stem, library otherwise)
+            assert_close(_np(conv(x)), _np(y64), what="no_grad y")
+    finally:
+        torch.backends.cudnn.allow_tf32 = keep
 
 
 @pytest.mark.parametrize("cin,size,bias", [(4, (16, 12, 32), False), (1, (5, 7, 8), True), (3, (32, 32, 64), True), (2, (1, 1, 4), False)])
