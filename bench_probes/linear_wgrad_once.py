@@ -7,7 +7,7 @@ from factorizer_b200 import _lib as L
 torch.backends.cuda.matmul.allow_tf32 = False
 dev = torch.device('cuda:0')
 lib = L.lib()
-for cout, cin, n in [(3, 32, 128), (64, 256, 64), (128, 512, 32), (64, 64, 64), (128, 64, 64), (64, 128, 64), (128, 128, 32), (256, 128, 32), (256, 256, 16), (512, 256, 16), (512, 512, 8), (1024, 512, 8)]:
+for cout, cin, n in [(32, 108, 128), (32, 64, 128), (3, 32, 128), (64, 256, 64), (128, 512, 32), (64, 64, 64), (128, 64, 64), (64, 128, 64), (128, 128, 32), (256, 128, 32), (256, 256, 16), (512, 256, 16), (512, 512, 8), (1024, 512, 8)]:
     vox = n ** 3
     gy = torch.randn(1, cout, vox, device=dev)
     x = torch.randn(1, cin, vox, device=dev)

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kWT, 3) linear_wgrad(const float* __restrict__
 // the wide layers (64 x 256 over 262144 voxels moves 1.07 GB that way) this one halves the re-reads and overlaps them:
 // 256 threads, stages of 128 voxels x (64 dy rows + 64 x rows) filled by cp.async (zero-filled past the end), warp w
 // owns 32 dy rows (w & 1) x all 64 x rows of every fourth float4 column (w >> 1).
-constexpr int kW2T = 256, kW2V = 128, kW2RS = kW2V + 4, kW2Stage = 128 * kW2RS;
+constexpr int kW2T = 256, kW2V = 128, kW2RS = kW2V + 4;
 
 __device__ __forceinline__ void cp_async16(float* dst, const float* src, bool real) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
@@ -126,14 +126,19 @@ __device__ __forceinline__ void cp_async16(float* dst, const float* src, bool re
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
 }
 
+// RB x CB = 2 x 1: a 64 x 64 block (warp halves split the dy rows); 1 x 2: a 32 x 128 block for layers with at most 32
+// outputs (the stem's unfolded 32 x 108 gradient, the decoder adapters), where the warp halves split the x rows.
+template <int RB, int CB>
 __global__ void __launch_bounds__(kW2T, 1) linear_wgrad64(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dW,
                                                           float* __restrict__ db, int cout, int cin, long long vox, int tiles_per_sample,
                                                           long long total_tiles) {
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, ro = lane & 3, co = lane >> 2;
-    const int kq = w >> 1, sr = w & 1;            // warp: float4 columns kq, kq+4, ... of dy rows [32 sr, 32 sr + 32) x all 64 x rows
-    const int o0 = blockIdx.y * 64, i0 = blockIdx.z * 64;
-    const bool sums = db != nullptr && blockIdx.z == 0;
+    static_assert((RB == 2 && CB == 1) || (RB == 1 && CB == 2), "block shape");
+    constexpr int NA = 32 * RB, NR = NA + 64 * CB, kW2Stage = NR * kW2RS;
+    const int kq = w >> 1, sr = RB == 2 ? (w & 1) : 0, sc = CB == 2 ? (w & 1) : 0;   // warp: float4 columns kq, kq+4, ... of 32 dy rows x 64 x rows
+    const int o0 = blockIdx.y * NA, i0 = blockIdx.z * 64 * CB;
+    const bool sums = db != nullptr && blockIdx.z == 0 && sc == 0;
     // an 8 x 8 register tile per lane: 16 LDS.128 per 128 FFMA2 (a 128-bit shared load holds the LSU for four cycles
     // whatever the broadcast, so the 8 x 4 tile of the kernel above is LSU-bound at two thirds of the FP32 pipe)
     float2 acc[8][8];
@@ -153,10 +158,10 @@ __global__ void __launch_bounds__(kW2T, 1) linear_wgrad64(const float* __restric
         const float* gdy = dy + b * cout * vox;
         const float* gx = x + b * cin * vox;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int r = (tid >> 5) + 8 * i;              // 0..127: dy rows, then x rows
-            const bool isx = r >= 64;
-            const int ch = isx ? i0 + r - 64 : o0 + r;
+        for (int i = 0; i < NR / 8; ++i) {
+            const int r = (tid >> 5) + 8 * i;              // dy rows, then x rows
+            const bool isx = r >= NA;
+            const int ch = isx ? i0 + r - NA : o0 + r;
             const bool real = in_v && ch < (isx ? cin : cout);
             const float* src = real ? (isx ? gx : gdy) + (long long)ch * vox + v : dy;
             cp_async16(S + r * kW2RS, src, real);
@@ -176,7 +181,7 @@ __global__ void __launch_bounds__(kW2T, 1) linear_wgrad64(const float* __restric
         }
         __syncthreads();
         const float* SA = sm + stage * kW2Stage + (32 * sr) * kW2RS;
-        const float* SB = sm + stage * kW2Stage + 64 * kW2RS;
+        const float* SB = sm + stage * kW2Stage + (NA + 64 * sc) * kW2RS;
 #pragma unroll 1
         for (int it = 0; it < kW2V / 4 / 4; ++it) {
             const int v = (4 * it + kq) * 4;
@@ -202,24 +207,24 @@ __global__ void __launch_bounds__(kW2T, 1) linear_wgrad64(const float* __restric
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int k = 0; k < 8; ++k) scr[w * 2048 + (ro + 4 * i) * 64 + co + 8 * k] = acc[i][k].x + acc[i][k].y;
-    float* rsum = sm + 8 * 2048;    // [64] row sums of dy
-    if (tid < 64) rsum[tid] = 0.f;
+    float* rsum = sm + 8 * 2048;    // [NA] row sums of dy
+    if (tid < NA) rsum[tid] = 0.f;
     __syncthreads();
     for (int e = tid; e < 4096; e += kW2T) {
-        const int half = e >> 11, q = e & 2047;
+        const int half = e >> 11, q = e & 2047;                   // half = the warp pair's sr (2 x 1) or sc (1 x 2)
         float t = 0.f;
 #pragma unroll
         for (int g = 0; g < 4; ++g) t += scr[(2 * g + half) * 2048 + q];
-        const int o = o0 + 32 * half + (q >> 6), c = i0 + (q & 63);
+        const int o = o0 + (RB == 2 ? 32 * half : 0) + (q >> 6), c = i0 + (CB == 2 ? 64 * half : 0) + (q & 63);
         if (o < cout && c < cin) atomicAdd(dW + (long long)o * cin + c, t);
     }
-    if (sums) {
-        if (co == 0) {
+    if (db != nullptr && blockIdx.z == 0) {                       // uniform over the CTA
+        if (sums && co == 0) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) atomicAdd(rsum + 32 * sr + ro + 4 * i, rs[i]);   // once per kernel
         }
         __syncthreads();
-        if (tid < 64 && o0 + tid < cout) atomicAdd(db + o0 + tid, rsum[tid]);
+        if (tid < NA && o0 + tid < cout) atomicAdd(db + o0 + tid, rsum[tid]);
     }
 }
 
@@ -353,17 +358,25 @@ int fz_linear_wgrad(const float* dy, const float* x, float* dW, float* db, int64
     int dev = 0, sms = 148;
     FZ_CUDA_CHECK(cudaGetDevice(&dev));
     FZ_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (cout >= 64 && cin >= 64 && batch * voxels >= 32768) {      // fewer voxels: the smaller CTAs spread better
+    // fewer voxels: the smaller CTAs of the 32 x 32 kernel spread better; a 32 x 128 block pays from 65 input rows on
+    if ((cout >= 64 ? cin >= 64 : cin > 64) && batch * voxels >= 32768) {
         const int tps = (int)((voxels + kW2V - 1) / kW2V);
         const long long tiles = batch * tps;
-        const int bo = (cout + 63) / 64, bi = (cin + 63) / 64;
+        const bool wide = cout >= 64;                 // 64 x 64 blocks, else 32 x 128
+        const int bo = wide ? (cout + 63) / 64 : (cout + 31) / 32, bi = wide ? (cin + 63) / 64 : (cin + 127) / 128;
         long long gx = (2LL * sms + bo * bi - 1) / (bo * bi);
         if (gx > tiles) gx = tiles;
         if (gx < 1) gx = 1;
-        const size_t smem = sizeof(float) * 2 * kW2Stage;       // 132 KB: two stages; the epilogue scratch (64.3 KB) aliases them
-        static SmemConfig cfg64;
-        FZ_CUDA_CHECK(cfg64.ensure(linear_wgrad64, smem));
-        linear_wgrad64<<<dim3((unsigned)gx, bo, bi), kW2T, smem, st>>>(dy, x, dW, db, cout, cin, voxels, tps, tiles);
+        // two cp.async stages; the epilogue scratch (64.3 KB) aliases them
+        const size_t smem = sizeof(float) * 2 * (wide ? 128 : 160) * kW2RS;
+        static SmemConfig cfg21, cfg12;
+        if (wide) {
+            FZ_CUDA_CHECK(cfg21.ensure(linear_wgrad64<2, 1>, smem));
+            linear_wgrad64<2, 1><<<dim3((unsigned)gx, bo, bi), kW2T, smem, st>>>(dy, x, dW, db, cout, cin, voxels, tps, tiles);
+        } else {
+            FZ_CUDA_CHECK(cfg12.ensure(linear_wgrad64<1, 2>, smem));
+            linear_wgrad64<1, 2><<<dim3((unsigned)gx, bo, bi), kW2T, smem, st>>>(dy, x, dW, db, cout, cin, voxels, tps, tiles);
+        }
         FZ_LAUNCH_CHECK();
         return FZ_OK;
     }

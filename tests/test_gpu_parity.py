@@ -484,7 +484,8 @@ def test_layernorm_channels_first(ft, dev, shape):
 
 
 @pytest.mark.parametrize("shape,cout,bias", [((1, 64, 32, 32, 32), 128, True), ((2, 96, 8200), 64, True),
-                                             ((1, 32, 40, 40, 12), 32, False), ((3, 128, 24, 24, 24), 256, True)])
+                                             ((1, 32, 40, 40, 12), 32, False), ((3, 128, 24, 24, 24), 256, True),
+                                             ((1, 96, 32, 32, 32), 40, True), ((2, 200, 32, 32, 16), 32, True)])
 def test_linear_weight_gradient_kernel(ft, dev, shape, cout, bias):
     """ft.Linear on long voxel axes: output and input gradient are library GEMMs, the weight / bias gradients come
     from csrc/fz_linear.cu; all four against the reference's formulation (a k=1 Conv1d, layers/linear.py:53-58) in
