@@ -455,15 +455,19 @@ class SpaceDepth2(torch.autograd.Function):
         return SpaceDepth2._run(g, g.shape[0], D, H, W, not ctx.to_depth), None, None
 
 
-def linear_wgrad_supported(x: torch.Tensor, out_channels: int, min_voxels: int = 4096) -> bool:
+def linear_wgrad_supported(x: torch.Tensor, out_channels: int, min_voxels: int = 4096, rows: Optional[int] = None,
+                           voxels: Optional[int] = None) -> bool:
     """The contraction over voxels is worth a kernel of its own when it is long (library SGEMMs take their slow
     large-K route there); short ones stay with cuBLAS."""
     if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() >= 3):
         return False
-    vox = x.numel() // max(x.shape[0] * x.shape[1], 1)
+    if torch.is_autocast_enabled():          # the fp32 kernels are not autocast-aware: leave mixed precision to the library
+        return False
+    # rows / voxels: the (B, rows, voxels) view the caller is about to build from x (space-to-depth), if not x itself
+    vox = x.numel() // max(x.shape[0] * x.shape[1], 1) if voxels is None else int(voxels)
     if x.shape[0] * vox < min_voxels:
         return False
-    return bool(L.lib().fz_linear_wgrad_supported(int(out_channels), x.shape[1], vox))
+    return bool(L.lib().fz_linear_wgrad_supported(int(out_channels), x.shape[1] if rows is None else int(rows), vox))
 
 
 class LinearCF(torch.autograd.Function):
@@ -502,7 +506,7 @@ def stem_conv_supported(x: torch.Tensor, weight: torch.Tensor, padding) -> bool:
     """3x3x3, stride 1, padding 1, 1..4 -> 32 channels on a contiguous CUDA fp32 volume: csrc/fz_linear.cu has a direct
     kernel for the forward (the caller checks stride / dilation / groups)."""
     return (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and x.is_contiguous()
-            and weight.dim() == 5 and tuple(weight.shape[2:]) == (3, 3, 3) and tuple(padding) == (1, 1, 1)
+            and not torch.is_autocast_enabled() and weight.dim() == 5 and tuple(weight.shape[2:]) == (3, 3, 3) and tuple(padding) == (1, 1, 1)
             and weight.is_contiguous() and weight.dtype == torch.float32
             and bool(L.lib().fz_conv3d_stem_supported(x.shape[1], weight.shape[0], *x.shape[2:])))
 

@@ -62,6 +62,8 @@ class _PatchConv:
         B, C = x.shape[:2]
         out_sp = [n // q for n, q in zip(x.shape[2:], k)]
         from . import _ops
+        if not _ops.linear_wgrad_supported(x, self.out_channels, min_voxels=64, rows=C * math.prod(k), voxels=math.prod(out_sp)):
+            return None
         if all(q == 1 for q in k):
             xf = x.reshape(B, C, -1)
         elif tuple(k) == (2, 2, 2) and _ops.space_depth2_supported(x):
@@ -71,8 +73,8 @@ class _PatchConv:
             nd = len(k)
             perm = [0, 1] + [3 + 2 * i for i in range(nd)] + [2 + 2 * i for i in range(nd)]
             xf = x.reshape(B, C, *split).permute(perm).reshape(B, C * math.prod(k), -1)     # (ci, k...) rows, one copy
-        if not (xf.is_contiguous() and _ops.linear_wgrad_supported(xf, self.out_channels, min_voxels=64)):
-            return None
+        if not xf.is_contiguous():
+            xf = xf.contiguous()
         return xf, out_sp
 
     def _unfold_ok(self, x: torch.Tensor) -> bool:
@@ -82,7 +84,8 @@ class _PatchConv:
         if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == len(k) + 2 and torch.is_grad_enabled()
                 and self.weight.requires_grad and self.groups == 1 and all(q == 1 for q in self.stride)
                 and all(d == 1 for d in self.dilation) and not isinstance(self.padding, str)
-                and self.padding_mode == "zeros" and math.prod(k) > 1 and x.is_contiguous()):
+                and self.padding_mode == "zeros" and math.prod(k) > 1 and x.is_contiguous()
+                and not torch.is_autocast_enabled()):
             return False
         rows = self.in_channels * math.prod(k)
         out_sp = [n + 2 * p - q + 1 for n, p, q in zip(x.shape[2:], self.padding, k)]

@@ -658,6 +658,30 @@ def test_space_to_depth_permutation(ft, dev, shape):
     assert not _ops.space_depth2_supported(torch.randn(1, 2, 4, 4, 6, device=dev))
 
 
+def test_channel_map_layers_leave_autocast_to_the_library(ft, dev):
+    """Under torch.autocast the fp32 channel-map kernels step aside: Linear and the patch / stem convolutions behave as
+    the stock modules (reduced-precision output, working backward)."""
+    from factorizer_b200 import layers
+    torch.manual_seed(10)
+    x = torch.randn(1, 32, 32, 32, 32, device=dev, requires_grad=True)
+    mods = [ft.Linear(32, 64).to(dev), layers.Conv3d(32, 64, kernel_size=2, stride=2).to(dev),
+            layers.ConvTranspose3d(32, 16, kernel_size=2, stride=2).to(dev)]
+    stem = layers.Conv3d(4, 32, kernel_size=3, padding=1, bias=False).to(dev)
+    x4 = torch.randn(1, 4, 32, 32, 32, device=dev)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        for m in mods:
+            y = m(x)
+            assert y.dtype == torch.bfloat16
+            y.float().sum().backward()
+            assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+        assert stem._patch_view(x4) is None and not stem._unfold_ok(x4)
+        y = stem(x4)
+        assert y.dtype == torch.bfloat16
+        y.float().sum().backward()
+        assert torch.isfinite(stem.weight.grad).all()
+    assert stem._unfold_ok(x4)
+
+
 def test_layernorm_fallback_shapes(ft, dev):
     """Channel counts / voxel counts without a kernel take the reference's own permute + nn.LayerNorm route."""
     from factorizer_b200 import _ops
