@@ -1,11 +1,17 @@
-// Weight gradient of the pointwise (k = 1) channel map y = W x + b on channels-first activations
-// (factorizer/layers/linear.py:53-58 runs it as a Conv1d; its weight gradient is the contraction over voxels):
-//     dW[o][i] = sum_{b,v} dy[b][o][v] x[b][i][v],     db[o] = sum_{b,v} dy[b][o][v]
-// The Swin Factorizer's wider stages give this a 64..1024 x 64..512 result over 512..262144 voxels, a shape library
-// SGEMMs handle badly (sgemm_largek: 340 us for 64 x 64 x 262144, 10 % of the FP32 pipe).  Here a CTA owns one
-// 32 x 32 block of dW and a share of the voxel tiles, stages 256 voxels of its 32 + 32 rows in shared memory, keeps
-// the 32 x 32 partial sums in registers (a warp takes every 4th float4 column, a lane an 8 x 4 sub-block read with
-// broadcast LDS.128) and adds them to dW once at the end.  FP32 pipe, exact fp32 products.
+// Channel maps around the Factorizer blocks: the pieces of the reference's pointwise Linear (factorizer/layers/linear.py:53-58),
+// of its U-Net scaffold's patch convolutions (factorizer/unet.py:53, 97-99, 247) and of its stem (factorizer/factorizer.py:
+// 139-140) that the libraries handle badly at these shapes.  Four groups of kernels, each behind its own C entry point:
+//
+//   fz_linear_wgrad          dW[o][i] = sum_{b,v} dy[b][o][v] x[b][i][v],  db[o] = sum_{b,v} dy[b][o][v]
+//   fz_space_depth2          (B,C,D,H,W) <-> (B,8C,DHW/8): the view on which a 2x2x2 stride-2 (transposed) convolution is a channel map
+//   fz_conv3d_stem_forward   3x3x3, padding 1, 1..4 -> 32 channels
+//
+// Weight gradient: the Swin Factorizer's wider stages give it a 64..1024 x 64..512 result over 512..262144 voxels, a shape
+// library SGEMMs handle badly (sgemm_largek: 340 us for 64 x 64 x 262144, 10 % of the FP32 pipe; cuDNN's fp32 wgrad of the
+// patch convolutions: 1.7-4.4 ms).  linear_wgrad: a CTA owns one 32 x 32 block of dW and a share of the voxel tiles, stages
+// 256 voxels of its 32 + 32 rows in shared memory, keeps the partial sums in registers (a warp takes every 4th float4 column,
+// a lane an 8 x 4 sub-block read with broadcast LDS.128) and adds them to dW once at the end.  linear_wgrad64 (further down):
+// 64 x 64 or 32 x 128 blocks, cp.async double buffering, 8 x 8 register tiles.  FP32 pipe, exact fp32 products.
 #include "fz_common.cuh"
 #include "fz_internal.cuh"
 
