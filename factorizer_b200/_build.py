@@ -12,12 +12,13 @@ LIB_PATH = os.path.join(OUT_DIR, "libfactorizer_b200.so")
 SOURCES = ["fz_api.cu", "fz_swmat.cu", "fz_nmf_generic.cu", "fz_swnmf_fast.cu", "fz_swnmf_phase.cu", "fz_layernorm.cu",
            "fz_block_glue.cu", "fz_swnmf_small.cu", "fz_nmf_big.cu", "fz_block_glue_tc.cu", "fz_linear.cu"]
 
+OBJ_DIR = os.path.join(OUT_DIR, "obj")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
-    "-cudart", "static",
+    "-Xcompiler", "-fPIC",
 ]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-cudart", "static"]
 
 
 def _nvcc() -> str:
@@ -36,20 +37,41 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu into factorizer_b200/_C/libfactorizer_b200.so."""
-    if not force and not _stale():
-        return LIB_PATH
-    os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+def _compile_one(src: str, obj: str, verbose: bool) -> str:
+    cmd = [_nvcc(), *NVCC_FLAGS, "-c", "-o", obj, src]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd))
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
+    return res.stderr
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu into factorizer_b200/_C/libfactorizer_b200.so: one object per source (only the
+    stale ones, in parallel), then one link."""
+    if not force and not _stale():
+        return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
+
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(os.path.dirname(HERE), "include", "factorizer_b200.h"))
+    headers.append(os.path.abspath(__file__))
+    t_hdr = max(os.path.getmtime(h) for h in headers)
+    jobs = []
+    for s in SOURCES:
+        src, obj = os.path.join(CSRC, s), os.path.join(OBJ_DIR, s[:-3] + ".o")
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), t_hdr):
+            jobs.append((src, obj))
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:
+        logs = list(ex.map(lambda j: _compile_one(j[0], j[1], verbose), jobs))
     if verbose:
-        print(res.stderr)
+        print("\n".join(logs))
+    objs = [os.path.join(OBJ_DIR, s[:-3] + ".o") for s in SOURCES]
+    res = subprocess.run([_nvcc(), *LINK_FLAGS, "-o", LIB_PATH, *objs], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     return LIB_PATH
 
 

@@ -3,6 +3,7 @@ autograd bookkeeping; every byte of arithmetic happens in libfactorizer_b200.so.
 from __future__ import annotations
 
 import ctypes
+import threading
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -46,6 +47,23 @@ class SolverSpec:
 
     def c_solver(self) -> L.FzSolver:
         return L.make_solver(self.kind, self.rank, self.num_iters, self.num_grad_steps, self.eps)
+
+
+class _GradModeFunction(torch.autograd.Function):
+    """autograd.Function whose forward can tell whether a backward may follow.  Function.forward always runs with grad
+    mode off and ctx.needs_input_grad only reflects requires_grad of the inputs, so under torch.no_grad() (inference
+    with an unfrozen model) it would still ask for the saved buffers; the caller's grad mode is recorded on entry."""
+    _caller = threading.local()
+
+    @classmethod
+    def apply(cls, *args, **kwargs):
+        _GradModeFunction._caller.grad = torch.is_grad_enabled()
+        return super().apply(*args, **kwargs)
+
+    @staticmethod
+    def wants_grad(ctx, upto=None) -> bool:
+        flags = ctx.needs_input_grad if upto is None else ctx.needs_input_grad[:upto]
+        return bool(getattr(_GradModeFunction._caller, "grad", True)) and any(flags)
 
 
 def _check_vol(x: torch.Tensor, geom: Geometry, name: str) -> torch.Tensor:
@@ -175,7 +193,7 @@ def _as_one_window_volume(spec: SolverSpec, size):
     return Geometry(channels=M, size=(N,), patch=(N,), head_dim=M, shifts=[(0,)])
 
 
-class NMFReconstruct(torch.autograd.Function):
+class NMFReconstruct(_GradModeFunction):
     """MatrixFactorization.forward = reconstruct(decompose(x))
     (reference matrix_factorization.py:514-533, 544-546) as one kernel per direction."""
 
@@ -188,7 +206,7 @@ class NMFReconstruct(torch.autograd.Function):
         geom = _as_one_window_volume(spec, size) if x3.shape[0] > 0 else None
         saved = None
         if geom is not None:
-            y, saved = _swnmf_forward(x3, u0, v0, geom, spec, False, ctx.needs_input_grad[0])
+            y, saved = _swnmf_forward(x3, u0, v0, geom, spec, False, _GradModeFunction.wants_grad(ctx, 1))
         else:
             _, _, y = _nmf_forward(x3, u0, v0, spec, want_uv=False, want_y=True)
         ctx.save_for_backward(x3, u0, v0, saved)
@@ -277,7 +295,7 @@ def _swnmf_backward(x, gy, u0, v0, saved, geom: Geometry, spec: SolverSpec, relu
     return gx
 
 
-class SWNMF(torch.autograd.Function):
+class SWNMF(_GradModeFunction):
     """reshape -> act -> factorize -> reshape.inverse_forward of FactMixer.forward
     (reference factorizer/factorizer.py:41-50): X is read once and Y written once."""
 
@@ -286,7 +304,7 @@ class SWNMF(torch.autograd.Function):
         x = _check_vol(x, geom, "x")
         u0 = L.require_cuda_f32(u0, "u0")
         v0 = L.require_cuda_f32(v0, "v0")
-        y, saved = _swnmf_forward(x, u0, v0, geom, spec, relu, ctx.needs_input_grad[0])
+        y, saved = _swnmf_forward(x, u0, v0, geom, spec, relu, _GradModeFunction.wants_grad(ctx, 1))
         ctx.save_for_backward(x, u0, v0, saved)
         ctx.geom, ctx.spec, ctx.relu = geom, spec, relu
         return y
@@ -310,7 +328,7 @@ def block_glue_supported(x: torch.Tensor, hidden: int) -> bool:
     return bool(L.lib().fz_glue_supported(x.shape[1], int(hidden), vox))
 
 
-class FactorizerBlockFn(torch.autograd.Function):
+class FactorizerBlockFn(_GradModeFunction):
     """FactorizerBlock.forward (reference factorizer/factorizer.py:74-77 with FactMixer.forward :34-57) for
     norm = LayerNorm, act = ReLU, no dropout: three launches forward (norm1+in_proj | fused matricize+NMF core |
     out_proj+residual+norm2+MLP+residual), four backward.  Saves x, z (in_proj output), m (core output) and x1
@@ -327,7 +345,7 @@ class FactorizerBlockFn(torch.autograd.Function):
         B, C = x.shape[0], x.shape[1]
         vox = x.numel() // max(B * C, 1)
         hid = w1.shape[0]
-        need_grad = any(ctx.needs_input_grad[:12])
+        need_grad = _GradModeFunction.wants_grad(ctx, 12)
         st = L.stream_ptr(x.device)
         z = torch.empty_like(x)
         out = torch.empty_like(x)

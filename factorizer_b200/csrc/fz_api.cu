@@ -121,9 +121,19 @@ int fz_nmf_backward(const float* x, const float* u0, const float* v0, const floa
 size_t fz_swnmf_saved_bytes(const fz_geom* g, const fz_solver* s) {
     DevGeom G;
     if (make_dev_geom(g, &G) || !s) return 0;
-    if (!phase_supported(G, *s, 1) && pairs_supported(G, *s, 1)) return pairs_saved_bytes(G, *s);
-    if (big_window(G, *s)) return big_saved_bytes(G.mats_per_shift, G.d, G.P, *s);
-    return fast_saved_bytes(G, *s);
+    // The caller does not say here whether the input passes through a ReLU, so size the buffer for whichever
+    // kernel family fz_swnmf_forward may pick for this geometry (the octant kernels and their paired variant have
+    // no limit on the number of windows, the window-at-a-time kernels do).
+    size_t need = fast_saved_bytes(G, *s);
+    if (phase_supported(G, *s, 1) || pairs_supported(G, *s, 1)) {
+        const size_t b = pairs_saved_bytes(G, *s);      // S * windows * record, the same record for both
+        if (b > need) need = b;
+    }
+    if (big_window(G, *s)) {
+        const size_t b = big_saved_bytes(G.mats_per_shift, G.d, G.P, *s);
+        if (b > need) need = b;
+    }
+    return need;
 }
 
 size_t fz_swnmf_workspace_bytes(const fz_geom* g, const fz_solver* s) {

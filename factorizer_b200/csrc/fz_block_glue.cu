@@ -653,16 +653,7 @@ int glue_mode() {
     return g_glue_mode;
 }
 
-int sm_count() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    return sms;
-}
+int sm_count() { return num_sms(); }
 
 int check_common(long long batch, int channels, long long voxels) {
     if (batch < 0 || voxels < 0) return fail(FZ_ERR_INVALID, "negative size");

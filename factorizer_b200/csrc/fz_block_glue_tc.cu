@@ -521,16 +521,7 @@ size_t lbw_tc_smem_bytes() { return (size_t)16 * kKS + (kC * kC + 2 * kC + 3 * k
 
 size_t tc_smem_bytes() { return (size_t)2 * kTM * kMaxHid * 4 + 2 * kC * kC * 4 + 4 * kMaxHid * kC * 4 + (4 * kC + kMaxHid) * 4 + 1024; }
 
-int tc_sm_count() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    return sms;
-}
+int tc_sm_count() { return num_sms(); }
 
 }  // namespace
 

@@ -50,6 +50,20 @@ struct SmemConfig {
     }
 };
 
+// Number of SMs of the CURRENT device (cached per device; a process may drive several GPUs).
+inline int num_sms() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    int& v = cached[dev & 63];
+    if (v <= 0) {
+        int sms = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        v = sms > 0 ? sms : 148;
+    }
+    return v;
+}
+
 // ---- device-side geometry ----------------------------------------------------------------------
 // Derived from fz_geom once on the host; passed to kernels by value.
 struct DevGeom {

@@ -411,16 +411,7 @@ int ln_slices(int channels, long long total_pairs) {
     return channels >= 256 ? 8 : (channels >= 128 ? 4 : 2);
 }
 
-int sm_count() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    return sms;
-}
+int sm_count() { return num_sms(); }
 
 template <int C>
 int launch_fwd(const float* x, const float* gamma, const float* beta, float* y, long long batch, long long voxels, float eps, cudaStream_t st) {

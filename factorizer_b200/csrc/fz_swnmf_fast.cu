@@ -141,14 +141,18 @@ __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void pair_bar(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-// Completion counters are polled with relaxed gpu-scope loads: everything that is read once a counter
-// shows "done" is fetched from L2 (cp.async.cg / TMA / ld.global.cg, never the SM's L1) by instructions
-// that are control-dependent on the poll, and the writer publishes with a release reduction, so no
-// L1-invalidating acquire (LD + CCTL.IVALL, ~1 us per poll) is needed on this side.
+// Completion counters are polled with relaxed gpu-scope loads (an acquire on every poll costs an L1 invalidation,
+// ~1 us, per iteration); once a poll shows "done" the observer issues ONE acquire fence, plus a proxy fence because
+// the dependent reads are TMA / bulk loads in the async proxy (acquire_after_poll).  The writer publishes with a
+// release reduction after its bulk stores have completed.
 __device__ __forceinline__ int ld_poll(const int* p) {
     int v;
     asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ void acquire_after_poll() {
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    asm volatile("fence.proxy.async;" ::: "memory");
 }
 __device__ __forceinline__ void red_release_add(int* p, int v) {
     asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -302,6 +306,7 @@ __device__ __forceinline__ void wait_rows(const FastParams& P, const Info& it, i
 #pragma unroll
     for (int q = 0; q < 4; ++q)
         while (ld_poll(d.p[q]) < P.TPR) __nanosleep(64);
+    acquire_after_poll();
 }
 // Completion of a window whose output left through TMA / bulk stores that the caller has already waited
 // for with cp.async.bulk.wait_group 0.  That wait alone is NOT enough to publish with a relaxed
@@ -548,6 +553,7 @@ __global__ void __launch_bounds__(kFwdPairs * 64, 1) swnmf_fwd_fast(const __grid
                     if (pend.set >= 0) { signal_row(P, pend.set, pend.b, pend.rowid); pend.set = -1; }
                     const int first = P.final_set == 0 ? 1 : 0;
                     if (dc[0] < P.TPR || dc[1] < P.TPR || dc[2] < P.TPR || dc[3] < P.TPR) wait_rows(P, it, first);
+                    else acquire_after_poll();
                     for (int s = first + 1; s < P.S; ++s)
                         if (s != P.final_set) wait_rows(P, it, s);
                 }
@@ -705,8 +711,10 @@ __global__ void __launch_bounds__(kBwdPairs * 64, 1) swnmf_bwd_fast(const __grid
                 gv[0] = fma2(g0, ui, gv[0]); gv[1] = fma2(g1, ui, gv[1]);
                 gv[2] = fma2(g2, ui, gv[2]); gv[3] = fma2(g3, ui, gv[3]);
             }
-            if (c.second)
+            if (c.second) {
                 ps.oready = (dep >= 0) && ((P.debug & 1) || (dc[0] >= P.TPR && dc[1] >= P.TPR && dc[2] >= P.TPR && dc[3] >= P.TPR));
+                if (ps.oready) acquire_after_poll();      // ordered before the pair's fetch by the barrier in pair_reduce9
+            }
             float dummy = 0.f;
             pair_reduce9(gu, dummy, ps.red, slot, c.wip, c.lane, c.barid);
             const f2 is2 = dup(P.inv_S);
@@ -917,16 +925,6 @@ size_t fast_workspace_bytes(const DevGeom& G, const fz_solver& s) {
     return counter_bytes(G) + (size_t)(G.S - 1) * G.mats_per_shift * kFacFloats * sizeof(float);
 }
 
-static int num_sms() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    return sms;
-}
 
 // rows of set `dep` overlapped by row `row` of set `s`; returns the largest of `when[]` over them
 static long long latest_needed(const DevGeom& G, const FastParams& P, int s, int row, int dep, const long long* when) {
@@ -1070,18 +1068,12 @@ int fast_forward(const float* x, const float* u0, const float* v0, float* y, voi
     P.fac = reinterpret_cast<float*>(static_cast<char*>(workspace) + counter_bytes(G));
     FZ_CUDA_CHECK(cudaMemsetAsync(workspace, 0, counter_bytes(G), st));
     const size_t smem = (size_t)kFwdPairs * kTileBytes;
-    static bool attr_set = false;
-    if (!attr_set) {
-        FZ_CUDA_CHECK(cudaFuncSetAttribute(swnmf_fwd_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    static SmemConfig cfg_fwd;
+    FZ_CUDA_CHECK(cfg_fwd.ensure(swnmf_fwd_fast<false>, smem));
     if (relu) {
         const size_t gsmem = (size_t)kGFwdWarps * (kTileBytes + kTileBytes / 2);
-        static bool gattr = false;
-        if (!gattr) {
-            FZ_CUDA_CHECK(cudaFuncSetAttribute(swnmf_fwd_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-            gattr = true;
-        }
+        static SmemConfig cfg_gfwd;
+        FZ_CUDA_CHECK(cfg_gfwd.ensure(swnmf_fwd_gram, gsmem));
         int ctas_needed = (P.total_items + kGFwdWarps - 1) / kGFwdWarps;
         int grid = num_sms();
         if (ctas_needed < grid) grid = ctas_needed;
@@ -1113,18 +1105,12 @@ int fast_backward(const float* x, const float* gy, const float* u0, const float*
     P.ctr = static_cast<int*>(workspace);
     FZ_CUDA_CHECK(cudaMemsetAsync(workspace, 0, counter_bytes(G), st));
     const size_t smem = (size_t)kBwdPairs * 3 * kTileBytes;
-    static bool attr_set = false;
-    if (!attr_set) {
-        FZ_CUDA_CHECK(cudaFuncSetAttribute(swnmf_bwd_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    static SmemConfig cfg_bwd;
+    FZ_CUDA_CHECK(cfg_bwd.ensure(swnmf_bwd_fast<false>, smem));
     if (relu) {
         const size_t gsmem = (size_t)kGBwdPairs * 3 * kTileBytes;
-        static bool gattr = false;
-        if (!gattr) {
-            FZ_CUDA_CHECK(cudaFuncSetAttribute(swnmf_bwd_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-            gattr = true;
-        }
+        static SmemConfig cfg_gbwd;
+        FZ_CUDA_CHECK(cfg_gbwd.ensure(swnmf_bwd_gram, gsmem));
         int ctas_needed = (P.total_items + kGBwdPairs - 1) / kGBwdPairs;
         int grid = num_sms();
         if (ctas_needed < grid) grid = ctas_needed;

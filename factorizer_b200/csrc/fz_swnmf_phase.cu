@@ -898,16 +898,6 @@ int make_map(CUtensorMap* m, const void* ptr, const DevGeom& G) {
     if (r != CUDA_SUCCESS) return fail(FZ_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return FZ_OK;
 }
-int num_sms() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    return sms;
-}
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 int rec_head_for(int T) { return ((9 * T + 3) / 4) * 4; }
 
@@ -994,12 +984,9 @@ int phase_forward(const float* x, const float* v0, float* y, void* saved, void* 
     fill(P, G, s, 0, workspace);
     if (int e = make_map(&P.tm_x, x, G)) return e;
     P.x = x; P.out = y; P.v0 = v0; P.saved = static_cast<float*>(saved);
-    static bool attr = false;
-    if (!attr) {
-        FZ_CUDA_CHECK(cudaFuncSetAttribute(phase_fwd_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, kW1 * 2 * kTileBytes));
-        FZ_CUDA_CHECK(cudaFuncSetAttribute(phase_fwd_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, kW3 * 2 * kTileBytes));
-        attr = true;
-    }
+    static SmemConfig cfg_gram, cfg_apply;
+    FZ_CUDA_CHECK(cfg_gram.ensure(phase_fwd_gram, kW1 * 2 * kTileBytes));
+    FZ_CUDA_CHECK(cfg_apply.ensure(phase_fwd_apply, kW3 * 2 * kTileBytes));
     // (sample, head) sub-volumes are independent problems: pass 1-3 can run chunk by chunk, so that
     // pass 3 finds what pass 1 read still in L2
     const int per_sv = G.G, svs = G.B * G.heads, svc = svs_per_chunk(G, 1);
@@ -1036,12 +1023,9 @@ int phase_backward(const float* x, const float* gy, const float* v0, const void*
     if (int e = make_map(&P.tm_g, gy, G)) return e;
     P.x = x; P.gy = gy; P.out = gx; P.v0 = v0;
     P.saved = const_cast<float*>(static_cast<const float*>(saved));
-    static bool attr = false;
-    if (!attr) {
-        FZ_CUDA_CHECK(cudaFuncSetAttribute(phase_bwd_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, kWB * 4 * kTileBytes));
-        FZ_CUDA_CHECK(cudaFuncSetAttribute(phase_bwd_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, kWB * 4 * kTileBytes));
-        attr = true;
-    }
+    static SmemConfig cfg_reduce, cfg_apply;
+    FZ_CUDA_CHECK(cfg_reduce.ensure(phase_bwd_reduce, kWB * 4 * kTileBytes));
+    FZ_CUDA_CHECK(cfg_apply.ensure(phase_bwd_apply, kWB * 4 * kTileBytes));
     const int per_sv = G.G, svs = G.B * G.heads, svc = svs_per_chunk(G, 2);
     for (int sv = 0; sv < svs; sv += svc) {
         P.t_begin = sv * per_sv;

@@ -514,16 +514,7 @@ __global__ void __launch_bounds__(kSmallThreads) small_bwd(const SmallParams P) 
     }
 }
 
-int small_sm_count() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    return sms;
-}
+int small_sm_count() { return num_sms(); }
 
 template <int M, int CPL, int L>
 int launch_small(const SmallParams& P, bool bwd, cudaStream_t st) {

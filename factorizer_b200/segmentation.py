@@ -108,7 +108,9 @@ class UNet(nn.Module):
             self.head = head(encoder_width[0], out_channels)
         else:
             self.num_deep_supr = 3 if num_deep_supr is True else num_deep_supr
-            self.heads = nn.ModuleList(head(encoder_width[j], out_channels) for j in range(self.num_deep_supr))
+            # as the reference (factorizer/unet.py:255-258): the stored count is 3 for True, but the heads are built
+            # over range(num_deep_supr) of the ARGUMENT, i.e. a single head for True -- state_dict keys must agree
+            self.heads = nn.ModuleList(head(encoder_width[j], out_channels) for j in range(int(num_deep_supr)))
 
     def forward_features(self, x):
         """Feature maps, finest first: decoder outputs where there is a decoder level, encoder outputs below."""

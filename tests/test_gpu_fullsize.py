@@ -1,0 +1,141 @@
+"""Parity of the PRODUCTION kernels at the sizes that are benchmarked (BASELINE configs 2 and 3).
+
+The golden cases are small (<= 48 tiles), so every streaming warp of the octant kernels sees at most one tile
+there; here each warp streams dozens of tiles (buffer reuse, mbarrier parity flips, prefetch, dependency
+waits), forward AND backward, against `oracle/nmf_oracle.c` -- the plain-C restatement of
+factorizer/factorizer.py:41-50 + matrix_factorization.py:224-227 that tests/test_oracle.py pins on the
+reference-generated golden vectors.  Tolerance: rtol 1e-4 / atol 1e-5 (north_star, fp32)."""
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+from conftest import assert_close, tol_ratio
+from oracle import c_oracle as CO
+
+pytestmark = pytest.mark.gpu
+
+SHIFTS = [(0, 0, 0), (4, 4, 4)]
+
+
+@pytest.fixture(scope="module")
+def ft():
+    import factorizer_b200
+    return factorizer_b200
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    CO.use_all_cores()
+    return torch.device("cuda:0")
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("shape", [(1, 32, 64, 64, 64), (1, 32, 128, 128, 128), (2, 16, 64, 128, 32), (3, 8, 40, 24, 56)],
+                         ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("k", [None, 2], ids=["full", "k2"])
+def test_core_full_size_vs_c_oracle(ft, dev, shape, k):
+    """BASELINE config 2 (and neighbours with batch > 1 / non-power-of-two grids): y and dx of the fused
+    SWMatricize + ReLU + HALS rank-1 + inverse op through the production path."""
+    from factorizer_b200 import _lib, _ops
+    if k is not None and shape[2] == 128:
+        pytest.skip("truncated unroll is covered at the smaller sizes")
+    rng = np.random.default_rng(abs(hash(shape)) % (1 << 31))
+    x_np = rng.standard_normal(shape, dtype=np.float32)
+    gy_np = rng.standard_normal(shape, dtype=np.float32)
+    sw = ft.SWMatricize((None, *shape[1:]), head_dim=8, patch_size=8)
+    torch.manual_seed(3)
+    nmf = ft.NMF((8, 512), rank=1, num_iters=5, num_grad_steps=k, init="uniform", solver="hals").to(dev)
+    x = torch.from_numpy(x_np).to(dev).requires_grad_(True)
+    y = _ops.SWNMF.apply(x, nmf.init.u0, nmf.init.v0, sw._geom, nmf.solver_spec(), True)
+    assert _lib.lib().fz_last_path() == 2
+    (gx,) = torch.autograd.grad((y * torch.from_numpy(gy_np).to(dev)).sum(), x)
+    torch.cuda.synchronize()
+    v0 = _np(nmf.init.v0)
+    y_ref = CO.swnmf_forward(x_np, v0, 8, (8, 8, 8), SHIFTS)
+    gx_ref = CO.swnmf_backward(x_np, gy_np, v0, 8, (8, 8, 8), SHIFTS, num_grad_steps=k)
+    assert_close(_np(y), y_ref, what="y")
+    assert_close(_np(gx), gx_ref, what="gx")
+    # a second call on the same buffers gives the same bits (no stale scratch state between calls)
+    y2 = _ops.SWNMF.apply(x, nmf.init.u0, nmf.init.v0, sw._geom, nmf.solver_spec(), True)
+    (gx2,) = torch.autograd.grad((y2 * torch.from_numpy(gy_np).to(dev)).sum(), x)
+    assert torch.equal(y2, y) and torch.equal(gx2, gx)
+
+
+class _OracleCore(torch.autograd.Function):
+    """The FactMixer core as the pinned C oracle computes it (fp32, CPU), inside an fp64 torch graph."""
+
+    @staticmethod
+    def forward(ctx, z, v0):
+        z32 = z.detach().to(torch.float32).cpu().numpy()
+        ctx.z32, ctx.v0 = z32, v0
+        return torch.from_numpy(CO.swnmf_forward(z32, v0, 8, (8, 8, 8), SHIFTS)).to(z.device, z.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        g32 = g.to(torch.float32).cpu().numpy()
+        return torch.from_numpy(CO.swnmf_backward(ctx.z32, g32, ctx.v0, 8, (8, 8, 8), SHIFTS)).to(g.device, g.dtype), None
+
+
+def _block_reference(blk, x, gy):
+    """FactorizerBlock.forward (factorizer/factorizer.py:74-77, 34-57) in plain torch fp64 around the C-oracle
+    core; gradients from torch autograd."""
+    sd = {k: v.detach().to(torch.float64) for k, v in blk.state_dict().items()}
+    p = {k: v.clone().requires_grad_(True) for k, v in sd.items() if not k.endswith(("u0", "v0"))}
+    C = x.shape[1]
+    xd = x.detach().to(torch.float64).requires_grad_(True)
+
+    def ln(t, w, b):
+        return torch.nn.functional.layer_norm(t.movedim(1, -1), (C,), w, b, 1e-5).movedim(-1, 1)
+
+    def lin(t, w, b=None):
+        out = torch.einsum("oi,bi...->bo...", w.squeeze(-1), t)
+        return out if b is None else out + b.view(1, -1, *([1] * (t.dim() - 2)))
+
+    v0 = _np(blk.fact.factorize.init.v0).astype(np.float32)
+    h = ln(xd, p["norm1.norm.weight"], p["norm1.norm.bias"])
+    z = lin(h, p["fact.in_proj.linear.weight"])
+    m = _OracleCore.apply(z, v0)
+    x1 = xd + lin(m, p["fact.out_proj.linear.weight"], p["fact.out_proj.linear.bias"])
+    h2 = ln(x1, p["norm2.norm.weight"], p["norm2.norm.bias"])
+    a = torch.nn.functional.gelu(lin(h2, p["mlp.block.0.linear.weight"], p["mlp.block.0.linear.bias"]))
+    out = x1 + lin(a, p["mlp.block.3.linear.weight"], p["mlp.block.3.linear.bias"])
+    names = list(p)
+    grads = torch.autograd.grad((out * gy.to(torch.float64)).sum(), [xd] + [p[k] for k in names])
+    return out.detach(), grads[0], dict(zip(names, grads[1:]))
+
+
+@pytest.mark.parametrize("n", [64, 128])
+def test_block_full_size_vs_oracle(ft, dev, n):
+    """BASELINE config 3: FactorizerBlock(32, n^3, LayerNorm, SWMatricize, HALS rank 1, mlp_ratio 2) through the
+    fused glue kernels + production core: output, input gradient and every parameter gradient."""
+    C = 32
+    torch.manual_seed(11)
+    blk = ft.FactorizerBlock(channels=C, spatial_size=(n, n, n), norm=ft.LayerNorm,
+                             reshape=(ft.SWMatricize, {"head_dim": 8, "patch_size": 8}), act=nn.ReLU,
+                             factorize=ft.NMF, rank=1, num_iters=5, init="uniform", solver="hals", mlp_ratio=2,
+                             dropout=0.0).to(dev)
+    with torch.no_grad():      # non-trivial affine parameters
+        for nm in ("norm1", "norm2"):
+            getattr(blk, nm).norm.weight.add_(0.2 * torch.randn(C, device=dev))
+            getattr(blk, nm).norm.bias.add_(0.2 * torch.randn(C, device=dev))
+    x = torch.randn(1, C, n, n, n, device=dev).requires_grad_(True)
+    gy = torch.randn(1, C, n, n, n, device=dev)
+    assert blk._fused_args(x) is not None
+    y = blk(x)
+    assert type(y.grad_fn).__name__ == "FactorizerBlockFnBackward"
+    params = dict(blk.named_parameters())
+    grads = torch.autograd.grad((y * gy).sum(), [x] + list(params.values()))
+    torch.cuda.synchronize()
+    y_ref, gx_ref, gp_ref = _block_reference(blk, x, gy)
+    assert_close(_np(y), _np(y_ref), what="block y")
+    assert_close(_np(grads[0]), _np(gx_ref), what="block gx")
+    for (k, _), gp in zip(params.items(), grads[1:]):
+        ref = _np(gp_ref[k]).reshape(_np(gp).shape)
+        # a parameter gradient is a sum over n^3 voxels of fp32 products: bound relative to its largest entry
+        scale = max(1.0, float(np.abs(ref).max()))
+        assert tol_ratio(_np(gp) / scale, ref / scale, rtol=1e-4, atol=1e-4) <= 1.0, k
