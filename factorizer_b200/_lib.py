@@ -15,6 +15,7 @@ FZ_MAX_SHIFTS = 8
 FZ_MAX_RANK = 4
 FZ_SOLVER_MU, FZ_SOLVER_HALS = 0, 1
 FZ_OK, FZ_ERR_INVALID, FZ_ERR_UNSUPPORTED, FZ_ERR_CUDA = 0, 1, 2, 3
+FZ_PATH_AUTO, FZ_PATH_GENERIC, FZ_PATH_NO_OCTANT, FZ_PATH_OCTANT_3LAUNCH, FZ_PATH_OCTANT_PIPELINE = 0, 1, 2, 3, 4
 
 
 class FzGeom(ctypes.Structure):
@@ -26,6 +27,7 @@ class FzGeom(ctypes.Structure):
         ("head_dim", c_int32),
         ("num_shifts", c_int32),
         ("shifts", (c_int32 * 3) * FZ_MAX_SHIFTS),
+        ("path", c_int32),
     ]
 
 
@@ -45,8 +47,6 @@ _SIGNATURES = {
     "fz_last_error": (c_char_p, []),
     "fz_last_path": (c_int, []),
     "fz_last_launches": (c_int, []),
-    "fz_set_path": (None, [c_int]),
-    "fz_set_pass_mask": (None, [c_int]),
     "fz_swmat_forward": (c_int, [c_void_p, c_void_p, POINTER(FzGeom), c_void_p]),
     "fz_swmat_inverse": (c_int, [c_void_p, c_void_p, POINTER(FzGeom), c_void_p]),
     "fz_swmat_forward_adjoint": (c_int, [c_void_p, c_void_p, POINTER(FzGeom), c_void_p]),
@@ -138,7 +138,7 @@ def stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def make_geom(batch: int, channels: int, size, patch, head_dim: int, shifts) -> FzGeom:
+def make_geom(batch: int, channels: int, size, patch, head_dim: int, shifts, path: int = 0) -> FzGeom:
     """size/patch/shifts given for the real spatial rank (1..3); padded on the left."""
     n = len(size)
     if not 1 <= n <= 3:
@@ -147,6 +147,7 @@ def make_geom(batch: int, channels: int, size, patch, head_dim: int, shifts) -> 
         raise NotImplementedError(f"factorizer_b200: more than {FZ_MAX_SHIFTS} window sets")
     g = FzGeom()
     g.batch, g.channels, g.head_dim, g.num_shifts = batch, channels, head_dim, len(shifts)
+    g.path = int(path)
     pad = 3 - n
     for k in range(3):
         g.size[k] = 1 if k < pad else int(size[k - pad])

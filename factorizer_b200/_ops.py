@@ -22,6 +22,7 @@ class Geometry:
         self.patch = tuple(int(p) for p in patch)
         self.head_dim = int(head_dim)
         self.shifts = tuple(tuple(int(v) for v in s) for s in shifts)
+        self.path = L.FZ_PATH_AUTO       # fz_geom.path: restrict the kernel family (tests / measurements)
         self.heads = self.channels // self.head_dim
         self.grid = tuple(s // p for s, p in zip(self.size, self.patch))
         self.num_windows = 1
@@ -31,7 +32,7 @@ class Geometry:
             self.num_cols *= p
 
     def c_geom(self, batch: int) -> L.FzGeom:
-        return L.make_geom(batch, self.channels, self.size, self.patch, self.head_dim, self.shifts)
+        return L.make_geom(batch, self.channels, self.size, self.patch, self.head_dim, self.shifts, self.path)
 
     def mat_shape(self, batch: int) -> Tuple[int, int, int, int]:
         return (len(self.shifts) * batch * self.heads, self.num_windows, self.head_dim, self.num_cols)
@@ -84,8 +85,21 @@ def _check_mat(y: torch.Tensor, geom: Geometry, name: str) -> Tuple[torch.Tensor
     return y, y.shape[0] // (S * geom.heads)
 
 
+class LaunchCounter:
+    """Kernel launches issued through this module (every C entry point reports its own count, read here on the calling
+    thread -- autograd runs backward on its own).  bench.py reads it for `gpu_launches`."""
+    _lock = threading.Lock()
+    total = 0
+
+    @classmethod
+    def add(cls, n: int) -> None:
+        with cls._lock:
+            cls.total += n
+
+
 def _call(fn, *args) -> None:
     L.check(fn(*args))
+    LaunchCounter.add(L.lib().fz_last_launches())
 
 
 # ---- standalone matricize ------------------------------------------------------------------------

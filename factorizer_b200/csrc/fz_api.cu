@@ -19,8 +19,6 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
-static volatile int g_forced_path = -1;  // process-wide: autograd runs backward on its own thread
-
 // One window per (sample, head), no roll, and more elements than a CTA can hold: Matricize(grid_size=1), the
 // reference's default FactMixer reshape (factorizer/factorizer.py:17).  The matrix is the contiguous block
 // x[b, h*d:(h+1)*d, :].
@@ -63,6 +61,9 @@ int make_dev_geom(const fz_geom* g, DevGeom* o) {
     for (int s = 0; s < FZ_MAX_SHIFTS; ++s)
         for (int k = 0; k < 3; ++k) o->sh[s][k] = s < g->num_shifts ? g->shifts[s][k] : 0;
     o->mats_per_shift = (long long)o->B * o->heads * o->G;
+    if (g->path < FZ_PATH_AUTO || g->path > FZ_PATH_OCTANT_PIPELINE)
+        return fail(FZ_ERR_INVALID, "fz_geom.path=%d is not one of FZ_PATH_*", g->path);
+    o->path = g->path;
     return FZ_OK;
 }
 
@@ -76,8 +77,6 @@ int fz_version(void) { return FZ_VERSION; }
 const char* fz_last_error(void) { return tls().msg; }
 int fz_last_path(void) { return tls().path; }
 int fz_last_launches(void) { return tls().launches; }
-void fz_set_path(int path) { g_forced_path = path; }
-void fz_set_pass_mask(int mask) { phase_set_pass_mask(mask); }
 
 int fz_nmf_forward(const float* x, const float* u0, const float* v0, float* u, float* v, float* y,
                    int64_t n, int32_t M, int32_t N, const fz_solver* s, void* stream) {
@@ -87,7 +86,7 @@ int fz_nmf_forward(const float* x, const float* u0, const float* v0, float* u, f
     if (int e = check_solver(s, M, N, &K)) return e;
     if (n < 0) return fail(FZ_ERR_INVALID, "n=%lld < 0", (long long)n);
     if (!x || !u0 || !v0) return fail(FZ_ERR_INVALID, "null input buffer");
-    if (g_forced_path != 0 && y && !u && !v && small_supported(M, N, *s)) {
+    if (y && !u && !v && small_supported(M, N, *s)) {
         tls().path = 3;
         return small_direct(x, u0, v0, nullptr, y, n, M, N, *s, K, false, (cudaStream_t)stream);
     }
@@ -107,7 +106,7 @@ int fz_nmf_backward(const float* x, const float* u0, const float* v0, const floa
     if (int e = check_solver(s, M, N, &K)) return e;
     if (n < 0) return fail(FZ_ERR_INVALID, "n=%lld < 0", (long long)n);
     if (!x || !u0 || !v0 || !gx) return fail(FZ_ERR_INVALID, "null buffer");
-    if (g_forced_path != 0 && gy && !gu && !gv && small_supported(M, N, *s)) {
+    if (gy && !gu && !gv && small_supported(M, N, *s)) {
         tls().path = 3;
         return small_direct(x, u0, v0, gy, gx, n, M, N, *s, K, true, (cudaStream_t)stream);
     }
@@ -141,8 +140,12 @@ size_t fz_swnmf_workspace_bytes(const fz_geom* g, const fz_solver* s) {
     if (make_dev_geom(g, &G) || !s) return 0;
     size_t a = fast_workspace_bytes(G, *s);
     if (phase_supported(G, *s, 1)) {
-        const size_t b = phase_workspace_bytes(G, *s);
+        size_t b = phase_workspace_bytes(G, *s);
         if (b > a) a = b;
+        if (pipe_supported(G, *s, 1, 1)) {
+            b = pipe_workspace_bytes(G, *s);
+            if (b > a) a = b;
+        }
     } else if (pairs_supported(G, *s, 1)) {
         const size_t b = pairs_workspace_bytes(G, *s);
         if (b > a) a = b;
@@ -164,21 +167,27 @@ int fz_swnmf_forward(const float* x, const float* u0, const float* v0, float* y,
     if (int e = check_solver(s, G.d, G.P, &K)) return e;
     if (G.B == 0) return FZ_OK;                       // empty batch: tensors carry null data pointers
     if (!x || !u0 || !v0 || !y) return fail(FZ_ERR_INVALID, "null buffer");
-    if ((g_forced_path == -1 || g_forced_path == 2) && phase_supported(G, *s, relu_input)) {
+    const bool octant_ok = G.path == FZ_PATH_AUTO || G.path == FZ_PATH_OCTANT_3LAUNCH || G.path == FZ_PATH_OCTANT_PIPELINE;
+    const bool fast_ok = G.path != FZ_PATH_GENERIC;
+    if (octant_ok && G.path != FZ_PATH_OCTANT_3LAUNCH && pipe_supported(G, *s, relu_input, G.path == FZ_PATH_OCTANT_PIPELINE)) {
+        tls().path = 6;
+        return pipe_forward(x, v0, y, saved, workspace, G, *s, (cudaStream_t)stream);
+    }
+    if (octant_ok && phase_supported(G, *s, relu_input)) {
         tls().path = 2;
         return phase_forward(x, v0, y, saved, workspace, G, *s, (cudaStream_t)stream);
     }
-    if ((g_forced_path == -1 || g_forced_path == 2) && pairs_supported(G, *s, relu_input)) {
+    if (octant_ok && pairs_supported(G, *s, relu_input)) {
         tls().path = 4;
         const int e = pairs_forward(x, v0, y, saved, workspace, G, *s, (cudaStream_t)stream);
         tls().path = 4;
         return e;
     }
-    if (g_forced_path != 0 && fast_supported(G, *s)) {
+    if (fast_ok && fast_supported(G, *s)) {
         tls().path = 1;
         return fast_forward(x, u0, v0, y, saved, workspace, G, *s, relu_input, (cudaStream_t)stream);
     }
-    if (g_forced_path != 0 && small_window_supported(G, *s)) {
+    if (fast_ok && small_window_supported(G, *s)) {
         tls().path = 3;
         return small_window(x, u0, v0, nullptr, y, G, *s, K, relu_input, false, (cudaStream_t)stream);
     }
@@ -205,20 +214,26 @@ int fz_swnmf_backward(const float* x, const float* gy, const float* u0, const fl
     if (int e = check_solver(s, G.d, G.P, &K)) return e;
     if (G.B == 0) return FZ_OK;
     if (!x || !gy || !u0 || !v0 || !gx) return fail(FZ_ERR_INVALID, "null buffer");
-    if ((g_forced_path == -1 || g_forced_path == 2) && phase_supported(G, *s, relu_input)) {
+    const bool octant_ok = G.path == FZ_PATH_AUTO || G.path == FZ_PATH_OCTANT_3LAUNCH || G.path == FZ_PATH_OCTANT_PIPELINE;
+    const bool fast_ok = G.path != FZ_PATH_GENERIC;
+    if (octant_ok && G.path != FZ_PATH_OCTANT_3LAUNCH && pipe_supported(G, *s, relu_input, G.path == FZ_PATH_OCTANT_PIPELINE)) {
+        tls().path = 6;
+        return pipe_backward(x, gy, v0, saved, gx, workspace, G, *s, K, (cudaStream_t)stream);
+    }
+    if (octant_ok && phase_supported(G, *s, relu_input)) {
         tls().path = 2;
         return phase_backward(x, gy, v0, saved, gx, workspace, G, *s, K, (cudaStream_t)stream);
     }
-    if ((g_forced_path == -1 || g_forced_path == 2) && pairs_supported(G, *s, relu_input)) {
+    if (octant_ok && pairs_supported(G, *s, relu_input)) {
         tls().path = 4;
         return pairs_backward(x, gy, v0, saved, gx, workspace, G, *s, K, (cudaStream_t)stream);
     }
-    if (g_forced_path != 0 && fast_supported(G, *s)) {
+    if (fast_ok && fast_supported(G, *s)) {
         tls().path = 1;
         return fast_backward(x, gy, u0, v0, saved, gx, workspace, G, *s, K, relu_input,
                              (cudaStream_t)stream);
     }
-    if (g_forced_path != 0 && small_window_supported(G, *s)) {
+    if (fast_ok && small_window_supported(G, *s)) {
         tls().path = 3;
         return small_window(x, u0, v0, gy, gx, G, *s, K, relu_input, true, (cudaStream_t)stream);
     }

@@ -77,6 +77,7 @@ struct DevGeom {
     int P;                   // columns per matrix: p0*p1*p2 (= N)
     long long vox;           // D*H*W
     long long mats_per_shift;  // B*heads*G
+    int path;                // fz_geom.path (FZ_PATH_*)
 };
 
 int make_dev_geom(const fz_geom* g, DevGeom* out);

@@ -51,12 +51,19 @@ int small_window(const float* x, const float* u0, const float* v0, const float* 
 
 // fz_swnmf_phase.cu: three-pass "octant" formulation for [unshifted, shifted by patch/2], act = ReLU
 bool phase_supported(const DevGeom& G, const fz_solver& s, int relu);
-void phase_set_pass_mask(int mask);
 size_t phase_workspace_bytes(const DevGeom& G, const fz_solver& s);
 int phase_forward(const float* x, const float* v0, float* y, void* saved, void* workspace,
                   const DevGeom& G, const fz_solver& s, cudaStream_t st);
 int phase_backward(const float* x, const float* gy, const float* v0, const void* saved, float* gx,
                    void* workspace, const DevGeom& G, const fz_solver& s, int K, cudaStream_t st);
+
+// fz_swnmf_pipe.cu: the same formulation as ONE persistent, software-pipelined launch per direction (large volumes)
+bool pipe_supported(const DevGeom& G, const fz_solver& s, int relu, int force);
+size_t pipe_workspace_bytes(const DevGeom& G, const fz_solver& s);
+int pipe_forward(const float* x, const float* v0, float* y, void* saved, void* workspace,
+                 const DevGeom& G, const fz_solver& s, cudaStream_t st);
+int pipe_backward(const float* x, const float* gy, const float* v0, const void* saved, float* gx,
+                  void* workspace, const DevGeom& G, const fz_solver& s, int K, cudaStream_t st);
 
 // fz_block_glue_tc.cu: tcgen05 / TMEM version of the out_proj + norm2 + MLP forward kernel (3xTF32)
 bool mixer_mlp_tc_supported(int hidden);

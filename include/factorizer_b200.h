@@ -51,7 +51,20 @@ typedef struct fz_geom {
     int32_t head_dim;                   /* d = rows M of every matrix                          */
     int32_t num_shifts;                 /* S (1 for a plain Matricize)                         */
     int32_t shifts[FZ_MAX_SHIFTS][3];   /* torch.roll shifts per window set; 0 = unshifted     */
+    int32_t path;                       /* FZ_PATH_AUTO (0), or one of FZ_PATH_* to restrict the
+                                           kernel family fz_swnmf_* may pick for this call (tests
+                                           and measurements; a per-call argument, no global state) */
 } fz_geom;
+
+/* fz_geom.path: which kernel families fz_swnmf_forward / _backward may use.  The value is part of the call, so a
+ * forward and its backward (which autograd may run on another thread) agree by construction. */
+enum {
+    FZ_PATH_AUTO = 0,            /* the fastest family that covers the geometry                               */
+    FZ_PATH_GENERIC = 1,         /* one CTA per matrix out of shared memory only                              */
+    FZ_PATH_NO_OCTANT = 2,       /* anything but the octant kernels (window-at-a-time / sub-warp / generic)   */
+    FZ_PATH_OCTANT_3LAUNCH = 3,  /* octant kernels as three launches per direction, never the pipelined one   */
+    FZ_PATH_OCTANT_PIPELINE = 4  /* octant kernels as one persistent launch per direction, whatever the size  */
+};
 
 /* The unrolled solver of MatrixFactorization.decompose
  * (factorizer/factorization/matrix_factorization.py:461-530). */
@@ -203,19 +216,11 @@ int fz_linear_backward(const float* dy, const float* a, const float* gamma, cons
  * 4..32 rows, 8x16, 8x128, 8x256; rank-1 HALS / MU, at most 5 sweeps; also used by fz_nmf_* when only y / dy
  * are involved), 4 = the octant kernels once per pair of window sets (a, a + patch/2) on the volume rolled by a
  * (e.g. shifts [0, 2, 4, 6]), 5 = one grid-wide pass per sweep for a single huge matrix per (sample, head)
- * (Matricize(grid_size=1), rank-1 MU / HALS).  For tests and the benchmark's bookkeeping. */
+ * (Matricize(grid_size=1), rank-1 MU / HALS), 6 = the octant kernels as one persistent, software-pipelined launch per
+ * direction (volumes beyond the L2).  For tests and the benchmark's bookkeeping. */
 int fz_last_path(void);
 /* Number of kernel launches issued by the last fz_* call on this thread. */
 int fz_last_launches(void);
-/* Force a path for fz_swnmf_*: -1 = automatic, 0 = generic only, 1 = never the octant kernels. */
-void fz_set_path(int path);
-
-/* Measurement hook for the octant kernels (path 2): run only the passes whose bit is set (bit 0 = pass 1,
- * per-octant partial sums; bit 1 = pass 2, per-window recursion; bit 2 = pass 3, per-voxel output).
- * With a mask other than 7 the RESULTS ARE NOT VALID; bench.py uses it to time one kernel of a call with
- * CUDA events after a complete call has filled the intermediate buffers.  Default 7. */
-void fz_set_pass_mask(int mask);
-
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,7 @@ from torch import nn
 
 from conftest import assert_close, tol_ratio
 from oracle import c_oracle as CO
+from oracle.block_reference import block_reference
 
 pytestmark = pytest.mark.gpu
 
@@ -38,7 +39,8 @@ def _np(t):
 @pytest.mark.parametrize("shape", [(1, 32, 64, 64, 64), (1, 32, 128, 128, 128), (2, 16, 64, 128, 32), (3, 8, 40, 24, 56)],
                          ids=lambda s: "x".join(map(str, s)))
 @pytest.mark.parametrize("k", [None, 2], ids=["full", "k2"])
-def test_core_full_size_vs_c_oracle(ft, dev, shape, k):
+@pytest.mark.parametrize("scheme", ["pipeline", "three-launch"])
+def test_core_full_size_vs_c_oracle(ft, dev, shape, k, scheme):
     """BASELINE config 2 (and neighbours with batch > 1 / non-power-of-two grids): y and dx of the fused
     SWMatricize + ReLU + HALS rank-1 + inverse op through the production path."""
     from factorizer_b200 import _lib, _ops
@@ -48,11 +50,12 @@ def test_core_full_size_vs_c_oracle(ft, dev, shape, k):
     x_np = rng.standard_normal(shape, dtype=np.float32)
     gy_np = rng.standard_normal(shape, dtype=np.float32)
     sw = ft.SWMatricize((None, *shape[1:]), head_dim=8, patch_size=8)
+    sw._geom.path = _lib.FZ_PATH_OCTANT_PIPELINE if scheme == "pipeline" else _lib.FZ_PATH_OCTANT_3LAUNCH
     torch.manual_seed(3)
     nmf = ft.NMF((8, 512), rank=1, num_iters=5, num_grad_steps=k, init="uniform", solver="hals").to(dev)
     x = torch.from_numpy(x_np).to(dev).requires_grad_(True)
     y = _ops.SWNMF.apply(x, nmf.init.u0, nmf.init.v0, sw._geom, nmf.solver_spec(), True)
-    assert _lib.lib().fz_last_path() == 2
+    assert _lib.lib().fz_last_path() == (6 if scheme == "pipeline" else 2)
     (gx,) = torch.autograd.grad((y * torch.from_numpy(gy_np).to(dev)).sum(), x)
     torch.cuda.synchronize()
     v0 = _np(nmf.init.v0)
@@ -64,49 +67,6 @@ def test_core_full_size_vs_c_oracle(ft, dev, shape, k):
     y2 = _ops.SWNMF.apply(x, nmf.init.u0, nmf.init.v0, sw._geom, nmf.solver_spec(), True)
     (gx2,) = torch.autograd.grad((y2 * torch.from_numpy(gy_np).to(dev)).sum(), x)
     assert torch.equal(y2, y) and torch.equal(gx2, gx)
-
-
-class _OracleCore(torch.autograd.Function):
-    """The FactMixer core as the pinned C oracle computes it (fp32, CPU), inside an fp64 torch graph."""
-
-    @staticmethod
-    def forward(ctx, z, v0):
-        z32 = z.detach().to(torch.float32).cpu().numpy()
-        ctx.z32, ctx.v0 = z32, v0
-        return torch.from_numpy(CO.swnmf_forward(z32, v0, 8, (8, 8, 8), SHIFTS)).to(z.device, z.dtype)
-
-    @staticmethod
-    def backward(ctx, g):
-        g32 = g.to(torch.float32).cpu().numpy()
-        return torch.from_numpy(CO.swnmf_backward(ctx.z32, g32, ctx.v0, 8, (8, 8, 8), SHIFTS)).to(g.device, g.dtype), None
-
-
-def _block_reference(blk, x, gy):
-    """FactorizerBlock.forward (factorizer/factorizer.py:74-77, 34-57) in plain torch fp64 around the C-oracle
-    core; gradients from torch autograd."""
-    sd = {k: v.detach().to(torch.float64) for k, v in blk.state_dict().items()}
-    p = {k: v.clone().requires_grad_(True) for k, v in sd.items() if not k.endswith(("u0", "v0"))}
-    C = x.shape[1]
-    xd = x.detach().to(torch.float64).requires_grad_(True)
-
-    def ln(t, w, b):
-        return torch.nn.functional.layer_norm(t.movedim(1, -1), (C,), w, b, 1e-5).movedim(-1, 1)
-
-    def lin(t, w, b=None):
-        out = torch.einsum("oi,bi...->bo...", w.squeeze(-1), t)
-        return out if b is None else out + b.view(1, -1, *([1] * (t.dim() - 2)))
-
-    v0 = _np(blk.fact.factorize.init.v0).astype(np.float32)
-    h = ln(xd, p["norm1.norm.weight"], p["norm1.norm.bias"])
-    z = lin(h, p["fact.in_proj.linear.weight"])
-    m = _OracleCore.apply(z, v0)
-    x1 = xd + lin(m, p["fact.out_proj.linear.weight"], p["fact.out_proj.linear.bias"])
-    h2 = ln(x1, p["norm2.norm.weight"], p["norm2.norm.bias"])
-    a = torch.nn.functional.gelu(lin(h2, p["mlp.block.0.linear.weight"], p["mlp.block.0.linear.bias"]))
-    out = x1 + lin(a, p["mlp.block.3.linear.weight"], p["mlp.block.3.linear.bias"])
-    names = list(p)
-    grads = torch.autograd.grad((out * gy.to(torch.float64)).sum(), [xd] + [p[k] for k in names])
-    return out.detach(), grads[0], dict(zip(names, grads[1:]))
 
 
 @pytest.mark.parametrize("n", [64, 128])
@@ -131,7 +91,15 @@ def test_block_full_size_vs_oracle(ft, dev, n):
     params = dict(blk.named_parameters())
     grads = torch.autograd.grad((y * gy).sum(), [x] + list(params.values()))
     torch.cuda.synchronize()
-    y_ref, gx_ref, gp_ref = _block_reference(blk, x, gy)
+    # the product's own z, through the same C entry point the block calls
+    from factorizer_b200 import _lib
+    z = torch.empty_like(x)
+    n1 = blk.norm1.norm
+    _lib.check(_lib.lib().fz_ln_linear_forward(x.data_ptr(), n1.weight.data_ptr(), n1.bias.data_ptr(),
+                                               blk.fact.in_proj.linear.weight.data_ptr(), z.data_ptr(), 1, C, n ** 3,
+                                               float(n1.eps), torch.cuda.current_stream().cuda_stream))
+    y_ref, gx_ref, gp_ref, _ = block_reference(blk.state_dict(), x, gy, z,
+                                               lambda got, ref: assert_close(_np(got), _np(ref), what="block z = in_proj(norm1(x))"))
     assert_close(_np(y), _np(y_ref), what="block y")
     assert_close(_np(grads[0]), _np(gx_ref), what="block gx")
     for (k, _), gp in zip(params.items(), grads[1:]):

@@ -122,21 +122,26 @@ def _fused_module(ft, c, g, name, dev):
     return reshape, nmf.to(dev)
 
 
-@pytest.mark.parametrize("path", ["auto", "window", "generic"])
+@pytest.mark.parametrize("path", ["auto", "pipeline", "three-launch", "window", "generic"])
 @pytest.mark.parametrize("name", list(cases.FUSED_CASES))
 def test_fused_core_matches_reference(ft, dev, golden, name, path):
+    """Every kernel family that covers a case, selected per call through fz_geom.path: the automatic choice, the octant
+    kernels as one pipelined launch and as three launches, the window-at-a-time / sub-warp kernels, the generic ones."""
     from factorizer_b200 import _lib, _ops
     c = cases.FUSED_CASES[name]
     g = golden["fused"]
     reshape, nmf = _fused_module(ft, c, g, name, dev)
     x = torch.from_numpy(cases.make_array(name, c["x_shape"], c["dist"])).to(dev).requires_grad_(True)
     gy = torch.from_numpy(cases.make_array(name, c["x_shape"], "randn", tag="gy")).to(dev)
-    _lib.lib().fz_set_path({"auto": -1, "window": 1, "generic": 0}[path])   # auto: octant kernels where they apply
-    try:
-        y = _ops.SWNMF.apply(x, nmf.init.u0, nmf.init.v0, reshape._geom, nmf.solver_spec(), c["relu"])
-        (gx,) = torch.autograd.grad((y * gy).sum(), x)
-    finally:
-        _lib.lib().fz_set_path(-1)
+    reshape._geom.path = {"auto": _lib.FZ_PATH_AUTO, "pipeline": _lib.FZ_PATH_OCTANT_PIPELINE, "three-launch": _lib.FZ_PATH_OCTANT_3LAUNCH,
+                          "window": _lib.FZ_PATH_NO_OCTANT, "generic": _lib.FZ_PATH_GENERIC}[path]
+    y = _ops.SWNMF.apply(x, nmf.init.u0, nmf.init.v0, reshape._geom, nmf.solver_spec(), c["relu"])
+    took = _lib.lib().fz_last_path()
+    (gx,) = torch.autograd.grad((y * gy).sum(), x)
+    if path == "pipeline" and name in ("fused_cfg2_16", "fused_cfg2_24_b2", "fused_k2"):
+        assert took == 6
+    if path == "three-launch" and name in ("fused_cfg2_16", "fused_cfg2_24_b2", "fused_k2"):
+        assert took == 2
     assert_close(_np(y), g[f"{name}/y"], what="y")
     assert_close(_np(gx), g[f"{name}/gx"], what="gx")
 

@@ -166,3 +166,25 @@ def test_oracle_block_matches_reference(golden, name):
         ref = g[f"{name}/gp/{k}"]
         scale = max(1.0, float(np.abs(ref).max()))
         assert_close(v / scale, ref / scale, rtol=1e-4, atol=1e-4, what=f"grad {k}")
+
+
+@pytest.mark.parametrize("name", ["block_c16_16", "block_c32_16"])
+def test_torch_port_matches_golden(golden, name):
+    """oracle/torch_port.py (the CPU baseline bench.py times: the reference's ATen operator sequence restated in plain
+    torch, differentiated by autograd) against the reference's own outputs and gradients for a FactorizerBlock."""
+    import torch
+    from oracle import torch_port as TP
+    c, g = cases.BLOCK_CASES[name], golden["block"]
+    sd = {k.split("/sd/")[1]: torch.from_numpy(g[k]).requires_grad_(True) for k in g.files if k.startswith(name + "/sd/")}
+    xs = (c["batch"], c["channels"], *c["spatial"])
+    x = torch.from_numpy(cases.make_array(name, xs, "randn")).requires_grad_(True)
+    gy = torch.from_numpy(cases.make_array(name, xs, "randn", tag="gy"))
+    y = TP.block_forward(x, sd)
+    names = [k for k in sd if not k.endswith(("u0", "v0"))]
+    grads = torch.autograd.grad((y * gy).sum(), [x] + [sd[k] for k in names])
+    assert_close(y.detach().numpy(), g[f"{name}/y"], what="y")
+    assert_close(grads[0].numpy(), g[f"{name}/gx"], what="gx")
+    for k, gp in zip(names, grads[1:]):
+        ref = g[f"{name}/gp/{k}"]
+        scale = max(1.0, float(np.abs(ref).max()))
+        assert_close(gp.numpy() / scale, ref / scale, rtol=1e-4, atol=1e-4, what=f"grad {k}")
