@@ -642,6 +642,138 @@ __device__ __forceinline__ void bwd_solve_window(const PhaseParams& P, float (*s
     mb[88 + row] = pick8(uT, row);
 }
 
+// The same recursion, ONE LANE PER WINDOW (three-launch scheme): all eight rows of M in registers, the Gram matrix packed,
+// no shuffles; sums and products in the order of the 8-lane form (same bits).
+__device__ __forceinline__ void bwd_solve_lane(const PhaseParams& P, long long gwin, int set, bool active) {
+    const float eps = P.eps;
+    const int T = P.T;
+    const float* rec = P.saved + gwin * P.rec_floats;
+    float G[36], r[8], u[8], unext[8], bcur, bnext = 0.f;
+    {
+        const float4* g4 = reinterpret_cast<const float4*>(rec + P.rec_head);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 a = __ldcg(g4 + 2 * i), b = __ldcg(g4 + 2 * i + 1);
+            const float row[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int j = i; j < 8; ++j) G[tri_index(i, j)] = row[j];
+        }
+    }
+    ld8(rec + P.rec_head + 64, r);
+    ld8(rec + 8 * (T - 1), u);
+    bcur = __ldcg(rec + 8 * T + (T - 1));
+    if (T >= 2) { ld8(rec + 8 * (T - 2), unext); bnext = __ldcg(rec + 8 * T + (T - 2)); }
+    float w[8], e = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = 0.f;
+    {
+        const int local = (int)(gwin - (long long)set * P.tiles);
+        const TileCoord c = tile_coord(P, local);
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            const long long src = rec_slot(P, set ? source_coord_of(P, c, o) : c);
+            const float4* g4 = reinterpret_cast<const float4*>(P.oct + (((size_t)src * 8 + o) * 2 + set) * kBwdOct);
+            const float4 a = __ldcg(g4), b = __ldcg(g4 + 1), cc = __ldcg(g4 + 2);
+            w[0] += a.x; w[1] += a.y; w[2] += a.z; w[3] += a.w; w[4] += b.x; w[5] += b.y; w[6] += b.z; w[7] += b.w;
+            e += cc.x;
+        }
+    }
+    const float rdT = rcp_nr(dot8(u, u) + eps);
+    float M[8][8], mi[8], ab[8], bbar;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        mi[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) M[i][j] = 0.f;
+    }
+    {
+        const float db = -e * rdT;
+        const float rb = rcp_nr(bcur + eps);
+        float bacc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float ub = fmaf(2.f * db, u[j], w[j]);
+            const float pb = (T == 1 && !(u[j] > 0.f)) ? 0.f : ub;
+            ab[j] = pb * rb;
+            bacc = fmaf(pb, u[j], bacc);
+        }
+        bbar = -bacc * rb;
+    }
+    float ruT[8], uT[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { uT[j] = u[j]; ruT[j] = u[j] * rdT; }
+    for (int t = T - 2; t >= T - P.K; --t) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) u[j] = unext[j];
+        bcur = bnext;
+        if (t >= 1) { ld8(rec + 8 * (t - 1), unext); bnext = __ldcg(rec + 8 * T + (t - 1)); }   // one step ahead
+        const float rd = rcp_nr(dot8(u, u) + eps);
+        const float brd = 2.f * bbar * rd, kappa = brd * eps;
+        float z[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[j] = fmaf(brd, u[j], ab[j]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float ur = u[i] * rd, ar = ab[i] * rd;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) M[i][j] = fmaf(ur, z[j], fmaf(ar, u[j], M[i][j]));
+            mi[i] = fmaf(kappa, ur, fmaf(eps, ar, mi[i]));
+        }
+        float gz[8], gu[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float sz = G[tri_index(0, i)] * z[0], su = G[tri_index(0, i)] * u[0];
+#pragma unroll
+            for (int j = 1; j < 8; ++j) {
+                const float gij = G[i <= j ? tri_index(i, j) : tri_index(j, i)];
+                sz = fmaf(gij, z[j], sz);
+                su = fmaf(gij, u[j], su);
+            }
+            gz[i] = sz; gu[i] = su;
+        }
+        const float qv = rd * (dot8(z, gu) + eps * dot8(z, r) + kappa * dot8(u, r) + 512.f * kappa * eps);
+        const float db = -qv * rd;
+        const float rb = rcp_nr(bcur + eps);
+        float bacc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float wj = rd * fmaf(kappa, r[j], gz[j]);
+            const float ub = fmaf(2.f * db, u[j], wj);
+            const float pb = (t == 0 && !(u[j] > 0.f)) ? 0.f : ub;
+            ab[j] = pb * rb;
+            bacc = fmaf(pb, u[j], bacc);
+        }
+        bbar = -bacc * rb;
+    }
+    if (P.K < T) {
+        // truncated unroll: a_L = X v_{L-1} still reads X, v_{L-1} = rd (X^T u_{L-1} + eps 1) is a constant
+#pragma unroll
+        for (int j = 0; j < 8; ++j) u[j] = unext[j];
+        const float rdl = rcp_nr(dot8(u, u) + eps);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float ar = ab[i] * rdl;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) M[i][j] = fmaf(ar, u[j], M[i][j]);
+            mi[i] = fmaf(eps, ar, mi[i]);
+        }
+    }
+    if (!active) return;
+    float* mb = P.mb + gwin * kMbF;
+    float4* m4 = reinterpret_cast<float4*>(mb);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        m4[2 * i] = make_float4(M[i][0], M[i][1], M[i][2], M[i][3]);
+        m4[2 * i + 1] = make_float4(M[i][4], M[i][5], M[i][6], M[i][7]);
+    }
+    m4[16] = make_float4(mi[0], mi[1], mi[2], mi[3]); m4[17] = make_float4(mi[4], mi[5], mi[6], mi[7]);
+    const bool full = P.K >= T;
+    m4[18] = full ? make_float4(ab[0], ab[1], ab[2], ab[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    m4[19] = full ? make_float4(ab[4], ab[5], ab[6], ab[7]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    m4[20] = make_float4(ruT[0], ruT[1], ruT[2], ruT[3]); m4[21] = make_float4(ruT[4], ruT[5], ruT[6], ruT[7]);
+    m4[22] = make_float4(uT[0], uT[1], uT[2], uT[3]); m4[23] = make_float4(uT[4], uT[5], uT[6], uT[7]);
+}
+
 // =====================================================================================================
 // backward pass 3 of one tile (X at `tile`, dY at `tile + 4096`, its nine window records at `mbs`: 0 = unshifted,
 // 1 + o = shifted window of octant o):

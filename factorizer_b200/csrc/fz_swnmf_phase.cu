@@ -12,7 +12,7 @@ namespace {
 constexpr int kW1 = 7;                // warps per CTA, pass 1 forward (2 x 16 KiB each)
 constexpr int kW3 = 6;                // pass 3 forward (2 x 16 KiB each; 7 warps measured slower: 111 vs 97 us)
 constexpr int kWB = 3;                // passes 1 and 3 backward (2 x 32 KiB each)
-constexpr int kSolveThreads = 128;
+constexpr int kSolveThreads = 64;      // backward pass 2: a lane per window, small CTAs so that 64 Ki windows spread over all SMs
 
 // one streaming warp: its tiles are gw, gw + nw, ...; buffers are filled one tile ahead by lane 0
 struct Stream {
@@ -75,8 +75,10 @@ __global__ void __launch_bounds__(kW1 * 32, 1) phase_fwd_gram(const __grid_const
 // =====================================================================================================
 // forward pass 2: per window (either set), 8 lanes: add the 8 octant records, run the T sweeps
 // =====================================================================================================
-__global__ void __launch_bounds__(kSolveThreads) phase_fwd_solve(const __grid_constant__ PhaseParams P) {
-    __shared__ __align__(16) float sums[kSolveThreads / 8][64];               // per window: Gam (36) | r (8) | a1 set 0 | a1 set 1
+__global__ void __launch_bounds__(128) phase_fwd_solve(const __grid_constant__ PhaseParams P) {
+    // 8 lanes per window.  (A lane-per-window variant, 5x fewer instructions, measured SLOWER here: 27 us against 18 us --
+    // its 2 048 warps each walk 8 dependent rounds of record loads; the backward's recursion is long enough to gain.)
+    __shared__ __align__(16) float sums[128 / 8][64];               // per window: Gam (36) | r (8) | a1 set 0 | a1 set 1
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 3;
     long long gidx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     const bool active = gidx < 2LL * P.t_count;     // a group past the end computes window 0 along with its warp, stores nothing
@@ -190,15 +192,13 @@ __global__ void __launch_bounds__(kWB * 32, 1) phase_bwd_reduce(const __grid_con
 // =====================================================================================================
 // backward pass 2: per window, 8 lanes: the 8-vector recursion t = T .. 1 (fz_swnmf_gram.cuh header)
 // =====================================================================================================
-__global__ void __launch_bounds__(kSolveThreads, 5) phase_bwd_solve(const __grid_constant__ PhaseParams P) {
-    __shared__ __align__(16) float stage[kSolveThreads / 8][8][kBwdOct];
-    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 3;
-    long long gidx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+__global__ void __launch_bounds__(kSolveThreads) phase_bwd_solve(const __grid_constant__ PhaseParams P) {
+    long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = gidx < 2LL * P.t_count;
     if (!active) gidx = 0;
     const int set = gidx >= P.t_count ? 1 : 0;
     const long long gwin = (long long)set * P.tiles + P.t_begin + (gidx - (long long)set * P.t_count);
-    bwd_solve_window(P, stage[grp], gwin, set, lane, active);
+    bwd_solve_lane(P, gwin, set, active);
 }
 
 // =====================================================================================================
@@ -316,7 +316,7 @@ int phase_forward(const float* x, const float* v0, float* y, void* saved, void* 
     phase_fwd_gram<<<grid_for(P.t_count, kW1), kW1 * 32, kW1 * 2 * kTileBytes, st>>>(P);
     FZ_LAUNCH_CHECK();
     const long long groups = 2LL * P.t_count;
-    phase_fwd_solve<<<(unsigned)((groups * 8 + kSolveThreads - 1) / kSolveThreads), kSolveThreads, 0, st>>>(P);
+    phase_fwd_solve<<<(unsigned)((groups * 8 + 127) / 128), 128, 0, st>>>(P);
     FZ_LAUNCH_CHECK();
     phase_fwd_apply<<<grid_for(P.t_count, kW3), kW3 * 32, kW3 * 2 * kTileBytes, st>>>(P);
     FZ_LAUNCH_CHECK();
@@ -343,7 +343,7 @@ int phase_backward(const float* x, const float* gy, const float* v0, const void*
     phase_bwd_reduce<<<grid_for(P.t_count, kWB), kWB * 32, kWB * 4 * kTileBytes, st>>>(P);
     FZ_LAUNCH_CHECK();
     const long long groups = 2LL * P.t_count;
-    phase_bwd_solve<<<(unsigned)((groups * 8 + kSolveThreads - 1) / kSolveThreads), kSolveThreads, 0, st>>>(P);
+    phase_bwd_solve<<<(unsigned)((groups + kSolveThreads - 1) / kSolveThreads), kSolveThreads, 0, st>>>(P);
     FZ_LAUNCH_CHECK();
     phase_bwd_apply<<<grid_for(P.t_count, kWB), kWB * 32, kWB * 4 * kTileBytes, st>>>(P);
     FZ_LAUNCH_CHECK();
