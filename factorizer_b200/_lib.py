@@ -15,6 +15,7 @@ FZ_MAX_SHIFTS = 8
 FZ_MAX_RANK = 4
 FZ_SOLVER_MU, FZ_SOLVER_HALS = 0, 1
 FZ_OK, FZ_ERR_INVALID, FZ_ERR_UNSUPPORTED, FZ_ERR_CUDA = 0, 1, 2, 3
+FZ_DTYPE_F32, FZ_DTYPE_BF16 = 0, 1
 FZ_PATH_AUTO, FZ_PATH_GENERIC, FZ_PATH_NO_OCTANT, FZ_PATH_OCTANT_3LAUNCH, FZ_PATH_OCTANT_PIPELINE = 0, 1, 2, 3, 4
 
 
@@ -27,6 +28,7 @@ class FzGeom(ctypes.Structure):
         ("head_dim", c_int32),
         ("num_shifts", c_int32),
         ("shifts", (c_int32 * 3) * FZ_MAX_SHIFTS),
+        ("dtype", c_int32),
         ("path", c_int32),
     ]
 
@@ -116,14 +118,14 @@ def check(code: int) -> None:
     raise RuntimeError(f"factorizer_b200: {msg}")
 
 
-def require_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+def require_cuda_f32(t: torch.Tensor, name: str, allow_bf16: bool = False) -> torch.Tensor:
     if not isinstance(t, torch.Tensor):
         raise TypeError(f"{name} must be a torch.Tensor")
     if not t.is_cuda:
         raise RuntimeError(
             f"factorizer_b200: `{name}` is on {t.device}; this package has CUDA kernels only "
             "(no CPU fallback) - move the module and its inputs to a CUDA device")
-    if t.dtype != torch.float32:
+    if t.dtype != torch.float32 and not (allow_bf16 and t.dtype == torch.bfloat16):
         raise NotImplementedError(
             f"factorizer_b200: `{name}` has dtype {t.dtype}; only float32 is implemented "
             "(the reference runs this path in fp32, amp: false)")
@@ -138,7 +140,7 @@ def stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def make_geom(batch: int, channels: int, size, patch, head_dim: int, shifts, path: int = 0) -> FzGeom:
+def make_geom(batch: int, channels: int, size, patch, head_dim: int, shifts, path: int = 0, dtype: int = 0) -> FzGeom:
     """size/patch/shifts given for the real spatial rank (1..3); padded on the left."""
     n = len(size)
     if not 1 <= n <= 3:
@@ -148,6 +150,7 @@ def make_geom(batch: int, channels: int, size, patch, head_dim: int, shifts, pat
     g = FzGeom()
     g.batch, g.channels, g.head_dim, g.num_shifts = batch, channels, head_dim, len(shifts)
     g.path = int(path)
+    g.dtype = int(dtype)
     pad = 3 - n
     for k in range(3):
         g.size[k] = 1 if k < pad else int(size[k - pad])

@@ -31,8 +31,9 @@ class Geometry:
             self.num_windows *= g
             self.num_cols *= p
 
-    def c_geom(self, batch: int) -> L.FzGeom:
-        return L.make_geom(batch, self.channels, self.size, self.patch, self.head_dim, self.shifts, self.path)
+    def c_geom(self, batch: int, dtype: torch.dtype = torch.float32) -> L.FzGeom:
+        return L.make_geom(batch, self.channels, self.size, self.patch, self.head_dim, self.shifts, self.path,
+                           L.FZ_DTYPE_BF16 if dtype == torch.bfloat16 else L.FZ_DTYPE_F32)
 
     def mat_shape(self, batch: int) -> Tuple[int, int, int, int]:
         return (len(self.shifts) * batch * self.heads, self.num_windows, self.head_dim, self.num_cols)
@@ -67,8 +68,8 @@ class _GradModeFunction(torch.autograd.Function):
         return bool(getattr(_GradModeFunction._caller, "grad", True)) and any(flags)
 
 
-def _check_vol(x: torch.Tensor, geom: Geometry, name: str) -> torch.Tensor:
-    x = L.require_cuda_f32(x, name)
+def _check_vol(x: torch.Tensor, geom: Geometry, name: str, allow_bf16: bool = False) -> torch.Tensor:
+    x = L.require_cuda_f32(x, name, allow_bf16)
     if tuple(x.shape[1:]) != (geom.channels, *geom.size):
         raise ValueError(f"{name}: expected (B, {geom.channels}, {', '.join(map(str, geom.size))}), "
                          f"got {tuple(x.shape)}")
@@ -285,7 +286,7 @@ def _workspace(device, nbytes: int) -> Optional[torch.Tensor]:
 def _swnmf_forward(x, u0, v0, geom: Geometry, spec: SolverSpec, relu: bool, need_grad: bool):
     """One launch sequence of the fused core; returns (y, saved-for-backward buffer or None)."""
     lib = L.lib()
-    g, s = geom.c_geom(x.shape[0]), spec.c_solver()
+    g, s = geom.c_geom(x.shape[0], x.dtype), spec.c_solver()
     y = torch.empty_like(x)
     saved = None
     with torch.cuda.device(x.device):
@@ -300,7 +301,7 @@ def _swnmf_forward(x, u0, v0, geom: Geometry, spec: SolverSpec, relu: bool, need
 
 def _swnmf_backward(x, gy, u0, v0, saved, geom: Geometry, spec: SolverSpec, relu: bool):
     lib = L.lib()
-    g, s = geom.c_geom(x.shape[0]), spec.c_solver()
+    g, s = geom.c_geom(x.shape[0], x.dtype), spec.c_solver()
     gx = torch.empty_like(x)
     with torch.cuda.device(x.device):
         ws = _workspace(x.device, lib.fz_swnmf_workspace_bytes(ctypes.byref(g), ctypes.byref(s)))
@@ -315,9 +316,11 @@ class SWNMF(_GradModeFunction):
 
     @staticmethod
     def forward(ctx, x, u0, v0, geom: Geometry, spec: SolverSpec, relu: bool):
-        x = _check_vol(x, geom, "x")
-        u0 = L.require_cuda_f32(u0, "u0")
-        v0 = L.require_cuda_f32(v0, "v0")
+        # bf16 volumes (an extension: the reference runs fp32) are read and written as bf16 by the octant kernels; u0, v0,
+        # the saved records and all arithmetic stay fp32
+        x = _check_vol(x, geom, "x", allow_bf16=True)
+        u0 = L.require_cuda_f32(u0.float(), "u0")
+        v0 = L.require_cuda_f32(v0.float(), "v0")
         y, saved = _swnmf_forward(x, u0, v0, geom, spec, relu, _GradModeFunction.wants_grad(ctx, 1))
         ctx.save_for_backward(x, u0, v0, saved)
         ctx.geom, ctx.spec, ctx.relu = geom, spec, relu
@@ -327,7 +330,7 @@ class SWNMF(_GradModeFunction):
     @once_differentiable
     def backward(ctx, gy):
         x, u0, v0, saved = ctx.saved_tensors
-        gy = _check_vol(gy, ctx.geom, "grad")
+        gy = _check_vol(gy.to(x.dtype), ctx.geom, "grad", allow_bf16=True)
         gx = _swnmf_backward(x, gy, u0, v0, saved, ctx.geom, ctx.spec, ctx.relu)
         return gx, None, None, None, None, None
 

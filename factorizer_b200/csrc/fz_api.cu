@@ -64,6 +64,9 @@ int make_dev_geom(const fz_geom* g, DevGeom* o) {
     if (g->path < FZ_PATH_AUTO || g->path > FZ_PATH_OCTANT_PIPELINE)
         return fail(FZ_ERR_INVALID, "fz_geom.path=%d is not one of FZ_PATH_*", g->path);
     o->path = g->path;
+    if (g->dtype != FZ_DTYPE_F32 && g->dtype != FZ_DTYPE_BF16)
+        return fail(FZ_ERR_INVALID, "fz_geom.dtype=%d is not one of FZ_DTYPE_*", g->dtype);
+    o->dtype = g->dtype;
     return FZ_OK;
 }
 
@@ -177,6 +180,9 @@ int fz_swnmf_forward(const float* x, const float* u0, const float* v0, float* y,
         tls().path = 2;
         return phase_forward(x, v0, y, saved, workspace, G, *s, (cudaStream_t)stream);
     }
+    if (G.dtype != FZ_DTYPE_F32)
+        return fail(FZ_ERR_UNSUPPORTED, "bf16 volumes are served by the octant kernels only (head_dim 8, patch 8x8x8, shifts "
+                    "[0, 4], ReLU, rank-1 HALS, an even number of patches along W)");
     if (octant_ok && pairs_supported(G, *s, relu_input)) {
         tls().path = 4;
         const int e = pairs_forward(x, v0, y, saved, workspace, G, *s, (cudaStream_t)stream);
@@ -224,6 +230,9 @@ int fz_swnmf_backward(const float* x, const float* gy, const float* u0, const fl
         tls().path = 2;
         return phase_backward(x, gy, v0, saved, gx, workspace, G, *s, K, (cudaStream_t)stream);
     }
+    if (G.dtype != FZ_DTYPE_F32)
+        return fail(FZ_ERR_UNSUPPORTED, "bf16 volumes are served by the octant kernels only (head_dim 8, patch 8x8x8, shifts "
+                    "[0, 4], ReLU, rank-1 HALS, an even number of patches along W)");
     if (octant_ok && pairs_supported(G, *s, relu_input)) {
         tls().path = 4;
         return pairs_backward(x, gy, v0, saved, gx, workspace, G, *s, K, (cudaStream_t)stream);

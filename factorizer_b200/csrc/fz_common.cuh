@@ -78,6 +78,7 @@ struct DevGeom {
     long long vox;           // D*H*W
     long long mats_per_shift;  // B*heads*G
     int path;                // fz_geom.path (FZ_PATH_*)
+    int dtype;               // fz_geom.dtype (FZ_DTYPE_*): element type of the volumes
 };
 
 int make_dev_geom(const fz_geom* g, DevGeom* out);

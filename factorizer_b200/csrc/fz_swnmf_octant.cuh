@@ -21,6 +21,7 @@
 // There are no wrapped or misaligned boxes and no partial-sum round trip through the volume.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <type_traits>
 #include <stdlib.h>
 #include <string.h>
@@ -178,6 +179,38 @@ __device__ __forceinline__ int chunk_f4_shifted(int lane, int j) {
     return 16 * (4 * (1 - o0) + j) + 2 * (4 * (1 - o1) + t) + (1 - o2);
 }
 
+// How a streaming warp sees one tile in shared memory.  fp32: an (8,8,8,8) box, rows of 32 bytes.  bf16 activations: two
+// tiles side by side along W travel as one (16,8,8,8) box -- again rows of 32 bytes, the row granularity TMA and the L2
+// sectors like -- and a tile is one 16-byte column of that box.  ld(i, lane, j): the lane's chunk j of channel i as floats.
+struct TileF32 {
+    const float* p;
+    __device__ __forceinline__ float4 ld(int i, int lane, int j) const {
+        return reinterpret_cast<const float4*>(p)[i * 128 + chunk_f4(lane, j)];
+    }
+};
+struct TileBf16 {
+    const unsigned char* p;       // pair buffer + 16 * (which tile of the pair)
+    __device__ __forceinline__ float4 ld(int i, int lane, int j) const {
+        const int o0 = lane >> 4, o1 = (lane >> 3) & 1, o2 = (lane >> 2) & 1, t = lane & 3;
+        const uint2 r = *reinterpret_cast<const uint2*>(p + (i * 64 + (4 * o0 + j) * 8 + 4 * o1 + t) * 32 + o2 * 8);
+        return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u),
+                           __uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u));
+    }
+};
+// four neighbouring voxels of the output
+__device__ __forceinline__ void store_out(float* p, float4 v, bool streaming) {
+    if (streaming) __stcs(reinterpret_cast<float4*>(p), v);
+    else *reinterpret_cast<float4*>(p) = v;
+}
+__device__ __forceinline__ void store_out(__nv_bfloat16* p, float4 v, bool streaming) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<const uint32_t*>(&a);
+    r.y = *reinterpret_cast<const uint32_t*>(&b);
+    if (streaming) __stcs(reinterpret_cast<uint2*>(p), r);
+    else *reinterpret_cast<uint2*>(p) = r;
+}
+
 template <int N, int CAP>
 __device__ __forceinline__ void halve_vals(float (&v)[CAP], bool hi, int bit) {
     constexpr int m = (N + 1) / 2;
@@ -231,16 +264,17 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 // forward pass 1 of one tile: per-octant Gram partials (Gam, r, a_1 for both window sets) -> rec_out (480 floats)
 // The tile buffer itself is the scratch area for the record once X sits in registers.
 // =====================================================================================================
-__device__ __forceinline__ void fwd_tile_gram(float* tile, const float* v0s, const int (&dst)[15], int lane, float* rec_out) {
-    float* scratch = tile;
+// scratch: where the record is assembled before it leaves, 16-byte pieces SPITCH float4 apart (1: a dense 1 920-byte area;
+// 2: the 16-byte column of a bf16 pair buffer whose tile already sits in registers)
+template <typename Tile, int SPITCH = 1>
+__device__ __forceinline__ void fwd_tile_gram(const Tile tile, float* scratch, const float* v0s, const int (&dst)[15], int lane, float* rec_out) {
     f2 x[8][8];
     {
-        const float4* t4 = reinterpret_cast<const float4*>(tile);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float4 a = t4[i * 128 + chunk_f4(lane, j)];
+                const float4 a = tile.ld(i, lane, j);
                 x[i][2 * j] = make_float2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f));
                 x[i][2 * j + 1] = make_float2(fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
             }
@@ -285,14 +319,18 @@ __device__ __forceinline__ void fwd_tile_gram(float* tile, const float* v0s, con
     halve_vals<30, kOctFloats>(pv, lane & 2, 2);
     __syncwarp();
 #pragma unroll
-    for (int s = 0; s < 15; ++s) scratch[dst[s]] = pv[s];
+    for (int s = 0; s < 15; ++s) scratch[(dst[s] >> 2) * (4 * SPITCH) + (dst[s] & 3)] = pv[s];
     __syncwarp();
     {
         const float4* s4 = reinterpret_cast<const float4*>(scratch);
         float4* o4 = reinterpret_cast<float4*>(rec_out);
-        for (int q = lane; q < kTileRec / 4; q += 32) o4[q] = s4[q];
+        for (int q = lane; q < kTileRec / 4; q += 32) o4[q] = s4[q * SPITCH];
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer goes back to TMA
+}
+// fp32 tile: the tile buffer itself is the scratch area
+__device__ __forceinline__ void fwd_tile_gram(float* tile, const float* v0s, const int (&dst)[15], int lane, float* rec_out) {
+    fwd_tile_gram<TileF32, 1>(TileF32{tile}, tile, v0s, dst, lane, rec_out);
 }
 
 // =====================================================================================================
@@ -399,24 +437,18 @@ __device__ __forceinline__ Fac load_fac(const float* fac, long long wid) {
     return f;
 }
 
-__device__ __forceinline__ void store_out(float* p, float4 v, bool streaming) {
-    if (streaming) __stcs(reinterpret_cast<float4*>(p), v);
-    else *reinterpret_cast<float4*>(p) = v;
-}
-
-template <bool UNROLL, bool STREAM = false>
-__device__ __forceinline__ void fwd_tile_apply(const PhaseParams& P, const float* tile, const Fac& f0, const Fac& f1,
-                                               const TileCoord& c, int lane) {
+template <bool UNROLL, bool STREAM, typename Tile, typename OutT>
+__device__ __forceinline__ void fwd_tile_apply_t(const PhaseParams& P, const Tile tile, const Fac& f0, const Fac& f1,
+                                                 const TileCoord& c, int lane) {
     const float eps = P.eps;
-    const float4* t4 = reinterpret_cast<const float4*>(tile);
-    float* base = P.out + ((long long)c.b * P.C + c.h * 8) * P.vox;
+    OutT* base = reinterpret_cast<OutT*>(P.out) + ((long long)c.b * P.C + c.h * 8) * P.vox;
     const f2 r0 = dup(f0.rd), e0 = dup(eps * f0.rd), r1 = dup(f1.rd), e1 = dup(eps * f1.rd);
 #pragma unroll(UNROLL ? 4 : 1)
     for (int j = 0; j < 4; ++j) {
         f2 xa[8], xb[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float4 a = t4[i * 128 + chunk_f4(lane, j)];
+            const float4 a = tile.ld(i, lane, j);
             xa[i] = make_float2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f));
             xb[i] = make_float2(fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
         }
@@ -436,7 +468,7 @@ __device__ __forceinline__ void fwd_tile_apply(const PhaseParams& P, const float
         d1b = mul2(make_float2(fmaxf(d1b.x, 0.f), fmaxf(d1b.y, 0.f)), half);
         // voxel offset of the chunk: q0 = 4 o0 + j, q1 = 4 o1 + t, q2 = 4 o2
         const int q0 = 4 * (lane >> 4) + j, q1 = 4 * ((lane >> 3) & 1) + (lane & 3), q2 = 4 * ((lane >> 2) & 1);
-        float* dstp = base + ((long long)(c.t0 * 8 + q0) * P.n1 + (c.t1 * 8 + q1)) * P.n2 + c.t2 * 8 + q2;
+        OutT* dstp = base + ((long long)(c.t0 * 8 + q0) * P.n1 + (c.t1 * 8 + q1)) * P.n2 + c.t2 * 8 + q2;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const f2 ya = fma2(dup(f1.u[i]), d1a, mul2(dup(f0.u[i]), d0a));
@@ -444,6 +476,12 @@ __device__ __forceinline__ void fwd_tile_apply(const PhaseParams& P, const float
             store_out(dstp + (long long)i * P.vox, make_float4(ya.x, ya.y, yb.x, yb.y), STREAM);
         }
     }
+}
+
+template <bool UNROLL, bool STREAM = false>
+__device__ __forceinline__ void fwd_tile_apply(const PhaseParams& P, const float* tile, const Fac& f0, const Fac& f1,
+                                               const TileCoord& c, int lane) {
+    fwd_tile_apply_t<UNROLL, STREAM, TileF32, float>(P, TileF32{tile}, f0, f1, c, lane);
 }
 
 // =====================================================================================================
@@ -461,12 +499,11 @@ __device__ __forceinline__ UT load_ut(const PhaseParams& P, long long wid) {
     return f;
 }
 
-__device__ __forceinline__ void bwd_tile_reduce(const PhaseParams& P, const float* tile, const UT& f0, const UT& f1, int lane,
-                                                float* rec_out) {
+template <typename Tile>
+__device__ __forceinline__ void bwd_tile_reduce_t(const PhaseParams& P, const Tile xt, const Tile gt, const UT& f0, const UT& f1, int lane,
+                                                  float* rec_out) {
     const float eps = P.eps;
     const int oct = lane >> 2;
-    const float4* x4 = reinterpret_cast<const float4*>(tile);
-    const float4* g4 = x4 + 1024;
     f2 w0[8], w1[8], e0 = make_float2(0.f, 0.f), e1 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) { w0[i] = make_float2(0.f, 0.f); w1[i] = make_float2(0.f, 0.f); }
@@ -476,7 +513,7 @@ __device__ __forceinline__ void bwd_tile_reduce(const PhaseParams& P, const floa
         f2 xa[8], xb[8], ga[8], gb[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float4 a = x4[i * 128 + chunk_f4(lane, j)], g = g4[i * 128 + chunk_f4(lane, j)];
+            const float4 a = xt.ld(i, lane, j), g = gt.ld(i, lane, j);
             xa[i] = make_float2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f));
             xb[i] = make_float2(fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
             ga[i] = mul2(make_float2(g.x, g.y), half);       // G = dY / S
@@ -524,6 +561,11 @@ __device__ __forceinline__ void bwd_tile_reduce(const PhaseParams& P, const floa
         o4[3] = make_float4(r1[0], r1[1], r1[2], r1[3]); o4[4] = make_float4(r1[4], r1[5], r1[6], r1[7]);
         o4[5] = make_float4(r1[8], 0.f, 0.f, 0.f);
     }
+}
+
+__device__ __forceinline__ void bwd_tile_reduce(const PhaseParams& P, const float* tile, const UT& f0, const UT& f1, int lane,
+                                                float* rec_out) {
+    bwd_tile_reduce_t(P, TileF32{tile}, TileF32{tile + 4096}, f0, f1, lane, rec_out);
 }
 
 // =====================================================================================================
@@ -789,15 +831,13 @@ __device__ __forceinline__ void bwd_fetch_records(const PhaseParams& P, float* m
     }
 }
 
-template <bool STREAM = false>
-__device__ __forceinline__ void bwd_tile_apply(const PhaseParams& P, const float* tile, const float* mbs, const float* v0s,
-                                               const TileCoord& c, int lane) {
+template <bool STREAM, typename Tile, typename OutT>
+__device__ __forceinline__ void bwd_tile_apply_t(const PhaseParams& P, const Tile xt, const Tile gt, const float* mbs, const float* v0s,
+                                                 const TileCoord& c, int lane) {
     const int oct = lane >> 2;
-    const float4* x4 = reinterpret_cast<const float4*>(tile);
-    const float4* g4 = x4 + 1024;
     const float* mb0 = mbs;
     const float* mb1 = mb0 + (1 + oct) * kMbF;
-    float* base = P.out + ((long long)c.b * P.C + c.h * 8) * P.vox;
+    OutT* base = reinterpret_cast<OutT*>(P.out) + ((long long)c.b * P.C + c.h * 8) * P.vox;
     const f2 half = dup(0.5f);
 #pragma unroll 1
     for (int j = 0; j < 4; ++j) {
@@ -813,7 +853,7 @@ __device__ __forceinline__ void bwd_tile_apply(const PhaseParams& P, const float
             h0a = h0b = h1a = h1b = make_float2(0.f, 0.f);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float4 a = x4[i * 128 + chunk_f4(lane, j)], g = g4[i * 128 + chunk_f4(lane, j)];
+                const float4 a = xt.ld(i, lane, j), g = gt.ld(i, lane, j);
                 xa[i] = make_float2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f));
                 xb[i] = make_float2(fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
                 const f2 ga = mul2(make_float2(g.x, g.y), half), gb = mul2(make_float2(g.z, g.w), half);
@@ -827,7 +867,7 @@ __device__ __forceinline__ void bwd_tile_apply(const PhaseParams& P, const float
         const f2 v0a = make_float2(va4.x, va4.y), v0b = make_float2(va4.z, va4.w);
         const f2 v1a = make_float2(vb4.x, vb4.y), v1b = make_float2(vb4.z, vb4.w);
         const int q0 = 4 * (lane >> 4) + j, q1 = 4 * ((lane >> 3) & 1) + (lane & 3), q2 = 4 * ((lane >> 2) & 1);
-        float* dstp = base + ((long long)(c.t0 * 8 + q0) * P.n1 + (c.t1 * 8 + q1)) * P.n2 + c.t2 * 8 + q2;
+        OutT* dstp = base + ((long long)(c.t0 * 8 + q0) * P.n1 + (c.t1 * 8 + q1)) * P.n2 + c.t2 * 8 + q2;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             // row i of both windows' M, and their m, abar_1, rd_T u_T entries
@@ -854,6 +894,12 @@ __device__ __forceinline__ void bwd_tile_apply(const PhaseParams& P, const float
     }
 }
 
+template <bool STREAM = false>
+__device__ __forceinline__ void bwd_tile_apply(const PhaseParams& P, const float* tile, const float* mbs, const float* v0s,
+                                               const TileCoord& c, int lane) {
+    bwd_tile_apply_t<STREAM, TileF32, float>(P, TileF32{tile}, TileF32{tile + 4096}, mbs, v0s, c, lane);
+}
+
 // ---- host helpers shared by both launch schemes ---------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -869,16 +915,19 @@ inline EncodeTiledFn encode_fn() {
     }
     return fn;
 }
+// box (8,8,8,8,1) of fp32, or -- bf16 activations -- (16,8,8,8,1) of bf16: two tiles side by side along W
 inline int make_tile_map(CUtensorMap* m, const void* ptr, const DevGeom& G) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return fail(FZ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     if (reinterpret_cast<uintptr_t>(ptr) & 15) return fail(FZ_ERR_INVALID, "volume pointer %p is not 16-byte aligned", ptr);
     cuuint64_t dims[5] = {(cuuint64_t)G.n[2], (cuuint64_t)G.n[1], (cuuint64_t)G.n[0], (cuuint64_t)G.C, (cuuint64_t)G.B};
-    cuuint64_t strides[4] = {(cuuint64_t)G.n[2] * 4, (cuuint64_t)G.n[2] * G.n[1] * 4, (cuuint64_t)G.vox * 4,
-                             (cuuint64_t)G.vox * G.C * 4};
-    cuuint32_t box[5] = {8, 8, 8, 8, 1};
+    const cuuint64_t e = G.dtype == FZ_DTYPE_BF16 ? 2 : 4;
+    cuuint64_t strides[4] = {(cuuint64_t)G.n[2] * e, (cuuint64_t)G.n[2] * G.n[1] * e, (cuuint64_t)G.vox * e,
+                             (cuuint64_t)G.vox * G.C * e};
+    cuuint32_t box[5] = {G.dtype == FZ_DTYPE_BF16 ? 16u : 8u, 8, 8, 8, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(ptr), dims, strides, box, es,
+    CUresult r = enc(m, G.dtype == FZ_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5,
+                     const_cast<void*>(ptr), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(FZ_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);

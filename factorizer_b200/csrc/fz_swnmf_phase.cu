@@ -25,9 +25,22 @@ struct Stream {
     }
 };
 
+// With bf16 activations (BF16 = true) a streaming warp's unit of work is a PAIR of tiles side by side along W, fetched as
+// one (16,8,8,8) box of bf16 = the same 16 KiB and the same 32-byte rows as one fp32 tile; the pair is then worked on
+// as two tiles, and whatever is prefetched for "the next tile" (window factors) is prefetched per tile of the pair.
+// Stream::tile(k) counts units: tiles (fp32) or pairs (bf16); a pair is tiles 2u and 2u + 1 (t2 is the fastest index).
+template <bool BF16> struct TileOf { typedef TileF32 type; typedef float out_t; };
+template <> struct TileOf<true> { typedef TileBf16 type; typedef __nv_bfloat16 out_t; };
+template <bool BF16>
+__device__ __forceinline__ typename TileOf<BF16>::type tile_at(const float* buf, int half) {
+    if constexpr (BF16) return TileBf16{reinterpret_cast<const unsigned char*>(buf) + 16 * half};
+    else return TileF32{buf};
+}
+
 // =====================================================================================================
 // forward pass 1: per-octant Gram partials of every unshifted tile
 // =====================================================================================================
+template <bool BF16>
 __global__ void __launch_bounds__(kW1 * 32, 1) phase_fwd_gram(const __grid_constant__ PhaseParams P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(16) float v0s[512];
@@ -49,13 +62,15 @@ __global__ void __launch_bounds__(kW1 * 32, 1) phase_fwd_gram(const __grid_const
         sq = warp_sum_f(sq);
         if (lane == 0) *P.b1 = sq;
     }
-    Stream S; S.gw = blockIdx.x * kW1 + warp; S.nw = gridDim.x * kW1; S.lane = lane; S.begin = P.t_begin; S.count = P.t_count; S.reverse = 0;
+    constexpr int kPer = BF16 ? 2 : 1;
+    const int units = P.t_count / kPer;
+    Stream S; S.gw = blockIdx.x * kW1 + warp; S.nw = gridDim.x * kW1; S.lane = lane; S.begin = P.t_begin / kPer; S.count = units; S.reverse = 0;
     int dst[15];
     gram_destinations(lane, dst);
     auto issue = [&](int k) {
-        const int tid = S.tile(k);
-        if (tid < P.tiles && lane == 0) {
-            const TileCoord c = tile_coord(P, tid);
+        const int u = S.tile(k);
+        if (u < P.tiles && lane == 0) {
+            const TileCoord c = tile_coord(P, u * kPer);
             mbar_arrive_expect_tx(&bars[warp][k & 1], kTileBytes);
             tma_load_tile(buf + (k & 1) * 4096, &P.tm_x, &bars[warp][k & 1], c.t2 * 8, c.t1 * 8, c.t0 * 8, c.h * 8, c.b);
         }
@@ -65,10 +80,21 @@ __global__ void __launch_bounds__(kW1 * 32, 1) phase_fwd_gram(const __grid_const
     for (int k = 0; S.tile(k) < P.tiles; ++k) {
         __syncwarp();            // everyone is done with the buffer that is refilled now
         issue(k + 1);
-        const int tid = S.tile(k), st = k & 1;
+        const int u = S.tile(k), st = k & 1;
         mbar_wait(&bars[warp][st], parity[st]);
         parity[st] ^= 1;
-        fwd_tile_gram(buf + st * 4096, v0s, dst, lane, P.oct + (size_t)tid * kTileRec);
+        if constexpr (BF16) {
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                // the record is assembled in the pair buffer's first 16-byte column: tile 0 of the pair is in registers
+                // by then (half 0) or long consumed (half 1)
+                fwd_tile_gram<TileBf16, 2>(tile_at<true>(buf + st * 4096, half), buf + st * 4096, v0s, dst, lane,
+                                           P.oct + (size_t)(2 * u + half) * kTileRec);
+                __syncwarp();
+            }
+        } else {
+            fwd_tile_gram(buf + st * 4096, v0s, dst, lane, P.oct + (size_t)u * kTileRec);
+        }
     }
 }
 
@@ -91,6 +117,7 @@ __global__ void __launch_bounds__(128) phase_fwd_solve(const __grid_constant__ P
 // =====================================================================================================
 // forward pass 3: y = 1/2 (u_0 v_0^T + u_1 v_1^T) voxel by voxel, v_s = relu(rd_s (X^T u_s + eps))
 // =====================================================================================================
+template <bool BF16>
 __global__ void __launch_bounds__(kW3 * 32, 1) phase_fwd_apply(const __grid_constant__ PhaseParams P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ uint64_t bars[kW3][2];
@@ -102,19 +129,25 @@ __global__ void __launch_bounds__(kW3 * 32, 1) phase_fwd_apply(const __grid_cons
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    Stream S; S.gw = blockIdx.x * kW3 + warp; S.nw = gridDim.x * kW3; S.lane = lane; S.begin = P.t_begin; S.count = P.t_count; S.reverse = P.reverse;
+    constexpr int kPer = BF16 ? 2 : 1;
+    Stream S; S.gw = blockIdx.x * kW3 + warp; S.nw = gridDim.x * kW3; S.lane = lane; S.begin = P.t_begin / kPer; S.count = P.t_count / kPer; S.reverse = P.reverse;
     const int oct = lane >> 2;
 
     auto issue = [&](int k) {
-        const int tid = S.tile(k);
-        if (tid < P.tiles && lane == 0) {
-            const TileCoord c = tile_coord(P, tid);
+        const int u = S.tile(k);
+        if (u < P.tiles && lane == 0) {
+            const TileCoord c = tile_coord(P, u * kPer);
             mbar_arrive_expect_tx(&bars[warp][k & 1], kTileBytes);
             tma_load_tile(buf + (k & 1) * 4096, &P.tm_x, &bars[warp][k & 1], c.t2 * 8, c.t1 * 8, c.t0 * 8, c.h * 8, c.b);
         }
     };
-    auto factors = [&](int k, Fac& f0, Fac& f1) {
-        const int tid = S.tile(k);
+    // tile number q of this warp's sequence of TILES (fp32: unit q; bf16: tile q % 2 of unit q / 2)
+    auto tile_of = [&](int q) -> int {
+        const int u = S.tile(q / kPer);
+        return u < P.tiles ? u * kPer + (q % kPer) : 0x7fffffff;
+    };
+    auto factors = [&](int q, Fac& f0, Fac& f1) {
+        const int tid = tile_of(q);
         if (tid < P.tiles) {
             const TileCoord c = tile_coord(P, tid);
             f0 = load_fac(P.fac, tid);
@@ -128,19 +161,26 @@ __global__ void __launch_bounds__(kW3 * 32, 1) phase_fwd_apply(const __grid_cons
     for (int k = 0; S.tile(k) < P.tiles; ++k) {
         __syncwarp();
         issue(k + 1);
-        const Fac f0 = n0, f1 = n1;
-        factors(k + 1, n0, n1);
-        const int tid = S.tile(k), st = k & 1;
-        const TileCoord c = tile_coord(P, tid);
-        mbar_wait(&bars[warp][st], parity[st]);
-        parity[st] ^= 1;
-        fwd_tile_apply<true>(P, buf + st * 4096, f0, f1, c, lane);
+        const int st = k & 1;
+#pragma unroll 1
+        for (int half = 0; half < kPer; ++half) {
+            const int q = k * kPer + half;
+            const Fac f0 = n0, f1 = n1;
+            factors(q + 1, n0, n1);
+            const TileCoord c = tile_coord(P, tile_of(q));
+            if (half == 0) {
+                mbar_wait(&bars[warp][st], parity[st]);
+                parity[st] ^= 1;
+            }
+            fwd_tile_apply_t<!BF16, false, typename TileOf<BF16>::type, typename TileOf<BF16>::out_t>(P, tile_at<BF16>(buf + st * 4096, half), f0, f1, c, lane);
+        }
     }
 }
 
 // =====================================================================================================
 // backward pass 1: per octant and window set, lane-partials of  w = G v_T / 2 + X cbar_T  and  e = qbar_T . v_T
 // =====================================================================================================
+template <bool BF16>
 __global__ void __launch_bounds__(kWB * 32, 1) phase_bwd_reduce(const __grid_constant__ PhaseParams P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ uint64_t bars[kWB][2];
@@ -152,21 +192,26 @@ __global__ void __launch_bounds__(kWB * 32, 1) phase_bwd_reduce(const __grid_con
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    Stream S; S.gw = blockIdx.x * kWB + warp; S.nw = gridDim.x * kWB; S.lane = lane; S.begin = P.t_begin; S.count = P.t_count; S.reverse = 0;
+    constexpr int kPer = BF16 ? 2 : 1;
+    Stream S; S.gw = blockIdx.x * kWB + warp; S.nw = gridDim.x * kWB; S.lane = lane; S.begin = P.t_begin / kPer; S.count = P.t_count / kPer; S.reverse = 0;
     const int oct = lane >> 2;
 
     auto issue = [&](int k) {
-        const int tid = S.tile(k);
-        if (tid < P.tiles && lane == 0) {
-            const TileCoord c = tile_coord(P, tid);
+        const int u = S.tile(k);
+        if (u < P.tiles && lane == 0) {
+            const TileCoord c = tile_coord(P, u * kPer);
             float* b = buf + (k & 1) * 8192;
             mbar_arrive_expect_tx(&bars[warp][k & 1], 2 * kTileBytes);
             tma_load_tile(b, &P.tm_x, &bars[warp][k & 1], c.t2 * 8, c.t1 * 8, c.t0 * 8, c.h * 8, c.b);
             tma_load_tile(b + 4096, &P.tm_g, &bars[warp][k & 1], c.t2 * 8, c.t1 * 8, c.t0 * 8, c.h * 8, c.b);
         }
     };
-    auto factors = [&](int k, UT& f0, UT& f1) {
-        const int tid = S.tile(k);
+    auto tile_of = [&](int q) -> int {
+        const int u = S.tile(q / kPer);
+        return u < P.tiles ? u * kPer + (q % kPer) : 0x7fffffff;
+    };
+    auto factors = [&](int q, UT& f0, UT& f1) {
+        const int tid = tile_of(q);
         if (tid < P.tiles) {
             const TileCoord c = tile_coord(P, tid);
             f0 = load_ut(P, tid);
@@ -180,12 +225,20 @@ __global__ void __launch_bounds__(kWB * 32, 1) phase_bwd_reduce(const __grid_con
     for (int k = 0; S.tile(k) < P.tiles; ++k) {
         __syncwarp();
         issue(k + 1);
-        const UT f0 = n0, f1 = n1;
-        factors(k + 1, n0, n1);
-        const int tid = S.tile(k), st = k & 1;
-        mbar_wait(&bars[warp][st], parity[st]);
-        parity[st] ^= 1;
-        bwd_tile_reduce(P, buf + st * 8192, f0, f1, lane, P.oct + (size_t)tid * kBwdTileRec);
+        const int st = k & 1;
+#pragma unroll 1
+        for (int half = 0; half < kPer; ++half) {
+            const int q = k * kPer + half;
+            const UT f0 = n0, f1 = n1;
+            factors(q + 1, n0, n1);
+            const int tid = tile_of(q);
+            if (half == 0) {
+                mbar_wait(&bars[warp][st], parity[st]);
+                parity[st] ^= 1;
+            }
+            bwd_tile_reduce_t(P, tile_at<BF16>(buf + st * 8192, half), tile_at<BF16>(buf + st * 8192 + 4096, half), f0, f1, lane,
+                              P.oct + (size_t)tid * kBwdTileRec);
+        }
     }
 }
 
@@ -204,46 +257,69 @@ __global__ void __launch_bounds__(kSolveThreads) phase_bwd_solve(const __grid_co
 // =====================================================================================================
 // backward pass 3: dx = [x > 0] sum_s ( rd_s u_s (u_s . g)/2 + M_s x + m_s + abar1_s v0[col_s] ) voxel by voxel
 // =====================================================================================================
+template <bool BF16>
 __global__ void __launch_bounds__(kWB * 32, 1) phase_bwd_apply(const __grid_constant__ PhaseParams P) {
+    constexpr int kPer = BF16 ? 2 : 1;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(16) float v0s[512];
-    __shared__ __align__(16) float mbs_all[kWB][2][9 * kMbF];     // [stage][window record: 0 = unshifted, 1 + o = shifted window of octant o]
+    __shared__ __align__(16) float mbs_all[kWB][2][9 * kMbF];     // [tile parity][window record: 0 = unshifted, 1 + o = shifted window of octant o]
     __shared__ uint64_t bars[kWB][2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* buf = reinterpret_cast<float*>(smem_raw) + (size_t)warp * 4 * 4096;
     for (int j = threadIdx.x; j < 512; j += blockDim.x) v0s[j] = P.v0[j];
     if (lane == 0) {
-        mbar_init(&bars[warp][0], 33);      // the TMA issuer + 32 cp.async completions
-        mbar_init(&bars[warp][1], 33);
+        mbar_init(&bars[warp][0], 1);
+        mbar_init(&bars[warp][1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    Stream S; S.gw = blockIdx.x * kWB + warp; S.nw = gridDim.x * kWB; S.lane = lane; S.begin = P.t_begin; S.count = P.t_count; S.reverse = P.reverse;
+    Stream S; S.gw = blockIdx.x * kWB + warp; S.nw = gridDim.x * kWB; S.lane = lane; S.begin = P.t_begin / kPer; S.count = P.t_count / kPer; S.reverse = P.reverse;
 
+    // the tile data of unit k (a tile, or a pair of bf16 tiles): one TMA box each for X and dY
     auto issue = [&](int k) {
-        const int tid = S.tile(k);
-        if (tid >= P.tiles) return;
-        const TileCoord c = tile_coord(P, tid);
-        uint64_t* bar = &bars[warp][k & 1];
-        if (lane == 0) {
+        const int u = S.tile(k);
+        if (u < P.tiles && lane == 0) {
+            const TileCoord c = tile_coord(P, u * kPer);
+            uint64_t* bar = &bars[warp][k & 1];
             float* b = buf + (k & 1) * 8192;
             mbar_arrive_expect_tx(bar, 2 * kTileBytes);
             tma_load_tile(b, &P.tm_x, bar, c.t2 * 8, c.t1 * 8, c.t0 * 8, c.h * 8, c.b);
             tma_load_tile(b + 4096, &P.tm_g, bar, c.t2 * 8, c.t1 * 8, c.t0 * 8, c.h * 8, c.b);
         }
-        bwd_fetch_records(P, mbs_all[warp][k & 1], tid, c, lane);
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    };
+    // tile number q of this warp's sequence of TILES (fp32: unit q; bf16: tile q % 2 of unit q / 2)
+    auto tile_of = [&](int q) -> int {
+        const int u = S.tile(q / kPer);
+        return u < P.tiles ? u * kPer + (q % kPer) : 0x7fffffff;
+    };
+    // the nine window records of tile q, one tile ahead of the arithmetic: cp.async group q
+    auto fetch = [&](int q) {
+        const int tid = tile_of(q);
+        if (tid < P.tiles) bwd_fetch_records(P, mbs_all[warp][q & 1], tid, tile_coord(P, tid), lane);
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
     issue(0);
+    fetch(0);
     uint32_t parity[2] = {0, 0};
     for (int k = 0; S.tile(k) < P.tiles; ++k) {
         __syncwarp();
         issue(k + 1);
-        const int tid = S.tile(k), st = k & 1;
-        const TileCoord c = tile_coord(P, tid);
-        mbar_wait(&bars[warp][st], parity[st]);
-        parity[st] ^= 1;
-        bwd_tile_apply(P, buf + st * 8192, mbs_all[warp][st], v0s, c, lane);
+        const int st = k & 1;
+#pragma unroll 1
+        for (int half = 0; half < kPer; ++half) {
+            const int q = k * kPer + half;
+            fetch(q + 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");     // this lane's copies of tile q have landed ...
+            __syncwarp();                                             // ... and so have everyone else's
+            if (half == 0) {
+                mbar_wait(&bars[warp][st], parity[st]);
+                parity[st] ^= 1;
+            }
+            const TileCoord c = tile_coord(P, tile_of(q));
+            bwd_tile_apply_t<false, typename TileOf<BF16>::type, typename TileOf<BF16>::out_t>(
+                P, tile_at<BF16>(buf + st * 8192, half), tile_at<BF16>(buf + st * 8192 + 4096, half), mbs_all[warp][q & 1], v0s, c, lane);
+            __syncwarp();                                             // records of tile q are free for tile q + 2
+        }
     }
 }
 
@@ -285,6 +361,7 @@ bool phase_supported(const DevGeom& G, const fz_solver& s, int relu) {
     if (s.num_iters < 1 || s.num_iters > 8) return false;
     if (G.d != 8 || G.p[0] != 8 || G.p[1] != 8 || G.p[2] != 8 || G.S != 2) return false;
     if (G.mats_per_shift == 0 || G.mats_per_shift >= (1LL << 28)) return false;
+    if (G.dtype == FZ_DTYPE_BF16 && (G.g[2] % 2)) return false;       // bf16 tiles travel in pairs along W
     for (int k = 0; k < 3; ++k) {
         int a = G.sh[0][k] % G.n[k], b = G.sh[1][k] % G.n[k];
         if (a < 0) a += G.n[k];
@@ -307,18 +384,27 @@ int phase_forward(const float* x, const float* v0, float* y, void* saved, void* 
     fill(P, G, s, 0, workspace);
     if (int e = make_map(&P.tm_x, x, G)) return e;
     P.x = x; P.out = y; P.v0 = v0; P.saved = static_cast<float*>(saved);
-    static SmemConfig cfg_gram, cfg_apply;
-    FZ_CUDA_CHECK(cfg_gram.ensure(phase_fwd_gram, kW1 * 2 * kTileBytes));
-    FZ_CUDA_CHECK(cfg_apply.ensure(phase_fwd_apply, kW3 * 2 * kTileBytes));
+    const bool bf16 = G.dtype == FZ_DTYPE_BF16;
+    static SmemConfig cfg_gram, cfg_apply, cfg_gram_h, cfg_apply_h;
+    if (bf16) {
+        FZ_CUDA_CHECK(cfg_gram_h.ensure(phase_fwd_gram<true>, kW1 * 2 * kTileBytes));
+        FZ_CUDA_CHECK(cfg_apply_h.ensure(phase_fwd_apply<true>, kW3 * 2 * kTileBytes));
+    } else {
+        FZ_CUDA_CHECK(cfg_gram.ensure(phase_fwd_gram<false>, kW1 * 2 * kTileBytes));
+        FZ_CUDA_CHECK(cfg_apply.ensure(phase_fwd_apply<false>, kW3 * 2 * kTileBytes));
+    }
     P.t_begin = 0;
     P.t_count = P.tiles;
     P.reverse = 1;          // pass 3 walks the tiles backwards: the tail of pass 1 is what L2 still holds
-    phase_fwd_gram<<<grid_for(P.t_count, kW1), kW1 * 32, kW1 * 2 * kTileBytes, st>>>(P);
+    const int units = bf16 ? P.t_count / 2 : P.t_count;        // streaming warps work on tiles (fp32) or pairs of tiles (bf16)
+    if (bf16) phase_fwd_gram<true><<<grid_for(units, kW1), kW1 * 32, kW1 * 2 * kTileBytes, st>>>(P);
+    else phase_fwd_gram<false><<<grid_for(units, kW1), kW1 * 32, kW1 * 2 * kTileBytes, st>>>(P);
     FZ_LAUNCH_CHECK();
     const long long groups = 2LL * P.t_count;
     phase_fwd_solve<<<(unsigned)((groups * 8 + 127) / 128), 128, 0, st>>>(P);
     FZ_LAUNCH_CHECK();
-    phase_fwd_apply<<<grid_for(P.t_count, kW3), kW3 * 32, kW3 * 2 * kTileBytes, st>>>(P);
+    if (bf16) phase_fwd_apply<true><<<grid_for(units, kW3), kW3 * 32, kW3 * 2 * kTileBytes, st>>>(P);
+    else phase_fwd_apply<false><<<grid_for(units, kW3), kW3 * 32, kW3 * 2 * kTileBytes, st>>>(P);
     FZ_LAUNCH_CHECK();
     return FZ_OK;
 }
@@ -334,18 +420,27 @@ int phase_backward(const float* x, const float* gy, const float* v0, const void*
     if (int e = make_map(&P.tm_g, gy, G)) return e;
     P.x = x; P.gy = gy; P.out = gx; P.v0 = v0;
     P.saved = const_cast<float*>(static_cast<const float*>(saved));
-    static SmemConfig cfg_reduce, cfg_apply;
-    FZ_CUDA_CHECK(cfg_reduce.ensure(phase_bwd_reduce, kWB * 4 * kTileBytes));
-    FZ_CUDA_CHECK(cfg_apply.ensure(phase_bwd_apply, kWB * 4 * kTileBytes));
+    const bool bf16 = G.dtype == FZ_DTYPE_BF16;
+    static SmemConfig cfg_reduce, cfg_apply, cfg_reduce_h, cfg_apply_h;
+    if (bf16) {
+        FZ_CUDA_CHECK(cfg_reduce_h.ensure(phase_bwd_reduce<true>, kWB * 4 * kTileBytes));
+        FZ_CUDA_CHECK(cfg_apply_h.ensure(phase_bwd_apply<true>, kWB * 4 * kTileBytes));
+    } else {
+        FZ_CUDA_CHECK(cfg_reduce.ensure(phase_bwd_reduce<false>, kWB * 4 * kTileBytes));
+        FZ_CUDA_CHECK(cfg_apply.ensure(phase_bwd_apply<false>, kWB * 4 * kTileBytes));
+    }
     P.t_begin = 0;
     P.t_count = P.tiles;
     P.reverse = 1;
-    phase_bwd_reduce<<<grid_for(P.t_count, kWB), kWB * 32, kWB * 4 * kTileBytes, st>>>(P);
+    const int units = bf16 ? P.t_count / 2 : P.t_count;
+    if (bf16) phase_bwd_reduce<true><<<grid_for(units, kWB), kWB * 32, kWB * 4 * kTileBytes, st>>>(P);
+    else phase_bwd_reduce<false><<<grid_for(units, kWB), kWB * 32, kWB * 4 * kTileBytes, st>>>(P);
     FZ_LAUNCH_CHECK();
     const long long groups = 2LL * P.t_count;
     phase_bwd_solve<<<(unsigned)((groups + kSolveThreads - 1) / kSolveThreads), kSolveThreads, 0, st>>>(P);
     FZ_LAUNCH_CHECK();
-    phase_bwd_apply<<<grid_for(P.t_count, kWB), kWB * 32, kWB * 4 * kTileBytes, st>>>(P);
+    if (bf16) phase_bwd_apply<true><<<grid_for(units, kWB), kWB * 32, kWB * 4 * kTileBytes, st>>>(P);
+    else phase_bwd_apply<false><<<grid_for(units, kWB), kWB * 32, kWB * 4 * kTileBytes, st>>>(P);
     FZ_LAUNCH_CHECK();
     return FZ_OK;
 }
@@ -476,6 +571,7 @@ int launch_combine(float* acc, const float* part, const DevGeom& G, const int* a
 }  // namespace
 
 bool pairs_supported(const DevGeom& G, const fz_solver& s, int relu) {
+    if (G.dtype != FZ_DTYPE_F32) return false;        // the roll / combine passes are fp32
     if (G.S < 2 || G.S % 2 || G.n[2] % 2) return false;
     int base[FZ_MAX_SHIFTS][3];
     if (!find_pairs(G, base)) return false;

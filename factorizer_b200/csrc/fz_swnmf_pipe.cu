@@ -616,7 +616,7 @@ constexpr size_t kBwdSmem = (size_t)kBwdSlots * kBwdSlotFloats * sizeof(float);
 // takes tens of microseconds per plane-group while the tiles of a plane-group are worth 1.6 us of HBM time.  It is
 // therefore only taken on request (fz_geom.path = FZ_PATH_OCTANT_PIPELINE); FZ_PATH_AUTO keeps the three-launch scheme.
 bool pipe_supported(const DevGeom& G, const fz_solver& s, int relu, int force) {
-    if (force <= 0) return false;
+    if (force <= 0 || G.dtype != FZ_DTYPE_F32) return false;
     if (!phase_supported(G, s, relu)) return false;
     return G.mats_per_shift < (1LL << 24);
 }

@@ -40,6 +40,7 @@ enum {
 };
 
 enum { FZ_SOLVER_MU = 0, FZ_SOLVER_HALS = 1 };
+enum { FZ_DTYPE_F32 = 0, FZ_DTYPE_BF16 = 1 };
 
 /* Window geometry of Matricize / SWMatricize
  * (factorizer/factorization/operations.py:299-355 and :381-415). */
@@ -51,6 +52,11 @@ typedef struct fz_geom {
     int32_t head_dim;                   /* d = rows M of every matrix                          */
     int32_t num_shifts;                 /* S (1 for a plain Matricize)                         */
     int32_t shifts[FZ_MAX_SHIFTS][3];   /* torch.roll shifts per window set; 0 = unshifted     */
+    int32_t dtype;                      /* FZ_DTYPE_F32 (0) or FZ_DTYPE_BF16: element type of the VOLUMES handed to
+                                           fz_swnmf_forward / _backward (x, y, dy, dx); u0, v0, the saved records and
+                                           all arithmetic stay fp32.  bf16 is served by the octant kernels only
+                                           (head_dim 8, patch 8^3, shifts [0, 4], ReLU, rank-1 HALS, an even number of
+                                           patches along W); anything else returns FZ_ERR_UNSUPPORTED              */
     int32_t path;                       /* FZ_PATH_AUTO (0), or one of FZ_PATH_* to restrict the
                                            kernel family fz_swnmf_* may pick for this call (tests
                                            and measurements; a per-call argument, no global state) */

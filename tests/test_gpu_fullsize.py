@@ -69,6 +69,42 @@ def test_core_full_size_vs_c_oracle(ft, dev, shape, k, scheme):
     assert torch.equal(y2, y) and torch.equal(gx2, gx)
 
 
+@pytest.mark.parametrize("shape", [(1, 32, 64, 64, 64), (2, 16, 32, 48, 64), (1, 8, 16, 16, 16), (1, 32, 128, 128, 128)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_core_bf16_activations(ft, dev, shape):
+    """bf16 volumes (north_star: "a stated looser bound applies for bf16 activations"): x, y, dy, dx travel as bf16, the
+    arithmetic and the factors stay fp32.  Reference = the fp32 C oracle on the SAME bf16-representable inputs, so the
+    only differences are the kernels' fp32 arithmetic and the final rounding of y / dx to bf16 (relative 2^-9):
+    bound rtol 1e-2 / atol 1e-3."""
+    from factorizer_b200 import _lib, _ops
+    rng = np.random.default_rng(5)
+    x = torch.from_numpy(rng.standard_normal(shape, dtype=np.float32)).to(dev).bfloat16()
+    gy = torch.from_numpy(rng.standard_normal(shape, dtype=np.float32)).to(dev).bfloat16()
+    sw = ft.SWMatricize((None, *shape[1:]), head_dim=8, patch_size=8)
+    torch.manual_seed(3)
+    nmf = ft.NMF((8, 512), rank=1, num_iters=5, init="uniform", solver="hals").to(dev)
+    xr = x.clone().requires_grad_(True)
+    y = _ops.SWNMF.apply(xr, nmf.init.u0, nmf.init.v0, sw._geom, nmf.solver_spec(), True)
+    assert y.dtype == torch.bfloat16 and _lib.lib().fz_last_path() == 2
+    (gx,) = torch.autograd.grad(y, xr, gy)
+    assert gx.dtype == torch.bfloat16
+    torch.cuda.synchronize()
+    v0 = _np(nmf.init.v0)
+    x_np, gy_np = _np(x.float()), _np(gy.float())
+    y_ref = CO.swnmf_forward(x_np, v0, 8, (8, 8, 8), SHIFTS)
+    gx_ref = CO.swnmf_backward(x_np, gy_np, v0, 8, (8, 8, 8), SHIFTS)
+    assert_close(_np(y.float()), y_ref, rtol=1e-2, atol=1e-3, what="y (bf16)")
+    assert_close(_np(gx.float()), gx_ref, rtol=1e-2, atol=1e-3, what="gx (bf16)")
+    # and against the fp32 kernels on the same inputs: only the output rounding differs (half a bf16 ulp, plus slack)
+    y32 = _ops.SWNMF.apply(x.float(), nmf.init.u0, nmf.init.v0, sw._geom, nmf.solver_spec(), True)
+    assert_close(_np(y.float()), _np(y32), rtol=4e-3, atol=1e-6, what="y bf16 vs fp32 kernels")
+    # geometries the bf16 kernels do not cover are refused, not silently converted
+    odd = ft.SWMatricize((None, 8, 16, 16, 24), head_dim=8, patch_size=8)
+    with pytest.raises(NotImplementedError):
+        _ops.SWNMF.apply(torch.zeros(1, 8, 16, 16, 24, device=dev, dtype=torch.bfloat16), nmf.init.u0, nmf.init.v0,
+                         odd._geom, nmf.solver_spec(), True)
+
+
 @pytest.mark.parametrize("n", [64, 128])
 def test_block_full_size_vs_oracle(ft, dev, n):
     """BASELINE config 3: FactorizerBlock(32, n^3, LayerNorm, SWMatricize, HALS rank 1, mlp_ratio 2) through the

@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol(ft):
 
 def test_struct_layout_matches_header(ft):
     from factorizer_b200 import _lib
-    assert ctypes.sizeof(_lib.FzGeom) == 4 * (2 + 3 + 3 + 2 + 3 * 8 + 1)
+    assert ctypes.sizeof(_lib.FzGeom) == 4 * (2 + 3 + 3 + 2 + 3 * 8 + 2)
     assert ctypes.sizeof(_lib.FzSolver) == 20
 
 
