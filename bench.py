@@ -535,6 +535,31 @@ def run_ours(args):
     barrier()
     core_ms = c0.elapsed_time(c1) / args.steps
 
+    # ---------------- the same core with bf16 activations (an extension: the reference is fp32) ----------------
+    core_bf16 = None
+    try:
+        gh, = (geom.c_geom(1, torch.bfloat16),)
+        zb, dmb = tz.bfloat16(), td2.bfloat16()
+        mb_, dzb = torch.empty_like(zb), torch.empty_like(zb)
+        fwd_h = lambda: lib.fz_swnmf_forward(P(zb), P(u0), P(v0), P(mb_), P(saved), P(ws), ctypes.byref(gh), ctypes.byref(s), 1, sp)
+        bwd_h = lambda: lib.fz_swnmf_backward(P(zb), P(dmb), P(u0), P(v0), P(saved), P(dzb), P(ws), ctypes.byref(gh), ctypes.byref(s), 1, sp)
+        for _ in range(3):
+            _lib.check(fwd_h()); _lib.check(bwd_h())
+        torch.cuda.synchronize(dev)
+        h0, h1, h2 = ev(), ev(), ev()
+        tf = tb = 0.0
+        for _ in range(reps):
+            h0.record(stream); _lib.check(fwd_h()); h1.record(stream); _lib.check(bwd_h()); h2.record(stream)
+            torch.cuda.synchronize(dev)
+            tf += h0.elapsed_time(h1); tb += h1.elapsed_time(h2)
+        core_bf16 = {"fwd_us": 1e3 * tf / reps, "bwd_us": 1e3 * tb / reps,
+                     "note": "x, y, dy, dx as bf16 (10*C bytes per voxel), arithmetic and factors fp32; parity bound rtol 1e-2 / atol 1e-3 "
+                             "(tests/test_gpu_fullsize.py::test_core_bf16_activations)"}
+        del zb, dmb, mb_, dzb
+    except Exception as e:
+        core_bf16 = {"error": f"{type(e).__name__}: {e}"[:200]}
+        torch.cuda.synchronize(dev)
+
     # ---------------- end-to-end with host buffers, through ft.FactorizerBlock + autograd ----------------
     # Every step copies its own x and dOut in from pinned host memory and its out and dX back out; the copy-in of step
     # k+1 and the copy-out of step k-1 run on side streams while step k computes (PCIe is full duplex).
@@ -651,6 +676,12 @@ def run_ours(args):
         if model and "train_step_ms" in model:
             model["train_voxels_per_s"] = world * voxels / (model["train_step_ms"] * 1e-3)
             model["infer_voxels_per_s"] = world * voxels / (model["infer_ms"] * 1e-3)
+        if core_bf16 and "fwd_us" in core_bf16:
+            hb = 1e-3 * (core_bf16["fwd_us"] + core_bf16["bwd_us"])
+            core_bf16["ms_per_step"] = hb
+            core_bf16["voxels_per_s_per_gpu"] = voxels / (hb * 1e-3)
+            core_bf16["hbm_frac_of_its_own_bytes"] = (floor_bytes / 2) / (hb * 1e-3) / 1e9 / peak
+            core_bf16["speedup_vs_fp32_core"] = core_ms / hb
         line = {
             "metric": METRIC, "value": world * voxels / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step,
@@ -673,6 +704,7 @@ def run_ours(args):
                      "fwd_us": core_fwd_us, "bwd_us": core_bwd_us,
                      "fused_op_hbm_frac": floor_bytes / (core_ms * 1e-3) / 1e9 / peak,
                      "path": {0: "generic", 1: "window-at-a-time", 2: "octant kernels, three launches per direction", 6: "octant kernels, one pipelined launch"}.get(core_path, str(core_path))},
+            "core_bf16": core_bf16,
             "e2e": {"value": world * voxels / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 2 * n_el * 4, "d2h_bytes_per_step": 2 * n_el * 4,
                     "api": "ft.FactorizerBlock(...)(x).backward(dOut) on tensors copied from / to pinned host memory every step"},
