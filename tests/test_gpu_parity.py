@@ -240,8 +240,8 @@ def test_factorizer_model_matches_reference(ft, dev, golden, name):
     gy = torch.from_numpy(cases.make_array(name, tuple(y.shape), "randn", tag="gy")).to(dev)
     params = dict(net.named_parameters())
     grads = torch.autograd.grad((y * gy).sum(), [x] + list(params.values()))
-    assert_close(_np(y), g[f"{name}/y"], rtol=2e-4, atol=2e-5, what="y")
-    assert_close(_np(grads[0]), g[f"{name}/gx"], rtol=2e-4, atol=2e-5, what="gx")
+    assert_close(_np(y), g[f"{name}/y"], what="y")
+    assert_close(_np(grads[0]), g[f"{name}/gx"], what="gx")
     for (k, _), gp in zip(params.items(), grads[1:]):
         ref = g[f"{name}/gp/{k}"]
         scale = max(1.0, float(np.abs(ref).max()))
@@ -696,3 +696,66 @@ def test_layernorm_fallback_shapes(ft, dev):
     ln = ft.LayerNorm(24).to(dev)
     ref = torch.nn.functional.layer_norm(x.movedim(1, -1), (24,), ln.norm.weight, ln.norm.bias, ln.norm.eps).movedim(-1, 1)
     assert torch.allclose(ln(x), ref)
+
+
+def test_saved_buffer_size_for_many_windows(ft, dev):
+    """fz_swnmf_saved_bytes must size the buffer for the kernel family that runs: the octant kernels have no limit on the
+    number of windows, the window-at-a-time kernels do (S * heads * g0 * g1 <= 4096).  A (1, 32, 8, 256, 256) volume has
+    2 * 4 * 1 * 32 = 256 ... use a geometry beyond the limit: heads * g0 * g1 = 4 * 32 * 32 = 4096 per set."""
+    import ctypes
+    from factorizer_b200 import _lib, _ops
+    shape = (1, 32, 256, 256, 8)
+    sw = ft.SWMatricize((None, *shape[1:]), head_dim=8, patch_size=8)
+    nmf = ft.NMF((8, 512), rank=1, num_iters=5, init="uniform", solver="hals").to(dev)
+    g, s = sw._geom.c_geom(1), nmf.solver_spec().c_solver()
+    need = _lib.lib().fz_swnmf_saved_bytes(ctypes.byref(g), ctypes.byref(s))
+    assert need == 2 * 4 * 32 * 32 * 1 * (48 + 72) * 4
+    x = torch.randn(shape, device=dev, requires_grad=True)
+    y = _ops.SWNMF.apply(x, nmf.init.u0, nmf.init.v0, sw._geom, nmf.solver_spec(), True)
+    (gx,) = torch.autograd.grad(y.sum(), x)          # used to fail with "saved buffer ... is required"
+    assert torch.isfinite(gx).all()
+
+
+def test_no_grad_inference_saves_nothing(ft, dev):
+    """Under torch.no_grad() with parameters that require grad (inference with an unfrozen model) the fused ops must not
+    allocate or fill the backward's buffers (ctx.needs_input_grad alone does not tell)."""
+    from factorizer_b200 import _ops
+    calls = []
+    orig = _ops._swnmf_forward
+
+    def spy(x, u0, v0, geom, spec, relu, need_grad):
+        calls.append(need_grad)
+        return orig(x, u0, v0, geom, spec, relu, need_grad)
+
+    _ops._swnmf_forward = spy
+    try:
+        blk = ft.FactorizerBlock(channels=32, spatial_size=(16, 16, 16), norm=ft.LayerNorm,
+                                 reshape=(ft.SWMatricize, {"head_dim": 8, "patch_size": 8}), act=nn.ReLU, factorize=ft.NMF,
+                                 rank=1, num_iters=5, init="uniform", solver="hals", mlp_ratio=2, dropout=0.0).to(dev)
+        x = torch.randn(1, 32, 16, 16, 16, device=dev)
+        with torch.no_grad():
+            blk(x)
+        blk(x)
+    finally:
+        _ops._swnmf_forward = orig
+    assert calls == [False, True]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process(ft):
+    """cudaFuncSetAttribute (dynamic shared memory above 48 KiB) and the SM count are per device: the second GPU of a
+    process must work like the first (the octant kernels use 192-224 KiB)."""
+    from factorizer_b200 import _ops
+    outs = []
+    for d in (0, 1):
+        dev = torch.device("cuda", d)
+        sw = ft.SWMatricize((None, 8, 16, 16, 16), head_dim=8, patch_size=8)
+        torch.manual_seed(0)
+        nmf = ft.NMF((8, 512), rank=1, num_iters=5, init="uniform", solver="hals").to(dev)
+        torch.manual_seed(1)
+        x = torch.randn(1, 8, 16, 16, 16).to(dev).requires_grad_(True)
+        with torch.cuda.device(dev):
+            y = _ops.SWNMF.apply(x, nmf.init.u0, nmf.init.v0, sw._geom, nmf.solver_spec(), True)
+            (gx,) = torch.autograd.grad(y.sum(), x)
+        outs.append((y.detach().cpu(), gx.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])

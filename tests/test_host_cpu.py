@@ -158,3 +158,16 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not pat.search(src), f
+
+
+def test_deep_supervision_heads_follow_the_reference(ft):
+    """factorizer/unet.py:251-258: `num_deep_supr=True` stores 3 but builds range(True) = ONE head; an int n builds n.
+    The module tree (state_dict keys heads.0 ...) must agree or reference checkpoints do not load."""
+    kw = dict(in_channels=1, out_channels=2, spatial_size=(16, 16, 16), encoder_depth=(1, 1), encoder_width=(8, 16), strides=(1, 2),
+              decoder_depth=(1,), norm=ft.LayerNorm, reshape=(ft.SWMatricize, {"head_dim": 8, "patch_size": 8}), act=nn.ReLU,
+              factorize=ft.NMF, rank=1, num_iters=2, init="uniform", solver="hals", mlp_ratio=2)
+    net = ft.Factorizer(num_deep_supr=True, **kw)
+    assert len(net.heads) == 1 and net.num_deep_supr == 3
+    assert [k for k in net.state_dict() if k.startswith("heads.")][0].startswith("heads.0.")
+    assert len(ft.Factorizer(num_deep_supr=2, **kw).heads) == 2
+    assert hasattr(ft.Factorizer(num_deep_supr=False, **kw), "head")
