@@ -648,7 +648,7 @@ volatile int g_glue_mode = -1;
 int glue_mode() {
     if (g_glue_mode < 0) {
         const char* e = getenv("FZ_GLUE_TC");
-        g_glue_mode = e ? atoi(e) & 3 : 1;
+        g_glue_mode = e ? atoi(e) & 7 : 5;
     }
     return g_glue_mode;
 }
@@ -676,7 +676,7 @@ using namespace fz;
 
 extern "C" {
 
-void fz_set_glue_mode(int32_t mode) { g_glue_mode = mode & 3; }
+void fz_set_glue_mode(int32_t mode) { g_glue_mode = mode & 7; }
 int fz_get_glue_mode(void) { return glue_mode(); }
 
 int fz_glue_supported(int32_t channels, int32_t hidden, int64_t voxels) {
@@ -781,6 +781,9 @@ int fz_mlp_backward(const float* x1, const float* dout, const float* gamma, cons
     if (dgamma) FZ_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, kC * sizeof(float), st));
     if (dbeta) FZ_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, kC * sizeof(float), st));
     if (batch == 0 || voxels == 0) return FZ_OK;
+    // tensor-core path (tcgen05, 3xTF32) for hidden width 64 unless the glue mode asks for the FP32-pipe kernel
+    if ((glue_mode() & 4) && mlp_bwd_tc_supported(hidden))
+        return mlp_bwd_tc_launch(x1, dout, gamma, beta, W1, b1, W2, dx1, dgamma, dbeta, dW1, db1, dW2, db2, batch, voxels, eps, st);
     const int tps = (int)((voxels + kTV - 1) / kTV);
     const long long tiles = batch * tps;
     const unsigned blocks = (unsigned)(tiles < sm_count() ? tiles : sm_count());

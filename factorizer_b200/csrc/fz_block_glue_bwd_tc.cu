@@ -1,0 +1,452 @@
+// Tensor-core (tcgen05 / TMEM, 3xTF32) backward of the MLP half of a 32-channel FactorizerBlock with hidden width 64:
+//     out = x1 + W2 gelu(W1 LN(x1) + b1) + b2      (reference factorizer/factorizer.py:76, layers/mlp.py:54-60,
+//                                                   layers/norm.py:29-34)
+// given x1 and d(out): d(x1) and the gradients of LN's gamma / beta, W1, b1, W2, b2.
+//
+// Per tile of 96 voxels (voxel = TMEM lane; lanes 96..127 idle), with xh = the normalised (pre-affine) input and
+// W1g = W1 diag(gamma):
+//   GEMM1  h      = xh  W1g^T (+ b1 + W1 beta)      N = 64, K = 32      per-voxel GEMMs, M = 128: the A operand is written
+//   GEMM2  dg     = dOut W2                         N = 64, K = 32      by its voxel's thread straight into TENSOR MEMORY
+//          g = gelu(h),  dh = dg gelu'(h)           (FP32 pipe, thread = voxel x half of the hidden units)
+//   GEMM3  d(xh)  = dh W1g                          N = 32, K = 64
+//   WG1    [g ; g_lo]   (128 rows) x [dOut | dOut_lo] (64 columns), contraction over the 96 voxels  -> dW2^T
+//   WG2    [dh ; dh_lo] (128 rows) x [xh | xh_lo]     (64 columns)                                  -> Q = sum_v dh xh^T
+//          dx1    = dOut + rstd (d(xh) - mean(d(xh)) - xh mean(d(xh) xh))
+// The contraction operands live in shared memory as "voxel rows" (MN-major SWIZZLE_128B_BASE32B, fz_tc.cuh): a thread
+// stores the 32 values of its voxel as one 128-byte row with STS.128.  3xTF32: every operand is staged as the fp32 word
+// (hi: the tensor core drops the low 13 bits) and its remainder (lo); a per-voxel GEMM issues a_lo b_hi + a_hi b_lo +
+// a_hi b_hi, a contraction computes all four hi / lo blocks in ONE MMA and the flush adds them.  WG1 / WG2 accumulate in
+// TMEM over ALL tiles of the CTA.  No per-voxel reductions for the small gradients:
+//   db1 = sum_v dh and db2 = sum_v dOut accumulate in registers (thread-private, reduced once per CTA),
+//   dW1 = Q diag(gamma) + db1 beta^T,  d(gamma)_c = sum_j W1[j][c] Q[j][c],  d(beta)_c = sum_j W1[j][c] db1[j].
+// One CTA per SM, 8 warps: warps 0-2 and 4-6 are the workers (warp w: voxels 32 (w % 4) .. + 31 = the TMEM lanes it may
+// touch; half w / 4 of the hidden units and of the channels), lane 0 of warp 3 issues the MMAs; mbarriers hand the phases
+// over.  Layouts and the TMEM A operand were pinned by bench_probes/tcgen05_layout_probe.cu and tcgen05_tmem_a_probe.cu.
+#include "fz_tc.cuh"
+
+namespace fz {
+namespace {
+
+using namespace tc;
+
+constexpr int kC = 32;
+constexpr int kH = 64;
+constexpr int kTV = 96;                   // voxels per tile
+constexpr int kWorkers = 192;
+constexpr int kThreads = 256;
+constexpr int kMmaWarp = 3;
+
+// shared memory map (bytes).  A voxel-row atom = 96 rows x 128 bytes.
+constexpr uint32_t kAtom = kTV * 128;     // 12 KiB
+constexpr uint32_t oXH = 0;               // xh   atoms [hi | lo]
+constexpr uint32_t oDO = 2 * kAtom;       // dOut atoms [hi | lo]
+constexpr uint32_t oG = 4 * kAtom;        // g    atoms [hi 0..31 | hi 32..63 | lo 0..31 | lo 32..63]
+constexpr uint32_t oDH = 8 * kAtom;       // dh   same
+constexpr uint32_t oW1 = 12 * kAtom;      // W1g  as B(n = j, k = c), K-major: hi 8 KiB | lo 8 KiB       (GEMM1)
+constexpr uint32_t oW2 = oW1 + 16384;     // W2   as B(n = j, k = o)                                     (GEMM2)
+constexpr uint32_t oW3 = oW2 + 16384;     // W1g  as B(n = c, k = j)                                     (GEMM3)
+constexpr uint32_t oPar = oW3 + 16384;    // b1f[64] | db1 of the CTA [64] | db2 [32]
+constexpr uint32_t oBar = oPar + 160 * 4; // 5 mbarriers
+constexpr uint32_t oTmem = oBar + 5 * 8;
+constexpr uint32_t kSmem = oTmem + 8;
+
+// TMEM columns: A operands (xh hi / lo, dOut hi / lo; later dh hi / lo) | h | dg | d(xh) | WG1 | WG2
+constexpr uint32_t cA = 0, cH = 128, cDG = 192, cDX = 256, cWG1 = 288, cWG2 = 352, kTmemCols = 512;
+
+// transposing warp reduction of N values: lane l ends with the warp total of element l / (32 / N)
+template <int N>
+__device__ __forceinline__ float warp_vec_sum(float (&v)[N], int lane) {
+    int off = 16;
+#pragma unroll
+    for (int n = N; n > 1; n >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float keep = up ? v[i + n / 2] : v[i];
+            const float send = up ? v[i] : v[i + n / 2];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+        off >>= 1;
+    }
+    float r = v[0];
+    for (; off > 0; off >>= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
+    return r;
+}
+
+// 8 consecutive values = one 32-byte chunk of a voxel row.  p0 / p1: the chunk's address + (swap ? 16 : 0) / + (swap ? 0 : 16);
+// lanes whose voxel has bit 2 set store the upper half first, so a quarter-warp's STS.128 covers all 32 banks
+__device__ __forceinline__ void st_chunk(unsigned char* p0, unsigned char* p1, bool swap, const float (&a)[8]) {
+    const float4 lo4 = make_float4(a[0], a[1], a[2], a[3]), hi4 = make_float4(a[4], a[5], a[6], a[7]);
+    *reinterpret_cast<float4*>(p0) = swap ? hi4 : lo4;
+    *reinterpret_cast<float4*>(p1) = swap ? lo4 : hi4;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_bwd_tc(const float* __restrict__ x1, const float* __restrict__ dout, const float* __restrict__ gamma,
+           const float* __restrict__ beta, const float* __restrict__ W1, const float* __restrict__ b1,
+           const float* __restrict__ W2, float* __restrict__ dx1, float* __restrict__ dgamma, float* __restrict__ dbeta,
+           float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2, float* __restrict__ db2, long long vox,
+           int tiles_per_sample, long long total_tiles, float eps) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float* par = reinterpret_cast<float*>(smem + oPar);
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar_p1 = sbase + oBar, bar_g12 = bar_p1 + 8, bar_p2 = bar_p1 + 16, bar_g3 = bar_p1 + 24, bar_wg = bar_p1 + 32;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // ---- once per CTA: weights (3xTF32 halves), folded bias, barriers, TMEM ----
+    for (int e = tid; e < kH * kC; e += kThreads) {
+        {
+            const int j = e >> 5, c = e & 31;                 // W1 (64, 32)
+            const float w = W1[e] * (gamma ? gamma[c] : 1.f);
+            const uint32_t o1 = oW1 + kmajor_off(j, c, kC), o3 = oW3 + kmajor_off(c, j, kH);
+            *reinterpret_cast<float*>(smem + o1) = w;
+            *reinterpret_cast<float*>(smem + o1 + 8192) = tf32_lo(w);
+            *reinterpret_cast<float*>(smem + o3) = w;
+            *reinterpret_cast<float*>(smem + o3 + 8192) = tf32_lo(w);
+        }
+        {
+            const int o_ = e >> 6, j = e & 63;                // W2 (32, 64): B(n = j, k = o)
+            const float w = W2[e];
+            const uint32_t o = oW2 + kmajor_off(j, o_, kC);
+            *reinterpret_cast<float*>(smem + o) = w;
+            *reinterpret_cast<float*>(smem + o + 8192) = tf32_lo(w);
+        }
+    }
+    for (int j = tid; j < kH; j += kThreads) {
+        float s = b1 ? b1[j] : 0.f;
+        if (beta)
+            for (int c = 0; c < kC; ++c) s = fmaf(W1[j * kC + c], beta[c], s);
+        par[j] = s;
+    }
+    if (tid == 0) {
+        bar_init(bar_p1, kWorkers); bar_init(bar_g12, 1); bar_init(bar_p2, kWorkers); bar_init(bar_g3, 1); bar_init(bar_wg, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kMmaWarp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(sbase + oTmem), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<const uint32_t*>(smem + oTmem);
+    const long long my_tiles = blockIdx.x < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp == kMmaWarp) {
+        // =============================== MMA issue (one thread) ===============================
+        if (lane == 0 && my_tiles > 0) {
+            const uint32_t id_g12 = make_idesc(128, kH, false, false);
+            const uint32_t id_g3 = make_idesc(128, kC, false, false);
+            const uint32_t id_wg = make_idesc(128, 64, true, true);
+            const uint64_t b_w1 = make_desc(sbase + oW1, 128, 1024, 0);
+            const uint64_t b_w2 = make_desc(sbase + oW2, 128, 1024, 0);
+            const uint64_t b_w3 = make_desc(sbase + oW3, 128, 2048, 0);
+            const uint64_t k_g = make_desc(sbase + oG, kAtom, 512, 1);            // voxel rows: 4 atoms of 32 rows (M = 128)
+            const uint64_t k_dh = make_desc(sbase + oDH, kAtom, 512, 1);
+            const uint64_t k_do = make_desc(sbase + oDO, kAtom, 512, 1);          //             2 atoms of 32 columns (N = 64)
+            const uint64_t k_xh = make_desc(sbase + oXH, kAtom, 512, 1);
+            for (long long it = 0; it < my_tiles; ++it) {
+                const uint32_t ph = (uint32_t)(it & 1);
+                bar_wait(bar_p1, ph);
+                tc_fence_after();
+#pragma unroll
+                for (int s = 0; s < kC / 8; ++s) {        // GEMM1: h = xh W1g^T   (A: hi columns cA .. + 31, lo + 32 ..)
+                    mma_tf32_ta(tmem + cH, tmem + cA + 32 + s * 8, desc_at(b_w1, s * 256), id_g12, s > 0);
+                    mma_tf32_ta(tmem + cH, tmem + cA + s * 8, desc_at(b_w1, 8192 + s * 256), id_g12, 1);
+                    mma_tf32_ta(tmem + cH, tmem + cA + s * 8, desc_at(b_w1, s * 256), id_g12, 1);
+                }
+#pragma unroll
+                for (int s = 0; s < kC / 8; ++s) {        // GEMM2: dg = dOut W2   (A: hi columns cA + 64 .., lo + 96 ..)
+                    mma_tf32_ta(tmem + cDG, tmem + cA + 96 + s * 8, desc_at(b_w2, s * 256), id_g12, s > 0);
+                    mma_tf32_ta(tmem + cDG, tmem + cA + 64 + s * 8, desc_at(b_w2, 8192 + s * 256), id_g12, 1);
+                    mma_tf32_ta(tmem + cDG, tmem + cA + 64 + s * 8, desc_at(b_w2, s * 256), id_g12, 1);
+                }
+                commit(bar_g12);
+                bar_wait(bar_p2, ph);
+                tc_fence_after();
+#pragma unroll
+                for (int s = 0; s < kH / 8; ++s) {        // GEMM3: d(xh) = dh W1g (A: hi columns cA .. + 63, lo + 64 ..)
+                    mma_tf32_ta(tmem + cDX, tmem + cA + 64 + s * 8, desc_at(b_w3, s * 256), id_g3, s > 0);
+                    mma_tf32_ta(tmem + cDX, tmem + cA + s * 8, desc_at(b_w3, 8192 + s * 256), id_g3, 1);
+                    mma_tf32_ta(tmem + cDX, tmem + cA + s * 8, desc_at(b_w3, s * 256), id_g3, 1);
+                }
+                commit(bar_g3);
+#pragma unroll 4
+                for (int s = 0; s < kTV / 8; ++s) {       // WG1 / WG2 over the tile's 12 groups of 8 voxels
+                    const uint32_t acc = (it > 0 || s > 0) ? 1u : 0u;
+                    mma_tf32(tmem + cWG1, desc_at(k_g, s * 1024), desc_at(k_do, s * 1024), id_wg, acc);
+                    mma_tf32(tmem + cWG2, desc_at(k_dh, s * 1024), desc_at(k_xh, s * 1024), id_wg, acc);
+                }
+                commit(bar_wg);
+            }
+        }
+    } else if ((warp & 3) != 3) {
+        // =============================== workers: thread = (voxel, half) ===============================
+        const int vq = warp & 3, hh = warp >> 2;
+        const int v = vq * 32 + lane;                                    // voxel of the tile = TMEM lane
+        const uint32_t lane_addr = tmem + ((uint32_t)(vq * 32) << 16);
+        const bool swap = (v & 4) != 0;
+        // voxel row addressing: chunk q of this voxel's row sits at row + 32 (q ^ (v % 4))
+        uint32_t co0[4], co1[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t c = (uint32_t)v * 128 + (uint32_t)((q ^ (v & 3)) << 5);
+            co0[q] = c + (swap ? 16u : 0u);
+            co1[q] = c + (swap ? 0u : 16u);
+        }
+        const float* const b1f = par + hh * 32;
+        float acc_db1[32], acc_db2[16];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc_db1[i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc_db2[i] = 0.f;
+
+        float xr[kC], dr[16];                                            // the tile's x1 (all channels) and dOut (own 16)
+        bool valid = false;
+        long long base = 0;
+        auto fetch = [&](long long tile) {
+            const long long b = tile / tiles_per_sample;
+            const long long v0 = (tile - b * tiles_per_sample) * kTV + v;
+            valid = v0 < vox;
+            base = b * kC * vox + v0;
+#pragma unroll
+            for (int c = 0; c < kC; ++c) xr[c] = valid ? __ldg(x1 + base + c * vox) : 0.f;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) dr[c] = valid ? __ldg(dout + base + (hh * 16 + c) * vox) : 0.f;
+        };
+        if (my_tiles > 0) fetch(blockIdx.x);
+        for (long long it = 0; it < my_tiles; ++it) {
+            const uint32_t ph = (uint32_t)(it & 1);
+            const bool cur_valid = valid;
+            const long long cur_base = base;
+            // ---- P1: LayerNorm statistics; xh and dOut -> TMEM (A of GEMM1 / GEMM2) and voxel rows (B of WG2 / WG1) ----
+            float mean = 0.f;
+#pragma unroll
+            for (int c = 0; c < kC; ++c) mean += xr[c];
+            mean *= (1.f / kC);
+            float var = 0.f;
+#pragma unroll
+            for (int c = 0; c < kC; ++c) { xr[c] -= mean; var = fmaf(xr[c], xr[c], var); }
+            const float rstd = rsqrtf(var * (1.f / kC) + eps);
+            if (it > 0) {
+                bar_wait(bar_wg, (uint32_t)((it - 1) & 1));              // the previous tile's MMAs have read their operands
+                // ... and the warp that shares these voxels has read the xh rows in its P3
+                asm volatile("bar.sync %0, 64;" :: "r"(1 + vq) : "memory");
+            }
+            tc_fence_after();
+            {
+                uint32_t th[16], tl[16];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    float h8[8], l8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float xh = (hh ? xr[16 + q * 8 + i] : xr[q * 8 + i]) * rstd;
+                        h8[i] = xh; l8[i] = tf32_lo(xh);
+                        th[q * 8 + i] = __float_as_uint(xh); tl[q * 8 + i] = __float_as_uint(l8[i]);
+                    }
+                    st_chunk(smem + oXH + co0[2 * hh + q], smem + oXH + co1[2 * hh + q], swap, h8);
+                    st_chunk(smem + oXH + kAtom + co0[2 * hh + q], smem + oXH + kAtom + co1[2 * hh + q], swap, l8);
+                }
+                tmem_st16(lane_addr + cA + hh * 16, th);
+                tmem_st16(lane_addr + cA + 32 + hh * 16, tl);
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    float h8[8], l8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float d = dr[q * 8 + i];
+                        h8[i] = d; l8[i] = tf32_lo(d);
+                        th[q * 8 + i] = __float_as_uint(d); tl[q * 8 + i] = __float_as_uint(l8[i]);
+                        acc_db2[q * 8 + i] += d;
+                    }
+                    st_chunk(smem + oDO + co0[2 * hh + q], smem + oDO + co1[2 * hh + q], swap, h8);
+                    st_chunk(smem + oDO + kAtom + co0[2 * hh + q], smem + oDO + kAtom + co1[2 * hh + q], swap, l8);
+                }
+                tmem_st16(lane_addr + cA + 64 + hh * 16, th);
+                tmem_st16(lane_addr + cA + 96 + hh * 16, tl);
+                tmem_st_wait();
+            }
+            tc_fence_before();
+            fence_async_smem();
+            bar_arrive(bar_p1);
+            // next tile's loads: in flight during this tile's GELU phase
+            if (it + 1 < my_tiles) fetch(blockIdx.x + (it + 1) * gridDim.x);
+            bar_wait(bar_g12, ph);
+            tc_fence_after();
+            // ---- P2: g = gelu(h), dh = dg gelu'(h) for this thread's 32 hidden units ----
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                uint32_t hr[16], gr[16], dh_hi[16], dh_lo[16];
+                tmem_ld16_nowait(lane_addr + cH + hh * 32 + q * 16, hr);
+                tmem_ld16_nowait(lane_addr + cDG + hh * 32 + q * 16, gr);
+                tmem_ld_wait();
+#pragma unroll
+                for (int o = 0; o < 2; ++o) {                            // one 32-byte chunk (8 hidden units) at a time
+                    float g8[8], gl8[8], d8[8], dl8[8];
+#pragma unroll
+                    for (int p = 0; p < 8; p += 2) {
+                        const int i = o * 8 + p, jj = q * 16 + i;
+                        const float2 bj = *reinterpret_cast<const float2*>(b1f + jj);
+                        float2 g, gp;
+                        gelu_grad2(make_float2(__uint_as_float(hr[i]) + bj.x, __uint_as_float(hr[i + 1]) + bj.y), g, gp);
+                        const float2 dh = __fmul2_rn(make_float2(__uint_as_float(gr[i]), __uint_as_float(gr[i + 1])), gp);
+                        acc_db1[jj] += dh.x;
+                        acc_db1[jj + 1] += dh.y;
+                        g8[p] = g.x; g8[p + 1] = g.y; gl8[p] = tf32_lo(g.x); gl8[p + 1] = tf32_lo(g.y);
+                        d8[p] = dh.x; d8[p + 1] = dh.y; dl8[p] = tf32_lo(dh.x); dl8[p + 1] = tf32_lo(dh.y);
+                        dh_hi[i] = __float_as_uint(dh.x); dh_hi[i + 1] = __float_as_uint(dh.y);
+                        dh_lo[i] = __float_as_uint(dl8[p]); dh_lo[i + 1] = __float_as_uint(dl8[p + 1]);
+                    }
+                    const int ch = 2 * q + o;                            // chunk of the thread's 32-value row
+                    st_chunk(smem + oG + hh * kAtom + co0[ch], smem + oG + hh * kAtom + co1[ch], swap, g8);
+                    st_chunk(smem + oG + (2 + hh) * kAtom + co0[ch], smem + oG + (2 + hh) * kAtom + co1[ch], swap, gl8);
+                    st_chunk(smem + oDH + hh * kAtom + co0[ch], smem + oDH + hh * kAtom + co1[ch], swap, d8);
+                    st_chunk(smem + oDH + (2 + hh) * kAtom + co0[ch], smem + oDH + (2 + hh) * kAtom + co1[ch], swap, dl8);
+                }
+                tmem_st16(lane_addr + cA + hh * 32 + q * 16, dh_hi);
+                tmem_st16(lane_addr + cA + 64 + hh * 32 + q * 16, dh_lo);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            fence_async_smem();
+            bar_arrive(bar_p2);
+            bar_wait(bar_g3, ph);
+            tc_fence_after();
+            // ---- P3: through LayerNorm, plus the residual branch ----
+            {
+                float d[32];
+                tmem_ld32(lane_addr + cDX, d);
+                float m1 = 0.f, m2 = 0.f;
+                float own_xh[16];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 a0 = *reinterpret_cast<const float4*>(smem + oXH + co0[q]);
+                    const float4 a1 = *reinterpret_cast<const float4*>(smem + oXH + co1[q]);
+                    const float4 lo4 = swap ? a1 : a0, hi4 = swap ? a0 : a1;
+                    const float xh8[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        m1 += d[q * 8 + i];
+                        m2 = fmaf(d[q * 8 + i], xh8[i], m2);
+                    }
+                    if ((q >> 1) == hh) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) own_xh[(q & 1) * 8 + i] = xh8[i];
+                    }
+                }
+                m1 *= (1.f / kC); m2 *= (1.f / kC);
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const float4 a0 = *reinterpret_cast<const float4*>(smem + oDO + co0[2 * hh + q]);
+                    const float4 a1 = *reinterpret_cast<const float4*>(smem + oDO + co1[2 * hh + q]);
+                    const float4 lo4 = swap ? a1 : a0, hi4 = swap ? a0 : a1;
+                    const float go8[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+                    if (cur_valid) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int c = q * 8 + i;
+                            const float dc = hh ? d[16 + c] : d[c];
+                            dx1[cur_base + (hh * 16 + c) * vox] = go8[i] + rstd * (dc - m1 - own_xh[c] * m2);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+        if (my_tiles > 0) bar_wait(bar_wg, (uint32_t)((my_tiles - 1) & 1));
+        tc_fence_after();
+        // ---- per-CTA totals of the register accumulators ----
+        {
+            const float t1 = warp_vec_sum<32>(acc_db1, lane);            // hidden unit 32 hh + lane
+            const float t2 = warp_vec_sum<16>(acc_db2, lane);            // channel 16 hh + lane / 2
+            float* scr = reinterpret_cast<float*>(smem + oW1);           // [warp][48]; every MMA has completed: the weights are dead
+            scr[warp * 48 + lane] = t1;
+            if ((lane & 1) == 0) scr[warp * 48 + 32 + (lane >> 1)] = t2;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (my_tiles > 0) {
+        // ---- flush.  Accumulator row r (TMEM lane r): hidden unit r % 64, hi block for r < 64, lo block above;
+        //      column n: channel n % 32 against the hi (n < 32) or lo operand.  The four blocks add up. ----
+        float* scr = reinterpret_cast<float*>(smem + oW1);
+        float* S1 = reinterpret_cast<float*>(smem + oG);                 // [128][65] dW2^T blocks
+        float* S2 = S1 + 128 * 65;                                       // [128][65] Q blocks
+        float* cdb1 = par + 64;
+        float* cdb2 = par + 128;
+        if (tid >= 128 && tid < 192) {
+            const int j = tid - 128, h2 = j >> 5;
+            float s = 0.f;
+            for (int w = 0; w < 3; ++w) s += scr[(h2 * 4 + w) * 48 + (j & 31)];
+            cdb1[j] = s;
+        } else if (tid >= 192 && tid < 224) {
+            const int c = tid - 192, h2 = c >> 4;
+            float s = 0.f;
+            for (int w = 0; w < 3; ++w) s += scr[(h2 * 4 + w) * 48 + 32 + (c & 15)];
+            cdb2[c] = s;
+        }
+        if (warp < 4) {
+            const uint32_t row_addr = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float d[32];
+                tmem_ld32(row_addr + cWG1 + half * 32, d);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) S1[tid * 65 + half * 32 + c] = d[c];
+                tmem_ld32(row_addr + cWG2 + half * 32, d);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) S2[tid * 65 + half * 32 + c] = d[c];
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        // thread t: column c = t % 32 of rows j = t / 32, + 8, ...
+        const int c = tid & 31;
+        const float gm = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+        float dgp = 0.f, dbp = 0.f;
+        for (int j = tid >> 5; j < kH; j += kThreads / 32) {
+            const float w2g = (S1[j * 65 + c] + S1[j * 65 + 32 + c]) + (S1[(64 + j) * 65 + c] + S1[(64 + j) * 65 + 32 + c]);   // dW2[o = c][j]
+            const float q = (S2[j * 65 + c] + S2[j * 65 + 32 + c]) + (S2[(64 + j) * 65 + c] + S2[(64 + j) * 65 + 32 + c]);     // Q[j][c]
+            atomicAdd(dW2 + c * kH + j, w2g);
+            atomicAdd(dW1 + j * kC + c, fmaf(gm, q, bt * cdb1[j]));
+            const float w = W1[j * kC + c];
+            dgp = fmaf(w, q, dgp);
+            dbp = fmaf(w, cdb1[j], dbp);
+        }
+        if (dgamma) atomicAdd(dgamma + c, dgp);
+        if (dbeta) atomicAdd(dbeta + c, dbp);
+        if (db1 && tid < kH) atomicAdd(db1 + tid, cdb1[tid]);
+        if (db2 && tid >= 64 && tid < 96) atomicAdd(db2 + tid - 64, cdb2[tid - 64]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(kTmemCols) : "memory");
+    }
+}
+
+}  // namespace
+
+bool mlp_bwd_tc_supported(int hidden) { return hidden == kH; }
+
+// gradients must be zeroed by the caller (the kernel adds its CTA totals with atomics)
+int mlp_bwd_tc_launch(const float* x1, const float* dout, const float* gamma, const float* beta, const float* W1, const float* b1,
+                      const float* W2, float* dx1, float* dgamma, float* dbeta, float* dW1, float* db1, float* dW2, float* db2,
+                      long long batch, long long voxels, float eps, cudaStream_t st) {
+    static SmemConfig cfg;
+    FZ_CUDA_CHECK(cfg.ensure(mlp_bwd_tc, kSmem));
+    const int tps = (int)((voxels + kTV - 1) / kTV);
+    const long long tiles = batch * tps;
+    const long long cap = num_sms();
+    const unsigned blocks = (unsigned)(tiles < cap ? tiles : cap);
+    mlp_bwd_tc<<<blocks, kThreads, kSmem, st>>>(x1, dout, gamma, beta, W1, b1, W2, dx1, dgamma, dbeta, dW1, db1, dW2, db2, voxels,
+                                                tps, tiles, eps);
+    FZ_LAUNCH_CHECK();
+    return FZ_OK;
+}
+
+}  // namespace fz

@@ -287,9 +287,10 @@ def _glue_call(fn, *args):
     L.check(fn(*[a.data_ptr() if isinstance(a, torch.Tensor) else a for a in args]))
 
 
-@pytest.fixture(params=[0, 1, 3], ids=["fp32-pipe", "tc-forward", "tc-forward+wgrad"])
+@pytest.fixture(params=[0, 5, 7], ids=["fp32-pipe", "tc-mlp", "tc-mlp+linear-wgrad"])
 def glue_mode(request):
-    """0 = every glue kernel on the FP32 pipe, 1 = forward MLP kernel on tcgen05 (default), 3 = also linear_bwd's wgrad."""
+    """0 = every glue kernel on the FP32 pipe; bit 0 = forward MLP kernel on tcgen05, bit 2 = MLP backward on tcgen05 (5 is
+    the default), bit 1 = also linear_bwd's weight gradient."""
     from factorizer_b200 import _lib as L
     lib = L.lib()
     before = lib.fz_get_glue_mode()
@@ -299,10 +300,11 @@ def glue_mode(request):
 
 
 @pytest.mark.parametrize("HID", [32, 48, 64, 136])
-@pytest.mark.parametrize("shape", [(1, 32, 8, 8, 8), (2, 32, 6, 10, 7), (3, 32, 1030)])
+@pytest.mark.parametrize("shape", [(1, 32, 8, 8, 8), (2, 32, 6, 10, 7), (3, 32, 1030), (2, 32, 30002)])
 def test_glue_kernels_against_torch_fp64(ft, dev, shape, HID, glue_mode):
-    """Each kernel of csrc/fz_block_glue.cu through the C ABI against fp64 torch autograd of the same
-    layers (LayerNorm over channels, k=1 Conv1d, exact GELU: the reference's factorizer/layers/*)."""
+    """Each kernel of csrc/fz_block_glue*.cu through the C ABI against fp64 torch autograd of the same
+    layers (LayerNorm over channels, k=1 Conv1d, exact GELU: the reference's factorizer/layers/*).  The last shape gives
+    every persistent CTA several tiles (470 tiles of 128 voxels on 148 SMs)."""
     from factorizer_b200 import _lib as L
     lib = L.lib()
     torch.manual_seed(3)
