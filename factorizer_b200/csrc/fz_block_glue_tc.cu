@@ -72,6 +72,16 @@ __device__ __forceinline__ void gemm3(uint32_t tmem_d, const unsigned char* a_hi
     }
 }
 
+// UTCHMMA reads uniform registers: issued under `if (tid == 0)` every MMA gets an ELECT / R2UR.BROADCAST / BRA.U.ANY loop
+// around it (~70 cycles each, measured); from warp-uniform control flow on warp-uniform values under elect_one() it is one
+// predicated instruction (bench_probes/tcgen05_rate_probe.cu)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 __device__ __forceinline__ void commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
@@ -160,6 +170,7 @@ __global__ void __launch_bounds__(kTM, 2) mixer_mlp_fwd_tc(const float* __restri
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5;
+    const bool issuer = uniform_u32((uint32_t)warp) == 0;      // warp-uniform: warp 0 issues the MMAs
 
     for (int e = tid; e < kC * kC; e += kTM) {
         const int n = e / kC, k = e % kC;
@@ -195,7 +206,7 @@ __global__ void __launch_bounds__(kTM, 2) mixer_mlp_fwd_tc(const float* __restri
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     publish_and_sync();
-    const uint32_t tmem = tmem_base;
+    const uint32_t tmem = uniform_u32(tmem_base);
     const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);     // this thread's TMEM lane, column 0
     // TMEM columns: [0, 32) x1 projection | [32, 32 + HID) hidden | [96, 128) output projection
     uint32_t parity = 0;
@@ -226,7 +237,10 @@ __global__ void __launch_bounds__(kTM, 2) mixer_mlp_fwd_tc(const float* __restri
 #pragma unroll
         for (int c = 0; c < kC; ++c) FZ_PUT_A(c, mreg[c]);
         publish_and_sync();
-        if (tid == 0) { gemm3(tmem, a_hi, a_lo, wo_hi, wo_lo, kC, kC); commit(&bar); }
+        if (issuer) {
+            if (elect_one()) { gemm3(tmem, a_hi, a_lo, wo_hi, wo_lo, kC, kC); commit(&bar); }
+            __syncwarp();
+        }
         float x1[kC];
 #pragma unroll
         for (int c = 0; c < kC; ++c) x1[c] = xreg[c];
@@ -255,7 +269,10 @@ __global__ void __launch_bounds__(kTM, 2) mixer_mlp_fwd_tc(const float* __restri
             for (int c = 0; c < kC; ++c) FZ_PUT_A(c, fmaf((x1[c] - mean) * rstd, par[2 * kC + c], par[3 * kC + c]));
         }
         publish_and_sync();
-        if (tid == 0) { gemm3(tmem + 32, a_hi, a_lo, w1_hi, w1_lo, kC, HID); commit(&bar); }
+        if (issuer) {
+            if (elect_one()) { gemm3(tmem + 32, a_hi, a_lo, w1_hi, w1_lo, kC, HID); commit(&bar); }
+            __syncwarp();
+        }
         // next tile's m and x: in flight during this tile's GELU and output phases
         {
             const long long nt = tile + gridDim.x;
@@ -284,7 +301,10 @@ __global__ void __launch_bounds__(kTM, 2) mixer_mlp_fwd_tc(const float* __restri
             }
         }
         publish_and_sync();
-        if (tid == 0) { gemm3(tmem + 96, a_hi, a_lo, w2_hi, w2_lo, HID, kC); commit(&bar); }
+        if (issuer) {
+            if (elect_one()) { gemm3(tmem + 96, a_hi, a_lo, w2_hi, w2_lo, HID, kC); commit(&bar); }
+            __syncwarp();
+        }
         wait_bar(&bar, parity); parity ^= 1;
         {
             float d[32];
@@ -376,7 +396,8 @@ __global__ void __launch_bounds__(kTM, 2) linear_bwd_tc(const float* __restrict_
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     publish_and_sync();
-    const uint32_t tmem = tmem_base;
+    const uint32_t tmem = uniform_u32(tmem_base);
+    const bool issuer = uniform_u32((uint32_t)warp) == 0;
     // D = F32, A = B = TF32, both K-major, N = 32, M = 64
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kC >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
     uint32_t parity = 0;
@@ -476,16 +497,20 @@ __global__ void __launch_bounds__(kTM, 2) linear_bwd_tc(const float* __restrict_
         scr[warp * 3 * kC + kC + lane] = r_dg;
         scr[warp * 3 * kC + 2 * kC + lane] = r_dbeta;
         publish_and_sync();
-        if (tid == 0) {
+        if (issuer) {
             const bool first = tile == (long long)blockIdx.x;
-            for (int s = 0; s < kTM / 8; ++s) {
-                const uint64_t ad = make_desc(smem_u32(KA) + s * 2 * kKP, kKP, kKS, 0);
-                const uint64_t bh = make_desc(smem_u32(KBh) + s * 2 * kKP, kKP, kKS, 0);
-                const uint64_t bl = make_desc(smem_u32(KBl) + s * 2 * kKP, kKP, kKS, 0);
-                mma_tf32_kk(tmem, ad, bh, idesc, !(first && s == 0));
-                mma_tf32_kk(tmem, ad, bl, idesc, 1);
+            if (elect_one()) {
+#pragma unroll
+                for (int s = 0; s < kTM / 8; ++s) {
+                    const uint64_t ad = make_desc(smem_u32(KA) + s * 2 * kKP, kKP, kKS, 0);
+                    const uint64_t bh = make_desc(smem_u32(KBh) + s * 2 * kKP, kKP, kKS, 0);
+                    const uint64_t bl = make_desc(smem_u32(KBl) + s * 2 * kKP, kKP, kKS, 0);
+                    mma_tf32_kk(tmem, ad, bh, idesc, !(first && s == 0));
+                    mma_tf32_kk(tmem, ad, bl, idesc, 1);
+                }
+                commit(&bar);
             }
-            commit(&bar);
+            __syncwarp();
         }
         pending = true;
         if (tid < 3 * kC) {
