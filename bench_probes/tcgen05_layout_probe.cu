@@ -88,6 +88,9 @@ int main(int argc, char** argv) {
         {1, 1, 2048, 512, 0, 64},     //          ... N = 64: two N atoms
         {1, 2, 4096, 1024, 0, 32},    // MN-major B with the plain 128B swizzle
         {0, 6, 16, 256, 0, 32},       // K-major SWIZZLE_32B
+        {1, 0, 128, 1024, 0, 32},     // MN-major B without swizzle: lbo between groups of 4 n?, sbo between groups of 8 k?
+        {1, 0, 1024, 128, 0, 32},     //          ... swapped
+        {1, 0, 128, 1024, 0, 64},     //          ... N = 64
     };
     int idx = -1;
     for (const Cfg& c : cfgs) {

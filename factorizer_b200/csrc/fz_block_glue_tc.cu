@@ -551,9 +551,9 @@ int tc_sm_count() { return num_sms(); }
 }  // namespace
 
 // hidden width 32 or 64 (mlp_ratio 1 or 2 at 32 channels): TMEM columns / shared memory of this version
-bool mixer_mlp_tc_supported(int hidden) { return hidden == 32 || hidden == 64; }
+bool mixer_mlp_tc_supported_v1(int hidden) { return hidden == 32 || hidden == 64; }
 
-int mixer_mlp_tc_launch(const float* x, const float* m, const float* Wout, const float* bout, const float* gamma, const float* beta,
+int mixer_mlp_tc_launch_v1(const float* x, const float* m, const float* Wout, const float* bout, const float* gamma, const float* beta,
                         const float* W1, const float* b1, const float* W2, const float* b2, float* x1, float* out, long long batch,
                         int hidden, long long voxels, float eps, cudaStream_t st) {
     const size_t smem = tc_smem_bytes();
