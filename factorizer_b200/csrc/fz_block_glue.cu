@@ -642,13 +642,13 @@ __global__ void __launch_bounds__(kTT, 1) mlp_bwd(const float* __restrict__ x1, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// bit 0: forward out_proj + norm2 + MLP on tcgen05 (default on); bit 1: weight gradient of linear_bwd on tcgen05 (default
-// off).  FZ_GLUE_TC=<n> sets the initial value, fz_set_glue_mode() changes it.
+// bit 0: forward out_proj + norm2 + MLP on tcgen05; bit 1: linear_bwd on tcgen05; bit 2: MLP backward on tcgen05 (all on by
+// default).  FZ_GLUE_TC=<n> sets the initial value, fz_set_glue_mode() changes it.
 volatile int g_glue_mode = -1;
 int glue_mode() {
     if (g_glue_mode < 0) {
         const char* e = getenv("FZ_GLUE_TC");
-        g_glue_mode = e ? atoi(e) & 7 : 5;
+        g_glue_mode = e ? atoi(e) & 7 : 7;
     }
     return g_glue_mode;
 }
@@ -742,10 +742,10 @@ int fz_linear_backward(const float* dy, const float* a, const float* gamma, cons
     if (dbeta) FZ_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, kC * sizeof(float), st));
     if (batch == 0 || voxels == 0) return FZ_OK;
     {
-        // weight gradient on the tensor core (tcgen05, 3xTF32): opt-in, measured slower than the FP32-pipe kernel as long as
-        // the per-voxel dgrad stays on the FP32 pipe (452 / 418 us against 354 / 284 us, profiles/r01g_tc_glue_ncu.md)
+        // tensor-core path (tcgen05, 3xTF32): dgrad with its A operand in tensor memory, weight gradient as a contraction over
+        // voxel rows (csrc/fz_block_glue_lin_tc.cu)
         if (glue_mode() & 2)
-            return linear_bwd_tc_launch(dy, a, gamma, beta, W, resid, da, dW, db, dgamma, dbeta, batch, voxels, eps, layernorm, st);
+            return linear_bwd_tc2_launch(dy, a, gamma, beta, W, resid, da, dW, db, dgamma, dbeta, batch, voxels, eps, layernorm, st);
     }
     const size_t smem = linear_bwd_smem();
     static SmemConfig cfg_ln, cfg_plain;

@@ -75,6 +75,12 @@ int linear_bwd_tc_launch(const float* dy, const float* a, const float* gamma, co
                          float* da, float* dW, float* db, float* dgamma, float* dbeta, long long batch, long long voxels, float eps,
                          int layernorm, cudaStream_t st);
 
+// fz_block_glue_lin_tc.cu: tcgen05 / TMEM version of linear_bwd (dgrad with A in tensor memory, weight gradient as a contraction
+// over voxel rows); the caller zeroes the gradients
+int linear_bwd_tc2_launch(const float* dy, const float* a, const float* gamma, const float* beta, const float* W, const float* resid,
+                          float* da, float* dW, float* db, float* dgamma, float* dbeta, long long batch, long long voxels, float eps,
+                          int layernorm, cudaStream_t st);
+
 // fz_block_glue_bwd_tc.cu: tcgen05 / TMEM version of the MLP + norm2 backward kernel (hidden width 64, 3xTF32); the caller
 // zeroes the gradients
 bool mlp_bwd_tc_supported(int hidden);
