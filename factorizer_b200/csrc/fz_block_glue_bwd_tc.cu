@@ -82,14 +82,6 @@ __device__ __forceinline__ float warp_vec_sum(float (&v)[N], int lane) {
     return r;
 }
 
-// 8 consecutive values = one 32-byte chunk of a voxel row.  p0 / p1: the chunk's address + (swap ? 16 : 0) / + (swap ? 0 : 16);
-// lanes whose voxel has bit 2 set store the upper half first, so a quarter-warp's STS.128 covers all 32 banks
-__device__ __forceinline__ void st_chunk(unsigned char* p0, unsigned char* p1, bool swap, const float (&a)[8]) {
-    const float4 lo4 = make_float4(a[0], a[1], a[2], a[3]), hi4 = make_float4(a[4], a[5], a[6], a[7]);
-    *reinterpret_cast<float4*>(p0) = swap ? hi4 : lo4;
-    *reinterpret_cast<float4*>(p1) = swap ? lo4 : hi4;
-}
-
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_bwd_tc(const float* __restrict__ x1, const float* __restrict__ dout, const float* __restrict__ gamma,
            const float* __restrict__ beta, const float* __restrict__ W1, const float* __restrict__ b1,
@@ -228,7 +220,7 @@ mlp_bwd_tc(const float* __restrict__ x1, const float* __restrict__ dout, const f
         const bool swap = (v & 4) != 0;
         // voxel row addressing: chunk q of this voxel's row sits at row + 32 (q ^ (v % 4)); the thread owns chunk qq of the
         // 32-channel rows (xh, dOut) and chunks 2 (qq % 2), + 1 of the 32-hidden-unit rows of atom qq / 2 (g, dh)
-        const uint32_t row = (uint32_t)v * 128, sw16 = swap ? 16u : 0u;
+        const uint32_t row = (uint32_t)v * 128;
         const uint32_t cx = row + (uint32_t)((qq ^ (v & 3)) << 5);
         const uint32_t cg0 = row + (uint32_t)(((2 * (qq & 1)) ^ (v & 3)) << 5) + (uint32_t)(qq >> 1) * kAtom;
         const uint32_t cg1 = row + (uint32_t)(((2 * (qq & 1) + 1) ^ (v & 3)) << 5) + (uint32_t)(qq >> 1) * kAtom;
@@ -299,8 +291,8 @@ mlp_bwd_tc(const float* __restrict__ x1, const float* __restrict__ dout, const f
                 if (it > 0) bar_wait(bar_wg, pph);                       // the previous tile's contractions have read their operands
                 tc_fence_after();
                 if (warp == 0) FZ_TR(1);
-                st_chunk(smem + oXH + cx + sw16, smem + oXH + cx + (16u - sw16), swap, xh);
-                st_chunk(smem + oXH + kAtom + cx + sw16, smem + oXH + kAtom + cx + (16u - sw16), swap, l8);
+                st_row_chunk(sbase + oXH + cx, swap, xh);
+                st_row_chunk(sbase + oXH + kAtom + cx, swap, l8);
                 tmem_st8(lane_addr + cA + qq * 8, th);
                 tmem_st8(lane_addr + cA + 32 + qq * 8, tl);
                 tmem_st_wait();
@@ -313,8 +305,8 @@ mlp_bwd_tc(const float* __restrict__ x1, const float* __restrict__ dout, const f
                     acc_db2[i] += go[i];
                 }
                 if (warp == 0) FZ_TR(2);
-                st_chunk(smem + oDO + cx + sw16, smem + oDO + cx + (16u - sw16), swap, go);
-                st_chunk(smem + oDO + kAtom + cx + sw16, smem + oDO + kAtom + cx + (16u - sw16), swap, l8);
+                st_row_chunk(sbase + oDO + cx, swap, go);
+                st_row_chunk(sbase + oDO + kAtom + cx, swap, l8);
                 tmem_st8(lane_addr + cA + 64 + qq * 8, th);
                 tmem_st8(lane_addr + cA + 96 + qq * 8, tl);
                 tmem_st_wait();
@@ -348,8 +340,8 @@ mlp_bwd_tc(const float* __restrict__ x1, const float* __restrict__ dout, const f
                         g8[p] = g.x; g8[p + 1] = g.y; gl8[p] = tf32_lo(g.x); gl8[p + 1] = tf32_lo(g.y);
                     }
                     const uint32_t cg = o ? cg1 : cg0;
-                    st_chunk(smem + oG + cg + sw16, smem + oG + cg + (16u - sw16), swap, g8);
-                    st_chunk(smem + oG + 2 * kAtom + cg + sw16, smem + oG + 2 * kAtom + cg + (16u - sw16), swap, gl8);
+                    st_row_chunk(sbase + oG + cg, swap, g8);
+                    st_row_chunk(sbase + oG + 2 * kAtom + cg, swap, gl8);
                 }
                 bar_wait(bar_g2, ph);
                 tc_fence_after();
@@ -367,8 +359,8 @@ mlp_bwd_tc(const float* __restrict__ x1, const float* __restrict__ dout, const f
                         dh_hi[i] = __float_as_uint(dh); dh_lo[i] = __float_as_uint(dl8[p]);
                     }
                     const uint32_t cg = o ? cg1 : cg0;
-                    st_chunk(smem + oDH + cg + sw16, smem + oDH + cg + (16u - sw16), swap, d8);
-                    st_chunk(smem + oDH + 2 * kAtom + cg + sw16, smem + oDH + 2 * kAtom + cg + (16u - sw16), swap, dl8);
+                    st_row_chunk(sbase + oDH + cg, swap, d8);
+                    st_row_chunk(sbase + oDH + 2 * kAtom + cg, swap, dl8);
                 }
                 tmem_st16(lane_addr + cA + qq * 16, dh_hi);
                 tmem_st16(lane_addr + cA + 64 + qq * 16, dh_lo);

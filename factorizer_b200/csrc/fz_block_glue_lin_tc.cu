@@ -52,14 +52,6 @@ __device__ __forceinline__ float warp_vec_sum(float (&v)[N], int lane) {
     return r;
 }
 
-// 8 consecutive values = one 32-byte chunk of a voxel row; lanes whose voxel has bit 2 set store the upper half first, so
-// that a quarter-warp's STS.128 covers all 32 banks
-__device__ __forceinline__ void st_chunk(unsigned char* p, uint32_t sw16, bool swap, const float (&a)[8]) {
-    const float4 lo4 = make_float4(a[0], a[1], a[2], a[3]), hi4 = make_float4(a[4], a[5], a[6], a[7]);
-    *reinterpret_cast<float4*>(p + sw16) = swap ? hi4 : lo4;
-    *reinterpret_cast<float4*>(p + (16u - sw16)) = swap ? lo4 : hi4;
-}
-
 template <bool LN>
 __global__ void __launch_bounds__(kThreads, 2)
 linear_bwd_tc2(const float* __restrict__ dy, const float* __restrict__ a, const float* __restrict__ gamma,
@@ -101,7 +93,6 @@ linear_bwd_tc2(const float* __restrict__ dy, const float* __restrict__ a, const 
     const int v = vq * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(vq * 32) << 16);
     const bool swap = (v & 4) != 0;
-    const uint32_t sw16 = swap ? 16u : 0u;
     // this thread's two 32-byte chunks (channels 16 hh .. + 15) of its voxel row
     const uint32_t c0 = (uint32_t)v * 128 + (uint32_t)(((2 * hh) ^ (v & 3)) << 5);
     const uint32_t c1 = (uint32_t)v * 128 + (uint32_t)(((2 * hh + 1) ^ (v & 3)) << 5);
@@ -171,12 +162,12 @@ linear_bwd_tc2(const float* __restrict__ dy, const float* __restrict__ a, const 
                     th[q * 8 + i] = __float_as_uint(g); tl[q * 8 + i] = __float_as_uint(l8[i]);
                     acc_s[q * 8 + i] += g;
                 }
-                st_chunk(smem + oDY + (q ? c1 : c0), sw16, swap, h8);
-                st_chunk(smem + oDY + kAtom + (q ? c1 : c0), sw16, swap, l8);
+                st_row_chunk(sbase + oDY + (q ? c1 : c0), swap, h8);
+                st_row_chunk(sbase + oDY + kAtom + (q ? c1 : c0), swap, l8);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { h8[i] = xh[q * 8 + i]; l8[i] = tf32_lo(h8[i]); }
-                st_chunk(smem + oXH + (q ? c1 : c0), sw16, swap, h8);
-                st_chunk(smem + oXH + kAtom + (q ? c1 : c0), sw16, swap, l8);
+                st_row_chunk(sbase + oXH + (q ? c1 : c0), swap, h8);
+                st_row_chunk(sbase + oXH + kAtom + (q ? c1 : c0), swap, l8);
             }
             tmem_st16(lane_addr + cA + hh * 16, th);
             tmem_st16(lane_addr + cA + 32 + hh * 16, tl);

@@ -134,6 +134,17 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// One 32-byte chunk (8 consecutive values) of a thread's voxel row, as two STS.128 (forced: left to itself the compiler
+// turns the select into predicated scalar stores, which conflict 8-way).  `chunk`: shared-memory address of the chunk;
+// lanes whose voxel has bit 2 set (swap) store the upper half first, so that a quarter-warp's STS.128 covers all 32 banks.
+__device__ __forceinline__ void st_row_chunk(uint32_t chunk, bool swap, const float (&a)[8]) {
+    const uint32_t first = chunk + (swap ? 16u : 0u), second = chunk + (swap ? 0u : 16u);
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "r"(first), "f"(swap ? a[4] : a[0]), "f"(swap ? a[5] : a[1]), "f"(swap ? a[6] : a[2]), "f"(swap ? a[7] : a[3]) : "memory");
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "r"(second), "f"(swap ? a[0] : a[4]), "f"(swap ? a[1] : a[5]), "f"(swap ? a[2] : a[6]), "f"(swap ? a[3] : a[7]) : "memory");
+}
+
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
