@@ -690,6 +690,7 @@ int fz_ln_linear_forward(const float* x, const float* gamma, const float* beta, 
     if (batch == 0 || voxels == 0) return FZ_OK;          // empty tensors carry null data pointers
     if (!x || !W || !y) return fail(FZ_ERR_INVALID, "null buffer");
     if (misaligned(x) || misaligned(y)) return fail(FZ_ERR_INVALID, "buffers must be 8-byte aligned");
+    if (glue_mode() & 1) return ln_linear_tc_launch(x, gamma, beta, W, y, batch, voxels, eps, (cudaStream_t)stream);
     const long long pps = voxels / 2, total = batch * pps;
     long long blocks = (total + 127) / 128;
     const long long cap = 3LL * sm_count();

@@ -237,6 +237,131 @@ mixer_mlp_fwd_tc2(const float* __restrict__ x, const float* __restrict__ m, cons
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(kTmemCols) : "memory");
 }
 
+// --------------------------------------------------------------------------------------------------------------------
+// z = W LN(x)   (norm1 + in_proj; reference factorizer/factorizer.py:38, layers/norm.py:29-34, layers/linear.py:53-58)
+// Same scheme: the normalised input is written into tensor memory by its voxel's two threads (16 channels each, both
+// compute the statistics), one 3xTF32 GEMM per 128-voxel tile with W diag(gamma) as B (the beta term is a bias W beta),
+// 8 KB of shared memory and 128 TMEM columns per CTA: up to four CTAs per SM keep the two HBM passes busy.
+// --------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t lW = 0, lPar = 8192, lBar = lPar + kC * 4, lTmem = lBar + 8, kSmemLn = lTmem + 8;
+
+__global__ void __launch_bounds__(kThreads, 3)
+ln_linear_fwd_tc(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 const float* __restrict__ W, float* __restrict__ y, long long vox, int tiles_per_sample, long long total_tiles,
+                 float eps) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float* wb = reinterpret_cast<float*>(smem + lPar);        // (W beta)[o]
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar = sbase + lBar;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool issuer = uniform_u32((uint32_t)warp) == 0;
+    for (int e = tid; e < kC * kC; e += kThreads) {
+        const int o = e >> 5, c = e & 31;
+        const float w = W[e] * (gamma ? gamma[c] : 1.f);
+        const uint32_t off = lW + kmajor_off(o, c, kC);
+        *reinterpret_cast<float*>(smem + off) = w;
+        *reinterpret_cast<float*>(smem + off + 4096) = tf32_lo(w);
+    }
+    for (int o = tid; o < kC; o += kThreads) {
+        float s = 0.f;
+        if (beta)
+            for (int c = 0; c < kC; ++c) s = fmaf(W[o * kC + c], beta[c], s);
+        wb[o] = s;
+    }
+    if (tid == 0) {
+        bar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" :: "r"(sbase + lTmem) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = uniform_u32(*reinterpret_cast<const uint32_t*>(smem + lTmem));
+    const int vq = warp & 3, hh = warp >> 2;
+    const int v = vq * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(vq * 32) << 16);
+    const uint32_t idesc = make_idesc(128, kC, false, false);
+    const uint64_t b_w = make_desc(sbase + lW, 128, kC * 32, 0);
+    uint32_t parity = 0;
+    long long nb = (long long)blockIdx.x / tiles_per_sample;
+    int nt = (int)((long long)blockIdx.x - nb * tiles_per_sample);
+    const long long my_tiles = blockIdx.x < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    float xr[kC];
+    bool valid = false;
+    long long base = 0;
+    auto fetch = [&]() {
+        const long long v0 = (long long)nt * kTM + v;
+        valid = v0 < vox;
+        base = nb * kC * vox + v0;
+        nt += (int)gridDim.x;
+        while (nt >= tiles_per_sample) { nt -= tiles_per_sample; ++nb; }
+        const float* px = x + base;
+#pragma unroll
+        for (int c = 0; c < kC; ++c) { xr[c] = valid ? __ldg(px) : 0.f; px += vox; }
+    };
+    if (my_tiles > 0) fetch();
+    for (long long it = 0; it < my_tiles; ++it) {
+        const bool cur_valid = valid;
+        const long long cur_base = base;
+        {
+            float mean = 0.f;
+#pragma unroll
+            for (int c = 0; c < kC; ++c) mean += xr[c];
+            mean *= (1.f / kC);
+            float var = 0.f;
+#pragma unroll
+            for (int c = 0; c < kC; ++c) { const float d = xr[c] - mean; var = fmaf(d, d, var); }
+            const float rstd = rsqrtf(var * (1.f / kC) + eps);
+            uint32_t th[16], tl[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const float xh = ((hh ? xr[16 + c] : xr[c]) - mean) * rstd;
+                th[c] = __float_as_uint(xh); tl[c] = __float_as_uint(tf32_lo(xh));
+            }
+            tmem_st16(lane_addr + hh * 16, th);               // A: hi columns 0 .. 31, lo 32 .. 63; D: 64 .. 95
+            tmem_st16(lane_addr + 32 + hh * 16, tl);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncthreads();
+        if (issuer) {
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int s = 0; s < kC / 8; ++s) {
+                    mma_tf32_ta(tmem + 64, tmem + 32 + s * 8, desc_at(b_w, s * 256), idesc, s > 0);
+                    mma_tf32_ta(tmem + 64, tmem + s * 8, desc_at(b_w, 4096 + s * 256), idesc, 1);
+                    mma_tf32_ta(tmem + 64, tmem + s * 8, desc_at(b_w, s * 256), idesc, 1);
+                }
+                commit(bar);
+            }
+            __syncwarp();
+        }
+        if (it + 1 < my_tiles) fetch();
+        bar_wait(bar, parity);
+        parity ^= 1;
+        tc_fence_after();
+        {
+            uint32_t d[16];
+            tmem_ld16_nowait(lane_addr + 64 + hh * 16, d);
+            tmem_ld_wait();
+            if (cur_valid) {
+                float* po = y + cur_base + (long long)(hh * 16) * vox;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) { *po = __uint_as_float(d[c]) + wb[hh * 16 + c]; po += vox; }
+            }
+        }
+        tc_fence_before();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" :: "r"(tmem) : "memory");
+}
+
 }  // namespace
 
 // hidden width 32 or 64 (mlp_ratio 1 or 2 at 32 channels)
@@ -260,4 +385,19 @@ int mixer_mlp_tc_launch(const float* x, const float* m, const float* Wout, const
     return FZ_OK;
 }
 
+}  // namespace fz
+
+namespace fz {
+int ln_linear_tc_launch(const float* x, const float* gamma, const float* beta, const float* W, float* y, long long batch,
+                        long long voxels, float eps, cudaStream_t st) {
+    static SmemConfig cfg;
+    FZ_CUDA_CHECK(cfg.ensure(ln_linear_fwd_tc, kSmemLn));
+    const int tps = (int)((voxels + kTM - 1) / kTM);
+    const long long tiles = batch * tps;
+    const long long cap = 3LL * num_sms();
+    const unsigned blocks = (unsigned)(tiles < cap ? tiles : cap);
+    ln_linear_fwd_tc<<<blocks, kThreads, kSmemLn, st>>>(x, gamma, beta, W, y, voxels, tps, tiles, eps);
+    FZ_LAUNCH_CHECK();
+    return FZ_OK;
+}
 }  // namespace fz

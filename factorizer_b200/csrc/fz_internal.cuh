@@ -71,6 +71,9 @@ int mixer_mlp_tc_launch(const float* x, const float* m, const float* Wout, const
                         const float* W1, const float* b1, const float* W2, const float* b2, float* x1, float* out, long long batch,
                         int hidden, long long voxels, float eps, cudaStream_t st);
 
+int ln_linear_tc_launch(const float* x, const float* gamma, const float* beta, const float* W, float* y, long long batch,
+                        long long voxels, float eps, cudaStream_t st);
+
 int linear_bwd_tc_launch(const float* dy, const float* a, const float* gamma, const float* beta, const float* W, const float* resid,
                          float* da, float* dW, float* db, float* dgamma, float* dbeta, long long batch, long long voxels, float eps,
                          int layernorm, cudaStream_t st);
