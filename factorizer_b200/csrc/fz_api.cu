@@ -7,7 +7,7 @@
 namespace fz {
 
 TlsState& tls() {
-    static thread_local TlsState s = {{0}, 0, 0};
+    static thread_local TlsState s = {{0}, 0, 0, 7};
     return s;
 }
 

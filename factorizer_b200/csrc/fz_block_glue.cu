@@ -20,10 +20,9 @@
 // threads add the slices into the per-CTA accumulator (fp32 atomics on shared memory are CAS loops on sm_100a), and the
 // CTA adds its total to the global gradient once at the end (global fp32 atomics).
 // Per-channel sums (bias / LayerNorm parameter gradients) use a transposing warp reduction (31 shuffles for 32 values).
-// mixer_mlp_fwd has a tensor-core twin in fz_block_glue_tc.cu (tcgen05 / TMEM, 3xTF32), which is the default for hidden
-// widths 32 and 64; fz_set_glue_mode() / FZ_GLUE_TC choose.
-#include <stdlib.h>
-
+// Every kernel here has a tensor-core twin (tcgen05 / TMEM, 3xTF32: fz_block_glue_fwd_tc.cu, fz_block_glue_lin_tc.cu,
+// fz_block_glue_bwd_tc.cu), which is the default where its shape restrictions hold (hidden width 64 for the MLP backward,
+// 32 or 64 for the forward); these FP32-pipe kernels take every other hidden width and fz_set_glue_mode(0).
 #include "fz_common.cuh"
 #include "fz_internal.cuh"
 
@@ -642,16 +641,9 @@ __global__ void __launch_bounds__(kTT, 1) mlp_bwd(const float* __restrict__ x1, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// bit 0: forward out_proj + norm2 + MLP on tcgen05; bit 1: linear_bwd on tcgen05; bit 2: MLP backward on tcgen05 (all on by
-// default).  FZ_GLUE_TC=<n> sets the initial value, fz_set_glue_mode() changes it.
-volatile int g_glue_mode = -1;
-int glue_mode() {
-    if (g_glue_mode < 0) {
-        const char* e = getenv("FZ_GLUE_TC");
-        g_glue_mode = e ? atoi(e) & 7 : 7;
-    }
-    return g_glue_mode;
-}
+// Per calling thread (no process-wide state): bit 0 = the forward kernels on tcgen05, bit 1 = linear_bwd, bit 2 = the MLP
+// backward; all on by default.  fz_set_glue_mode() exists for the parity tests and the benchmark's FP32-pipe comparison.
+int glue_mode() { return tls().glue_mode; }
 
 int sm_count() { return num_sms(); }
 
@@ -676,7 +668,7 @@ using namespace fz;
 
 extern "C" {
 
-void fz_set_glue_mode(int32_t mode) { g_glue_mode = mode & 7; }
+void fz_set_glue_mode(int32_t mode) { tls().glue_mode = mode & 7; }
 int fz_get_glue_mode(void) { return glue_mode(); }
 
 int fz_glue_supported(int32_t channels, int32_t hidden, int64_t voxels) {

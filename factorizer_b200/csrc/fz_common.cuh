@@ -14,6 +14,7 @@ struct TlsState {
     char msg[512];
     int path;
     int launches;
+    int glue_mode;   // fz_set_glue_mode() of the calling thread (all tensor-core paths on by default)
 };
 TlsState& tls();
 int fail(int code, const char* fmt, ...);

@@ -65,18 +65,13 @@ int pipe_forward(const float* x, const float* v0, float* y, void* saved, void* w
 int pipe_backward(const float* x, const float* gy, const float* v0, const void* saved, float* gx,
                   void* workspace, const DevGeom& G, const fz_solver& s, int K, cudaStream_t st);
 
-// fz_block_glue_tc.cu: tcgen05 / TMEM version of the out_proj + norm2 + MLP forward kernel (3xTF32)
+// fz_block_glue_fwd_tc.cu: tcgen05 / TMEM versions of the two forward glue kernels (A operands in tensor memory, 3xTF32)
 bool mixer_mlp_tc_supported(int hidden);
 int mixer_mlp_tc_launch(const float* x, const float* m, const float* Wout, const float* bout, const float* gamma, const float* beta,
                         const float* W1, const float* b1, const float* W2, const float* b2, float* x1, float* out, long long batch,
                         int hidden, long long voxels, float eps, cudaStream_t st);
-
 int ln_linear_tc_launch(const float* x, const float* gamma, const float* beta, const float* W, float* y, long long batch,
                         long long voxels, float eps, cudaStream_t st);
-
-int linear_bwd_tc_launch(const float* dy, const float* a, const float* gamma, const float* beta, const float* W, const float* resid,
-                         float* da, float* dW, float* db, float* dgamma, float* dbeta, long long batch, long long voxels, float eps,
-                         int layernorm, cudaStream_t st);
 
 // fz_block_glue_lin_tc.cu: tcgen05 / TMEM version of linear_bwd (dgrad with A in tensor memory, weight gradient as a contraction
 // over voxel rows); the caller zeroes the gradients

@@ -183,9 +183,11 @@ int fz_conv3d_stem_forward(const float* x, const float* weight, const float* bia
  * multiple of 8 up to 256 (the backward runs in slices of 64 hidden units). */
 int fz_glue_supported(int32_t channels, int32_t hidden, int64_t voxels);
 
-/* Which glue kernels run on the tensor cores (tcgen05 / TMEM, 3xTF32): bit 0 = fz_mixer_mlp_forward (hidden width 32 or
- * 64; default on), bit 1 = the weight gradient inside fz_linear_backward (default off: measured slower).  The environment
- * variable FZ_GLUE_TC=<mode> sets the initial value.  Both paths meet the same parity bounds. */
+/* Which glue kernels run on the tensor cores (tcgen05 / TMEM, 3xTF32), for calls made by the CALLING THREAD: bit 0 =
+ * fz_ln_linear_forward and fz_mixer_mlp_forward (hidden width 32 or 64), bit 1 = fz_linear_backward, bit 2 =
+ * fz_mlp_backward (hidden width 64).  Default 7 = all; 0 = the FP32-pipe kernels.  Both families meet the same parity
+ * bounds; the switch exists for the parity tests and for timing one against the other.  No environment variable, no
+ * process-wide state. */
 void fz_set_glue_mode(int32_t mode);
 int fz_get_glue_mode(void);
 
