@@ -774,9 +774,9 @@ int fz_mlp_backward(const float* x1, const float* dout, const float* gamma, cons
     if (dgamma) FZ_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, kC * sizeof(float), st));
     if (dbeta) FZ_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, kC * sizeof(float), st));
     if (batch == 0 || voxels == 0) return FZ_OK;
-    // tensor-core path (tcgen05, 3xTF32) for hidden width 64 unless the glue mode asks for the FP32-pipe kernel
+    // tensor-core path (tcgen05, 3xTF32) for hidden widths that are multiples of 64 unless the glue mode asks for the FP32-pipe kernel
     if ((glue_mode() & 4) && mlp_bwd_tc_supported(hidden))
-        return mlp_bwd_tc_launch(x1, dout, gamma, beta, W1, b1, W2, dx1, dgamma, dbeta, dW1, db1, dW2, db2, batch, voxels, eps, st);
+        return mlp_bwd_tc_launch(x1, dout, gamma, beta, W1, b1, W2, dx1, dgamma, dbeta, dW1, db1, dW2, db2, batch, hidden, voxels, eps, st);
     const int tps = (int)((voxels + kTV - 1) / kTV);
     const long long tiles = batch * tps;
     const unsigned blocks = (unsigned)(tiles < sm_count() ? tiles : sm_count());

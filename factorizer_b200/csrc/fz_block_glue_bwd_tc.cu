@@ -86,8 +86,11 @@ __global__ void __launch_bounds__(kThreads, 1)
 mlp_bwd_tc(const float* __restrict__ x1, const float* __restrict__ dout, const float* __restrict__ gamma,
            const float* __restrict__ beta, const float* __restrict__ W1, const float* __restrict__ b1,
            const float* __restrict__ W2, float* __restrict__ dx1, float* __restrict__ dgamma, float* __restrict__ dbeta,
-           float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2, float* __restrict__ db2, long long vox,
-           int tiles_per_sample, long long total_tiles, float eps) {
+           float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2, float* __restrict__ db2, int ldw2,
+           int accumulate, long long vox, int tiles_per_sample, long long total_tiles, float eps) {
+    // One launch covers 64 hidden units; wider MLPs run slice by slice (the backward is additive over hidden units): W1 / b1 /
+    // dW1 / db1 point at the slice's first row, W2 / dW2 at its first column (rows ldw2 apart), and with `accumulate` dx1
+    // already holds dOut + the other slices' contributions.
     extern __shared__ __align__(1024) unsigned char smem[];
     float* par = reinterpret_cast<float*>(smem + oPar);
     const uint32_t sbase = smem_u32(smem);
@@ -111,7 +114,7 @@ mlp_bwd_tc(const float* __restrict__ x1, const float* __restrict__ dout, const f
         }
         {
             const int o_ = e >> 6, j = e & 63;                // W2 (32, 64): B(n = j, k = o)
-            const float w = W2[e];
+            const float w = W2[o_ * ldw2 + j];
             const uint32_t o = oW2 + kmajor_off(j, o_, kC);
             *reinterpret_cast<float*>(smem + o) = w;
             *reinterpret_cast<float*>(smem + o + 8192) = tf32_lo(w);
@@ -396,7 +399,7 @@ mlp_bwd_tc(const float* __restrict__ x1, const float* __restrict__ dout, const f
                     float* po = dx1 + cur_base;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        *po = go[i] + rstd * (dx[i] - m1 - xh[i] * m2);
+                        *po = (accumulate ? *po : go[i]) + rstd * (dx[i] - m1 - xh[i] * m2);
                         po += vox;
                     }
                 }
@@ -459,7 +462,7 @@ mlp_bwd_tc(const float* __restrict__ x1, const float* __restrict__ dout, const f
         for (int j = tid >> 5; j < kH; j += kThreads / 32) {
             const float w2g = (S1[j * 65 + c] + S1[j * 65 + 32 + c]) + (S1[(64 + j) * 65 + c] + S1[(64 + j) * 65 + 32 + c]);   // dW2[o = c][j]
             const float q = (S2[j * 65 + c] + S2[j * 65 + 32 + c]) + (S2[(64 + j) * 65 + c] + S2[(64 + j) * 65 + 32 + c]);     // Q[j][c]
-            atomicAdd(dW2 + c * kH + j, w2g);
+            atomicAdd(dW2 + c * ldw2 + j, w2g);
             atomicAdd(dW1 + j * kC + c, fmaf(gm, q, bt * cdb1[j]));
             const float w = W1[j * kC + c];
             dgp = fmaf(w, q, dgp);
@@ -487,21 +490,24 @@ extern "C" int fz_debug_mlp_bwd_trace(long long* buf) {
 }
 #endif
 
-bool mlp_bwd_tc_supported(int hidden) { return hidden == kH; }
+bool mlp_bwd_tc_supported(int hidden) { return hidden >= kH && hidden % kH == 0; }
 
 // gradients must be zeroed by the caller (the kernel adds its CTA totals with atomics)
 int mlp_bwd_tc_launch(const float* x1, const float* dout, const float* gamma, const float* beta, const float* W1, const float* b1,
                       const float* W2, float* dx1, float* dgamma, float* dbeta, float* dW1, float* db1, float* dW2, float* db2,
-                      long long batch, long long voxels, float eps, cudaStream_t st) {
+                      long long batch, int hidden, long long voxels, float eps, cudaStream_t st) {
     static SmemConfig cfg;
     FZ_CUDA_CHECK(cfg.ensure(mlp_bwd_tc, kSmem));
     const int tps = (int)((voxels + kTV - 1) / kTV);
     const long long tiles = batch * tps;
     const long long cap = num_sms();
     const unsigned blocks = (unsigned)(tiles < cap ? tiles : cap);
-    mlp_bwd_tc<<<blocks, kThreads, kSmem, st>>>(x1, dout, gamma, beta, W1, b1, W2, dx1, dgamma, dbeta, dW1, db1, dW2, db2, voxels,
-                                                tps, tiles, eps);
-    FZ_LAUNCH_CHECK();
+    for (int h0 = 0; h0 < hidden; h0 += kH) {
+        mlp_bwd_tc<<<blocks, kThreads, kSmem, st>>>(x1, dout, gamma, beta, W1 + (size_t)h0 * kC, b1 ? b1 + h0 : nullptr, W2 + h0, dx1,
+                                                    dgamma, dbeta, dW1 + (size_t)h0 * kC, db1 ? db1 + h0 : nullptr, dW2 + h0,
+                                                    h0 == 0 ? db2 : nullptr, hidden, h0 > 0, voxels, tps, tiles, eps);
+        FZ_LAUNCH_CHECK();
+    }
     return FZ_OK;
 }
 

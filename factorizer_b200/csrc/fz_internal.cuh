@@ -79,12 +79,12 @@ int linear_bwd_tc2_launch(const float* dy, const float* a, const float* gamma, c
                           float* da, float* dW, float* db, float* dgamma, float* dbeta, long long batch, long long voxels, float eps,
                           int layernorm, cudaStream_t st);
 
-// fz_block_glue_bwd_tc.cu: tcgen05 / TMEM version of the MLP + norm2 backward kernel (hidden width 64, 3xTF32); the caller
+// fz_block_glue_bwd_tc.cu: tcgen05 / TMEM version of the MLP + norm2 backward kernel (hidden width a multiple of 64, 3xTF32); the caller
 // zeroes the gradients
 bool mlp_bwd_tc_supported(int hidden);
 int mlp_bwd_tc_launch(const float* x1, const float* dout, const float* gamma, const float* beta, const float* W1, const float* b1,
                       const float* W2, float* dx1, float* dgamma, float* dbeta, float* dW1, float* db1, float* dW2, float* db2,
-                      long long batch, long long voxels, float eps, cudaStream_t st);
+                      long long batch, int hidden, long long voxels, float eps, cudaStream_t st);
 
 // fz_nmf_big.cu: rank-1 MU / HALS on matrices too large for one CTA (global Matricize: M channels x all voxels), one
 // grid-wide pass per sweep
