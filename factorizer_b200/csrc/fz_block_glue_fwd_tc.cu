@@ -239,13 +239,13 @@ mixer_mlp_fwd_tc2(const float* __restrict__ x, const float* __restrict__ m, cons
 
 // --------------------------------------------------------------------------------------------------------------------
 // z = W LN(x)   (norm1 + in_proj; reference factorizer/factorizer.py:38, layers/norm.py:29-34, layers/linear.py:53-58)
-// Same scheme: the normalised input is written into tensor memory by its voxel's two threads (16 channels each, both
-// compute the statistics), one 3xTF32 GEMM per 128-voxel tile with W diag(gamma) as B (the beta term is a bias W beta),
-// 8 KB of shared memory and 128 TMEM columns per CTA: up to four CTAs per SM keep the two HBM passes busy.
+// Same scheme: the normalised input is written into tensor memory by its voxel's two threads (16 channels each; they
+// exchange their partial sums for the statistics), one 3xTF32 GEMM per 128-voxel tile with W diag(gamma) as B (the beta term is a bias W beta),
+// 12 KB of shared memory and 128 TMEM columns per CTA: four CTAs per SM keep the two HBM passes busy.
 // --------------------------------------------------------------------------------------------------------------------
-constexpr uint32_t lW = 0, lPar = 8192, lBar = lPar + kC * 4, lTmem = lBar + 8, kSmemLn = lTmem + 8;
+constexpr uint32_t lW = 0, lPar = 8192, lEx = lPar + kC * 4, lBar = lEx + 2 * 256 * 8, lTmem = lBar + 8, kSmemLn = lTmem + 8;
 
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 4)
 ln_linear_fwd_tc(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  const float* __restrict__ W, float* __restrict__ y, long long vox, int tiles_per_sample, long long total_tiles,
                  float eps) {
@@ -290,36 +290,39 @@ ln_linear_fwd_tc(const float* __restrict__ x, const float* __restrict__ gamma, c
     long long nb = (long long)blockIdx.x / tiles_per_sample;
     int nt = (int)((long long)blockIdx.x - nb * tiles_per_sample);
     const long long my_tiles = blockIdx.x < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    float xr[kC];
+    float xr[16];                             // this thread's 16 channels of the next tile
+    float2* const slots = reinterpret_cast<float2*>(smem + lEx);
+    uint32_t turn = 0;
     bool valid = false;
     long long base = 0;
     auto fetch = [&]() {
         const long long v0 = (long long)nt * kTM + v;
         valid = v0 < vox;
-        base = nb * kC * vox + v0;
+        base = (nb * kC + hh * 16) * vox + v0;
         nt += (int)gridDim.x;
         while (nt >= tiles_per_sample) { nt -= tiles_per_sample; ++nb; }
         const float* px = x + base;
 #pragma unroll
-        for (int c = 0; c < kC; ++c) { xr[c] = valid ? __ldg(px) : 0.f; px += vox; }
+        for (int c = 0; c < 16; ++c) { xr[c] = valid ? __ldg(px) : 0.f; px += vox; }
     };
     if (my_tiles > 0) fetch();
     for (long long it = 0; it < my_tiles; ++it) {
         const bool cur_valid = valid;
         const long long cur_base = base;
         {
-            float mean = 0.f;
+            // LayerNorm statistics: the two threads of a voxel own 16 channels each and exchange their partial sums
+            float s = 0.f;
 #pragma unroll
-            for (int c = 0; c < kC; ++c) mean += xr[c];
-            mean *= (1.f / kC);
-            float var = 0.f;
+            for (int c = 0; c < 16; ++c) s += xr[c];
+            const float mean = pair_sum2(make_float2(s, 0.f), slots, turn, hh, vq, v).x * (1.f / kC);
+            float ss = 0.f;
 #pragma unroll
-            for (int c = 0; c < kC; ++c) { const float d = xr[c] - mean; var = fmaf(d, d, var); }
-            const float rstd = rsqrtf(var * (1.f / kC) + eps);
+            for (int c = 0; c < 16; ++c) { xr[c] -= mean; ss = fmaf(xr[c], xr[c], ss); }
+            const float rstd = rsqrtf(pair_sum2(make_float2(ss, 0.f), slots, turn, hh, vq, v).x * (1.f / kC) + eps);
             uint32_t th[16], tl[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
-                const float xh = ((hh ? xr[16 + c] : xr[c]) - mean) * rstd;
+                const float xh = xr[c] * rstd;
                 th[c] = __float_as_uint(xh); tl[c] = __float_as_uint(tf32_lo(xh));
             }
             tmem_st16(lane_addr + hh * 16, th);               // A: hi columns 0 .. 31, lo 32 .. 63; D: 64 .. 95
@@ -350,7 +353,7 @@ ln_linear_fwd_tc(const float* __restrict__ x, const float* __restrict__ gamma, c
             tmem_ld16_nowait(lane_addr + 64 + hh * 16, d);
             tmem_ld_wait();
             if (cur_valid) {
-                float* po = y + cur_base + (long long)(hh * 16) * vox;
+                float* po = y + cur_base;
 #pragma unroll
                 for (int c = 0; c < 16; ++c) { *po = __uint_as_float(d[c]) + wb[hh * 16 + c]; po += vox; }
             }
@@ -394,7 +397,7 @@ int ln_linear_tc_launch(const float* x, const float* gamma, const float* beta, c
     FZ_CUDA_CHECK(cfg.ensure(ln_linear_fwd_tc, kSmemLn));
     const int tps = (int)((voxels + kTM - 1) / kTM);
     const long long tiles = batch * tps;
-    const long long cap = 3LL * num_sms();
+    const long long cap = 4LL * num_sms();
     const unsigned blocks = (unsigned)(tiles < cap ? tiles : cap);
     ln_linear_fwd_tc<<<blocks, kThreads, kSmemLn, st>>>(x, gamma, beta, W, y, voxels, tps, tiles, eps);
     FZ_LAUNCH_CHECK();

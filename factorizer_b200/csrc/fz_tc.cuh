@@ -145,6 +145,18 @@ __device__ __forceinline__ void st_row_chunk(uint32_t chunk, bool swap, const fl
                  :: "r"(second), "f"(swap ? a[0] : a[4]), "f"(swap ? a[1] : a[5]), "f"(swap ? a[2] : a[6]), "f"(swap ? a[3] : a[7]) : "memory");
 }
 
+// Sums of two values over the TWO threads that share a voxel (warps w and w + 4 of a 256-thread CTA: same lane, same TMEM
+// lane quarter).  `slots`: 2 x 2 x 128 float2 of shared memory ([call parity][half][voxel]); `turn` counts the calls (two
+// buffers: the partner is at most one exchange behind); named barrier 1 + quarter, 64 threads.
+__device__ __forceinline__ float2 pair_sum2(float2 mine, float2* slots, uint32_t& turn, int hh, int vq, int v) {
+    float2* s = slots + (turn & 1u) * 256;
+    s[hh * 128 + v] = mine;
+    asm volatile("bar.sync %0, 64;" :: "r"(1 + vq) : "memory");
+    const float2 other = s[(hh ^ 1) * 128 + v];
+    ++turn;
+    return make_float2(mine.x + other.x, mine.y + other.y);
+}
+
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
