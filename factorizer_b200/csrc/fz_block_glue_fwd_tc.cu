@@ -9,8 +9,7 @@
 // swizzle.  D comes back through tcgen05.ld (32x32b: a thread reads ITS voxel's row), so bias / residual / LayerNorm /
 // GELU run per thread in registers.
 // A CTA has 8 warps: warp w owns the voxels 32 (w % 4) .. + 31 (the TMEM lanes it may touch) and half w / 4 of the channels
-// and hidden units; the LayerNorm statistics are computed redundantly by the two threads of a voxel (x comes from L1 the
-// second time).  Warp 0 issues the MMAs from warp-uniform code under elect.sync.  40 KB of shared memory and 256 TMEM
+// and hidden units; the two threads of a voxel exchange their partial sums for the LayerNorm statistics.  Warp 0 issues the MMAs from warp-uniform code under elect.sync.  40 KB of shared memory and 256 TMEM
 // columns per CTA: two CTAs per SM overlap each other's MMA round trips.
 #include "fz_tc.cuh"
 
@@ -29,7 +28,8 @@ constexpr uint32_t oWo = 0;                               // W_out (32, 32) as B
 constexpr uint32_t oW1 = oWo + 2 * kC * kC * 4;           // W1 (HID, 32)   as B(n = j, k = c)
 constexpr uint32_t oW2 = oW1 + 2 * kMaxHid * kC * 4;      // W2 (32, HID)   as B(n = o, k = j)
 constexpr uint32_t oPar = oW2 + 2 * kC * kMaxHid * 4;     // bout | b2 | gamma | beta | b1
-constexpr uint32_t oBar = oPar + (4 * kC + kMaxHid) * 4;
+constexpr uint32_t oEx = oPar + (4 * kC + kMaxHid) * 4;   // pair_sum2 slots: 2 x [half][128] float2
+constexpr uint32_t oBar = oEx + 2 * 256 * 8;
 constexpr uint32_t oTmem = oBar + 8;
 constexpr uint32_t kSmem = oTmem + 8;
 
@@ -102,21 +102,23 @@ mixer_mlp_fwd_tc2(const float* __restrict__ x, const float* __restrict__ m, cons
     long long nb = (long long)blockIdx.x / tiles_per_sample;
     int nt = (int)((long long)blockIdx.x - nb * tiles_per_sample);
     const long long my_tiles = blockIdx.x < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    float mr[16], xr[kC];                     // the next tile's m (own 16 channels) and x (all channels)
+    float mr[16], xr[16];                     // the next tile's m and x (own 16 channels)
+    float2* const slots = reinterpret_cast<float2*>(smem + oEx);
+    uint32_t turn = 0;
     bool valid = false;
     long long base = 0;
     auto fetch = [&]() {
         const long long v0 = (long long)nt * kTM + v;
         valid = v0 < vox;
-        base = nb * kC * vox + v0;
+        base = (nb * kC + hh * 16) * vox + v0;
         nt += (int)gridDim.x;
         while (nt >= tiles_per_sample) { nt -= tiles_per_sample; ++nb; }
-        const float* pm = m + base + (long long)(hh * 16) * vox;
+        const float* pm = m + base;
         const float* px = x + base;
 #pragma unroll
         for (int c = 0; c < 16; ++c) { mr[c] = valid ? __ldg(pm) : 0.f; pm += vox; }
 #pragma unroll
-        for (int c = 0; c < kC; ++c) { xr[c] = valid ? __ldg(px) : 0.f; px += vox; }
+        for (int c = 0; c < 16; ++c) { xr[c] = valid ? __ldg(px) : 0.f; px += vox; }
     };
     // one GEMM D[cols d ..) = A[128 x K] W^T, A hi at TMEM columns a_hi .., lo at a_lo ..; issued by warp 0 once every thread has
     // published its part of A; every thread then waits for the result
@@ -157,46 +159,43 @@ mixer_mlp_fwd_tc2(const float* __restrict__ x, const float* __restrict__ m, cons
             tmem_st16(lane_addr + cA + 32 + hh * 16, tl);
         }
         gemm(cD, cA, cA + 32, b_wo, kC * kC * 4, kC, id32);
-        float x1[kC];
+        float x1o[16];
 #pragma unroll
-        for (int c = 0; c < kC; ++c) x1[c] = xr[c];
+        for (int c = 0; c < 16; ++c) x1o[c] = xr[c];
         wait_gemm();
-        // ---- x1 = x + out_proj(m) + b (all channels, both threads of the voxel), LayerNorm, A <- LN(x1) (own 16) ----
+        // ---- x1 = x + out_proj(m) + b, LayerNorm (the two threads of a voxel exchange partial sums), A <- LN(x1): own 16 channels ----
         {
-            float d[32];
-            tmem_ld32(lane_addr + cD, d);
+            uint32_t d[16];
+            tmem_ld16_nowait(lane_addr + cD + hh * 16, d);
+            tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < kC; ++c) x1[c] += d[c] + par[c];
+            for (int c = 0; c < 16; ++c) x1o[c] += __uint_as_float(d[c]) + par[hh * 16 + c];
         }
         if (x1_out && cur_valid) {
-            float* po = x1_out + cur_base + (long long)(hh * 16) * vox;
+            float* po = x1_out + cur_base;
 #pragma unroll
-            for (int c = 0; c < 16; ++c) { *po = hh ? x1[16 + c] : x1[c]; po += vox; }
+            for (int c = 0; c < 16; ++c) { *po = x1o[c]; po += vox; }
         }
         {
-            float mean = 0.f;
+            float sm = 0.f;
 #pragma unroll
-            for (int c = 0; c < kC; ++c) mean += x1[c];
-            mean *= (1.f / kC);
-            float var = 0.f;
+            for (int c = 0; c < 16; ++c) sm += x1o[c];
+            const float mean = pair_sum2(make_float2(sm, 0.f), slots, turn, hh, vq, v).x * (1.f / kC);
+            float ss = 0.f;
 #pragma unroll
-            for (int c = 0; c < kC; ++c) { const float dlt = x1[c] - mean; var = fmaf(dlt, dlt, var); }
-            const float rstd = rsqrtf(var * (1.f / kC) + eps);
+            for (int c = 0; c < 16; ++c) { const float dlt = x1o[c] - mean; ss = fmaf(dlt, dlt, ss); }
+            const float rstd = rsqrtf(pair_sum2(make_float2(ss, 0.f), slots, turn, hh, vq, v).x * (1.f / kC) + eps);
             uint32_t th[16], tl[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
-                const float xc = hh ? x1[16 + c] : x1[c];
-                const float n = fmaf((xc - mean) * rstd, par[2 * kC + hh * 16 + c], par[3 * kC + hh * 16 + c]);
+                const float n = fmaf((x1o[c] - mean) * rstd, par[2 * kC + hh * 16 + c], par[3 * kC + hh * 16 + c]);
                 th[c] = __float_as_uint(n); tl[c] = __float_as_uint(tf32_lo(n));
             }
             tmem_st16(lane_addr + cA + hh * 16, th);
             tmem_st16(lane_addr + cA + 32 + hh * 16, tl);
         }
         gemm(cHid, cA, cA + 32, b_w1, kMaxHid * kC * 4, kC, idH);
-        // keep this tile's own x1 channels, then fetch the next tile's m and x: in flight during the GELU and output phases
-        float x1o[16];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) x1o[c] = hh ? x1[16 + c] : x1[c];
+        // fetch the next tile's m and x: in flight during the GELU and output phases
         if (it + 1 < my_tiles) fetch();
         wait_gemm();
         // ---- A <- gelu(h) (own HID / 2 hidden units): hi over the pre-activation's columns, lo over the old A region ----
@@ -224,7 +223,7 @@ mixer_mlp_fwd_tc2(const float* __restrict__ x, const float* __restrict__ m, cons
             tmem_ld16_nowait(lane_addr + cD + hh * 16, d);
             tmem_ld_wait();
             if (cur_valid) {
-                float* po = out + cur_base + (long long)(hh * 16) * vox;
+                float* po = out + cur_base;
 #pragma unroll
                 for (int c = 0; c < 16; ++c) { *po = x1o[c] + __uint_as_float(d[c]) + par[kC + hh * 16 + c]; po += vox; }
             }

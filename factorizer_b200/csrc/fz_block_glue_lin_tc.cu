@@ -26,8 +26,8 @@ constexpr uint32_t oDY = 0;                   // dy atoms [hi | lo]
 constexpr uint32_t oXH = 2 * kAtom;           // xh atoms [hi | lo]
 constexpr uint32_t oW = 4 * kAtom;            // Wg as B(n = c, k = o), K-major: hi 4 KiB | lo 4 KiB
 constexpr uint32_t oPar = oW + 8192;          // gamma | beta | S of the CTA
-constexpr uint32_t oEx = oPar + 3 * kC * 4;   // exchange slots of the LayerNorm backward's partial sums: 2 x [half][128]
-constexpr uint32_t oBar = oEx + 2 * 256 * 4;  // bar_g | bar_wg
+constexpr uint32_t oEx = oPar + 3 * kC * 4;   // pair_sum2 slots: 2 x [half][128] float2
+constexpr uint32_t oBar = oEx + 2 * 256 * 8;  // bar_g | bar_wg
 constexpr uint32_t oTmem = oBar + 16;
 constexpr uint32_t kSmem = oTmem + 8;
 // TMEM columns: A = dy hi | lo, D = d(xh), contraction accumulator (64 rows x 64 columns)
@@ -103,8 +103,9 @@ linear_bwd_tc2(const float* __restrict__ dy, const float* __restrict__ a, const 
     long long nb = (long long)blockIdx.x / tiles_per_sample;
     int nt = (int)((long long)blockIdx.x - nb * tiles_per_sample);
     const long long my_tiles = blockIdx.x < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    constexpr int NA = LN ? kC : 16;          // channels of a this thread loads: all for the LayerNorm statistics, else its own
-    float gr[16], ar[NA];                     // the next tile's dy (own 16 channels) and a
+    float gr[16], ar[16];                     // the next tile's dy and a (own 16 channels)
+    float2* const slots = reinterpret_cast<float2*>(smem + oEx);
+    uint32_t turn = 0;
     float acc_s[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc_s[i] = 0.f;
@@ -118,31 +119,31 @@ linear_bwd_tc2(const float* __restrict__ dy, const float* __restrict__ a, const 
         while (nt >= tiles_per_sample) { nt -= tiles_per_sample; ++nb; }
         const long long own = base + (long long)(hh * 16) * vox;
         const float* pg = dy + own;
-        const float* pa = a + (LN ? base : own);
+        const float* pa = a + own;
 #pragma unroll
         for (int c = 0; c < 16; ++c) { gr[c] = valid ? __ldg(pg) : 0.f; pg += vox; }
 #pragma unroll
-        for (int c = 0; c < NA; ++c) { ar[c] = valid ? __ldg(pa) : 0.f; pa += vox; }
+        for (int c = 0; c < 16; ++c) { ar[c] = valid ? __ldg(pa) : 0.f; pa += vox; }
     };
     if (my_tiles > 0) fetch();
     uint32_t ph = 0;
     for (long long it = 0; it < my_tiles; ++it, ph ^= 1) {
         const bool cur_valid = valid;
         const long long cur_base = base;
-        // ---- LayerNorm statistics (both threads of a voxel), own channels of xh ----
+        // ---- LayerNorm statistics (the two threads of a voxel exchange their partial sums), own channels of xh ----
         float xh[16];
         float rstd = 1.f;
         if (LN) {
-            float mean = 0.f;
+            float sm = 0.f;
 #pragma unroll
-            for (int c = 0; c < kC; ++c) mean += ar[c];
-            mean *= (1.f / kC);
-            float var = 0.f;
+            for (int c = 0; c < 16; ++c) sm += ar[c];
+            const float mean = pair_sum2(make_float2(sm, 0.f), slots, turn, hh, vq, v).x * (1.f / kC);
+            float ss = 0.f;
 #pragma unroll
-            for (int c = 0; c < kC; ++c) { const float d = ar[c] - mean; var = fmaf(d, d, var); }
-            rstd = rsqrtf(var * (1.f / kC) + eps);
+            for (int c = 0; c < 16; ++c) { xh[c] = ar[c] - mean; ss = fmaf(xh[c], xh[c], ss); }
+            rstd = rsqrtf(pair_sum2(make_float2(ss, 0.f), slots, turn, hh, vq, v).x * (1.f / kC) + eps);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) xh[c] = ((hh ? ar[(16 + c) % NA] : ar[c]) - mean) * rstd;
+            for (int c = 0; c < 16; ++c) xh[c] *= rstd;
         } else {
 #pragma unroll
             for (int c = 0; c < 16; ++c) xh[c] = ar[c];
@@ -205,24 +206,19 @@ linear_bwd_tc2(const float* __restrict__ dy, const float* __restrict__ a, const 
         tc_fence_after();
         // ---- da ----
         if (LN) {
-            float d[32];
-            tmem_ld32(lane_addr + cD, d);
-            float m1 = 0.f, m2p = 0.f;
+            uint32_t du[16];
+            tmem_ld16_nowait(lane_addr + cD + hh * 16, du);
+            tmem_ld_wait();
+            float m1 = 0.f, m2 = 0.f;
 #pragma unroll
-            for (int c = 0; c < kC; ++c) m1 += d[c];
-#pragma unroll
-            for (int c = 0; c < 16; ++c) m2p = fmaf(hh ? d[16 + c] : d[c], xh[c], m2p);
-            // the other half of sum_c d(xh)_c xh_c lives in the thread that owns the voxel's other 16 channels
-            float* ex = reinterpret_cast<float*>(smem + oEx) + (it & 1) * 256;
-            ex[hh * 128 + v] = m2p;
-            asm volatile("bar.sync %0, 64;" :: "r"(1 + vq) : "memory");
-            const float m2 = (m2p + ex[(hh ^ 1) * 128 + v]) * (1.f / kC);
-            m1 *= (1.f / kC);
+            for (int c = 0; c < 16; ++c) { m1 += __uint_as_float(du[c]); m2 = fmaf(__uint_as_float(du[c]), xh[c], m2); }
+            const float2 m = pair_sum2(make_float2(m1, m2), slots, turn, hh, vq, v);
+            m1 = m.x * (1.f / kC); m2 = m.y * (1.f / kC);
             if (cur_valid) {
                 float* po = da + cur_base + (long long)(hh * 16) * vox;
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
-                    *po = rstd * ((hh ? d[16 + c] : d[c]) - m1 - xh[c] * m2) + rs[c];
+                    *po = rstd * (__uint_as_float(du[c]) - m1 - xh[c] * m2) + rs[c];
                     po += vox;
                 }
             }
