@@ -21,21 +21,24 @@ using namespace tc;
 constexpr int kC = 32;
 constexpr int kTM = 128;                  // voxels per tile
 constexpr int kThreads = 256;
-constexpr int kMaxHid = 64;
+constexpr int kSlice = 64;                // hidden units per GEMM pair; wider MLPs run slice by slice inside a tile
 
 // shared memory (bytes): weights hi | lo
-constexpr uint32_t oWo = 0;                               // W_out (32, 32) as B(n = o, k = c)
-constexpr uint32_t oW1 = oWo + 2 * kC * kC * 4;           // W1 (HID, 32)   as B(n = j, k = c)
-constexpr uint32_t oW2 = oW1 + 2 * kMaxHid * kC * 4;      // W2 (32, HID)   as B(n = o, k = j)
-constexpr uint32_t oPar = oW2 + 2 * kC * kMaxHid * 4;     // bout | b2 | gamma | beta | b1
-constexpr uint32_t oEx = oPar + (4 * kC + kMaxHid) * 4;   // pair_sum2 slots: 2 x [half][128] float2
-constexpr uint32_t oBar = oEx + 2 * 256 * 8;
-constexpr uint32_t oTmem = oBar + 8;
-constexpr uint32_t kSmem = oTmem + 8;
+template <int HID>
+struct FwdSmem {
+    static constexpr uint32_t oWo = 0;                               // W_out (32, 32) as B(n = o, k = c)
+    static constexpr uint32_t oW1 = oWo + 2 * kC * kC * 4;           // W1 (HID, 32)   as B(n = j, k = c)
+    static constexpr uint32_t oW2 = oW1 + 2 * HID * kC * 4;          // W2 (32, HID)   as B(n = o, k = j)
+    static constexpr uint32_t oPar = oW2 + 2 * kC * HID * 4;         // bout | b2 | gamma | beta | b1
+    static constexpr uint32_t oEx = oPar + (4 * kC + HID) * 4;       // pair_sum2 slots: 2 x [half][128] float2
+    static constexpr uint32_t oBar = oEx + 2 * 256 * 8;
+    static constexpr uint32_t oTmem = oBar + 8;
+    static constexpr uint32_t bytes = oTmem + 8;
+};
 
-// TMEM columns: D of out_proj, later of the output projection | hidden pre-activation, later gelu hi | A operand (m, then
-// LN(x1): hi 32 | lo 32; later gelu lo)
-constexpr uint32_t cD = 0, cHid = 32, cA = 96, kTmemCols = 256;
+// TMEM columns: D of out_proj, later of the output projection | hidden pre-activation of a slice, later its gelu hi |
+// A operand (m, then LN(x1): hi 32 | lo 32) | gelu lo of the slice
+constexpr uint32_t cD = 0, cHid = 32, cA = 96, cGlo = 160, kTmemCols = 256;
 
 template <int HID>
 __global__ void __launch_bounds__(kThreads, 2)
@@ -44,31 +47,33 @@ mixer_mlp_fwd_tc2(const float* __restrict__ x, const float* __restrict__ m, cons
                   const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
                   const float* __restrict__ b2, float* __restrict__ x1_out, float* __restrict__ out, long long vox,
                   int tiles_per_sample, long long total_tiles, float eps) {
+    using L = FwdSmem<HID>;
+    constexpr int NS = HID > kSlice ? kSlice : HID;      // hidden units per slice
     extern __shared__ __align__(1024) unsigned char smem[];
-    float* par = reinterpret_cast<float*>(smem + oPar);
+    float* par = reinterpret_cast<float*>(smem + L::oPar);
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t bar = sbase + oBar;
+    const uint32_t bar = sbase + L::oBar;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool issuer = uniform_u32((uint32_t)warp) == 0;
 
     for (int e = tid; e < kC * kC; e += kThreads) {
         const float w = Wout[e];
-        const uint32_t o = oWo + kmajor_off(e >> 5, e & 31, kC);
+        const uint32_t o = L::oWo + kmajor_off(e >> 5, e & 31, kC);
         *reinterpret_cast<float*>(smem + o) = w;
         *reinterpret_cast<float*>(smem + o + kC * kC * 4) = tf32_lo(w);
     }
     for (int e = tid; e < HID * kC; e += kThreads) {
         {
             const float w = W1[e];                            // (HID, 32)
-            const uint32_t o = oW1 + kmajor_off(e >> 5, e & 31, kC);
+            const uint32_t o = L::oW1 + kmajor_off(e >> 5, e & 31, kC);
             *reinterpret_cast<float*>(smem + o) = w;
-            *reinterpret_cast<float*>(smem + o + kMaxHid * kC * 4) = tf32_lo(w);
+            *reinterpret_cast<float*>(smem + o + HID * kC * 4) = tf32_lo(w);
         }
         {
             const float w = W2[e];                            // (32, HID)
-            const uint32_t o = oW2 + kmajor_off(e / HID, e % HID, HID);
+            const uint32_t o = L::oW2 + kmajor_off(e / HID, e % HID, HID);
             *reinterpret_cast<float*>(smem + o) = w;
-            *reinterpret_cast<float*>(smem + o + kC * kMaxHid * 4) = tf32_lo(w);
+            *reinterpret_cast<float*>(smem + o + kC * HID * 4) = tf32_lo(w);
         }
     }
     for (int c = tid; c < kC; c += kThreads) {
@@ -81,21 +86,21 @@ mixer_mlp_fwd_tc2(const float* __restrict__ x, const float* __restrict__ m, cons
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(sbase + oTmem), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(sbase + L::oTmem), "n"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = uniform_u32(*reinterpret_cast<const uint32_t*>(smem + oTmem));
+    const uint32_t tmem = uniform_u32(*reinterpret_cast<const uint32_t*>(smem + L::oTmem));
     const int vq = warp & 3, hh = warp >> 2;
     const int v = vq * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(vq * 32) << 16);
-    const uint32_t id32 = make_idesc(128, kC, false, false), idH = make_idesc(128, HID, false, false);
-    const uint64_t b_wo = make_desc(sbase + oWo, 128, kC * 32, 0);
-    const uint64_t b_w1 = make_desc(sbase + oW1, 128, kC * 32, 0);
-    const uint64_t b_w2 = make_desc(sbase + oW2, 128, HID * 32, 0);
+    const uint32_t id32 = make_idesc(128, kC, false, false), idH = make_idesc(128, NS, false, false);
+    const uint64_t b_wo = make_desc(sbase + L::oWo, 128, kC * 32, 0);
+    const uint64_t b_w1 = make_desc(sbase + L::oW1, 128, kC * 32, 0);
+    const uint64_t b_w2 = make_desc(sbase + L::oW2, 128, HID * 32, 0);
     uint32_t parity = 0;
 
     // (sample, tile of the sample) of the next fetch, advanced by the grid size
@@ -103,7 +108,7 @@ mixer_mlp_fwd_tc2(const float* __restrict__ x, const float* __restrict__ m, cons
     int nt = (int)((long long)blockIdx.x - nb * tiles_per_sample);
     const long long my_tiles = blockIdx.x < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     float mr[16], xr[16];                     // the next tile's m and x (own 16 channels)
-    float2* const slots = reinterpret_cast<float2*>(smem + oEx);
+    float2* const slots = reinterpret_cast<float2*>(smem + L::oEx);
     uint32_t turn = 0;
     bool valid = false;
     long long base = 0;
@@ -122,7 +127,7 @@ mixer_mlp_fwd_tc2(const float* __restrict__ x, const float* __restrict__ m, cons
     };
     // one GEMM D[cols d ..) = A[128 x K] W^T, A hi at TMEM columns a_hi .., lo at a_lo ..; issued by warp 0 once every thread has
     // published its part of A; every thread then waits for the result
-    auto gemm = [&](uint32_t d, uint32_t a_hi, uint32_t a_lo, uint64_t b, uint32_t b_lo_off, int K, uint32_t idesc) {
+    auto gemm = [&](uint32_t d, uint32_t a_hi, uint32_t a_lo, uint64_t b, uint32_t b_lo_off, int K, uint32_t idesc, bool acc0) {
         tmem_st_wait();
         tc_fence_before();
         __syncthreads();
@@ -131,7 +136,7 @@ mixer_mlp_fwd_tc2(const float* __restrict__ x, const float* __restrict__ m, cons
             if (elect_one()) {
 #pragma unroll
                 for (int s = 0; s < K / 8; ++s) {
-                    mma_tf32_ta(tmem + d, tmem + a_lo + s * 8, desc_at(b, s * 256), idesc, s > 0);
+                    mma_tf32_ta(tmem + d, tmem + a_lo + s * 8, desc_at(b, s * 256), idesc, acc0 || s > 0);
                     mma_tf32_ta(tmem + d, tmem + a_hi + s * 8, desc_at(b, b_lo_off + s * 256), idesc, 1);
                     mma_tf32_ta(tmem + d, tmem + a_hi + s * 8, desc_at(b, s * 256), idesc, 1);
                 }
@@ -158,7 +163,7 @@ mixer_mlp_fwd_tc2(const float* __restrict__ x, const float* __restrict__ m, cons
             tmem_st16(lane_addr + cA + hh * 16, th);
             tmem_st16(lane_addr + cA + 32 + hh * 16, tl);
         }
-        gemm(cD, cA, cA + 32, b_wo, kC * kC * 4, kC, id32);
+        gemm(cD, cA, cA + 32, b_wo, kC * kC * 4, kC, id32, false);
         float x1o[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) x1o[c] = xr[c];
@@ -194,30 +199,34 @@ mixer_mlp_fwd_tc2(const float* __restrict__ x, const float* __restrict__ m, cons
             tmem_st16(lane_addr + cA + hh * 16, th);
             tmem_st16(lane_addr + cA + 32 + hh * 16, tl);
         }
-        gemm(cHid, cA, cA + 32, b_w1, kMaxHid * kC * 4, kC, idH);
-        // fetch the next tile's m and x: in flight during the GELU and output phases
-        if (it + 1 < my_tiles) fetch();
-        wait_gemm();
-        // ---- A <- gelu(h) (own HID / 2 hidden units): hi over the pre-activation's columns, lo over the old A region ----
+#pragma unroll 1
+        for (int sl = 0; sl < HID / NS; ++sl) {
+            // hidden units NS sl .. + NS - 1: h = W1 LN(x1), then the output projection accumulates over the slices
+            gemm(cHid, cA, cA + 32, desc_at(b_w1, sl * NS * 128), HID * kC * 4, kC, idH, false);
+            // fetch the next tile's m and x: in flight during the GELU and output phases
+            if (sl == 0 && it + 1 < my_tiles) fetch();
+            wait_gemm();
+            // ---- A <- gelu(h) (own NS / 2 hidden units): hi over the pre-activation's columns, lo in its own columns ----
 #pragma unroll
-        for (int q = 0; q < HID / 32; ++q) {
-            uint32_t hr[16], gh[16], gl[16];
-            tmem_ld16_nowait(lane_addr + cHid + hh * (HID / 2) + q * 16, hr);
-            tmem_ld_wait();
+            for (int q = 0; q < NS / 32; ++q) {
+                uint32_t hr[16], gh[16], gl[16];
+                tmem_ld16_nowait(lane_addr + cHid + hh * (NS / 2) + q * 16, hr);
+                tmem_ld_wait();
 #pragma unroll
-            for (int p = 0; p < 16; p += 2) {
-                const float2 bj = *reinterpret_cast<const float2*>(par + 4 * kC + hh * (HID / 2) + q * 16 + p);
-                float2 e;
-                const float2 h2 = make_float2(__uint_as_float(hr[p]) + bj.x, __uint_as_float(hr[p + 1]) + bj.y);
-                const float2 g = __fmul2_rn(h2, gauss_cdf2(h2, e));
-                gh[p] = __float_as_uint(g.x); gh[p + 1] = __float_as_uint(g.y);
-                gl[p] = __float_as_uint(tf32_lo(g.x)); gl[p + 1] = __float_as_uint(tf32_lo(g.y));
+                for (int p = 0; p < 16; p += 2) {
+                    const float2 bj = *reinterpret_cast<const float2*>(par + 4 * kC + sl * NS + hh * (NS / 2) + q * 16 + p);
+                    float2 e;
+                    const float2 h2 = make_float2(__uint_as_float(hr[p]) + bj.x, __uint_as_float(hr[p + 1]) + bj.y);
+                    const float2 g = __fmul2_rn(h2, gauss_cdf2(h2, e));
+                    gh[p] = __float_as_uint(g.x); gh[p + 1] = __float_as_uint(g.y);
+                    gl[p] = __float_as_uint(tf32_lo(g.x)); gl[p + 1] = __float_as_uint(tf32_lo(g.y));
+                }
+                tmem_st16(lane_addr + cHid + hh * (NS / 2) + q * 16, gh);
+                tmem_st16(lane_addr + cGlo + hh * (NS / 2) + q * 16, gl);
             }
-            tmem_st16(lane_addr + cHid + hh * (HID / 2) + q * 16, gh);
-            tmem_st16(lane_addr + cA + hh * (HID / 2) + q * 16, gl);
+            gemm(cD, cHid, cGlo, desc_at(b_w2, sl * (NS / 4) * 128), kC * HID * 4, NS, id32, sl > 0);
+            wait_gemm();                 // before the next slice's pre-activation overwrites the gelu columns
         }
-        gemm(cD, cHid, cA, b_w2, kC * kMaxHid * 4, HID, id32);
-        wait_gemm();
         {
             uint32_t d[16];
             tmem_ld16_nowait(lane_addr + cD + hh * 16, d);
@@ -366,25 +375,35 @@ ln_linear_fwd_tc(const float* __restrict__ x, const float* __restrict__ gamma, c
 
 }  // namespace
 
-// hidden width 32 or 64 (mlp_ratio 1 or 2 at 32 channels)
-bool mixer_mlp_tc_supported(int hidden) { return hidden == 32 || hidden == 64; }
+// hidden width 32, 64, 128 or 256 (mlp_ratio 1, 2, 4, 8 at 32 channels)
+bool mixer_mlp_tc_supported(int hidden) { return hidden == 32 || hidden == 64 || hidden == 128 || hidden == 256; }
+
+template <int HID>
+static int launch_fwd(const float* x, const float* m, const float* Wout, const float* bout, const float* gamma, const float* beta,
+                      const float* W1, const float* b1, const float* W2, const float* b2, float* x1, float* out, long long batch,
+                      long long voxels, float eps, cudaStream_t st) {
+    static SmemConfig cfg;
+    FZ_CUDA_CHECK(cfg.ensure(mixer_mlp_fwd_tc2<HID>, FwdSmem<HID>::bytes));
+    const int tps = (int)((voxels + kTM - 1) / kTM);
+    const long long tiles = batch * tps;
+    const long long cap = (FwdSmem<HID>::bytes > 110 * 1024 ? 1LL : 2LL) * num_sms();
+    const unsigned blocks = (unsigned)(tiles < cap ? tiles : cap);
+    mixer_mlp_fwd_tc2<HID><<<blocks, kThreads, FwdSmem<HID>::bytes, st>>>(x, m, Wout, bout, gamma, beta, W1, b1, W2, b2, x1, out, voxels,
+                                                                          tps, tiles, eps);
+    FZ_LAUNCH_CHECK();
+    return FZ_OK;
+}
 
 int mixer_mlp_tc_launch(const float* x, const float* m, const float* Wout, const float* bout, const float* gamma, const float* beta,
                         const float* W1, const float* b1, const float* W2, const float* b2, float* x1, float* out, long long batch,
                         int hidden, long long voxels, float eps, cudaStream_t st) {
-    static SmemConfig cfg32, cfg64;
-    FZ_CUDA_CHECK(cfg32.ensure(mixer_mlp_fwd_tc2<32>, kSmem));
-    FZ_CUDA_CHECK(cfg64.ensure(mixer_mlp_fwd_tc2<64>, kSmem));
-    const int tps = (int)((voxels + kTM - 1) / kTM);
-    const long long tiles = batch * tps;
-    const long long cap = 2LL * num_sms();
-    const unsigned blocks = (unsigned)(tiles < cap ? tiles : cap);
-    if (hidden == 64)
-        mixer_mlp_fwd_tc2<64><<<blocks, kThreads, kSmem, st>>>(x, m, Wout, bout, gamma, beta, W1, b1, W2, b2, x1, out, voxels, tps, tiles, eps);
-    else
-        mixer_mlp_fwd_tc2<32><<<blocks, kThreads, kSmem, st>>>(x, m, Wout, bout, gamma, beta, W1, b1, W2, b2, x1, out, voxels, tps, tiles, eps);
-    FZ_LAUNCH_CHECK();
-    return FZ_OK;
+    switch (hidden) {
+        case 32: return launch_fwd<32>(x, m, Wout, bout, gamma, beta, W1, b1, W2, b2, x1, out, batch, voxels, eps, st);
+        case 64: return launch_fwd<64>(x, m, Wout, bout, gamma, beta, W1, b1, W2, b2, x1, out, batch, voxels, eps, st);
+        case 128: return launch_fwd<128>(x, m, Wout, bout, gamma, beta, W1, b1, W2, b2, x1, out, batch, voxels, eps, st);
+        case 256: return launch_fwd<256>(x, m, Wout, bout, gamma, beta, W1, b1, W2, b2, x1, out, batch, voxels, eps, st);
+    }
+    return fail(FZ_ERR_UNSUPPORTED, "tensor-core MLP forward: hidden width %d", hidden);
 }
 
 }  // namespace fz

@@ -299,7 +299,7 @@ def glue_mode(request):
     lib.fz_set_glue_mode(before)
 
 
-@pytest.mark.parametrize("HID", [32, 48, 64, 128, 136])
+@pytest.mark.parametrize("HID", [32, 48, 64, 128, 136, 256])
 @pytest.mark.parametrize("shape", [(1, 32, 8, 8, 8), (2, 32, 6, 10, 7), (3, 32, 1030), (2, 32, 30002)])
 def test_glue_kernels_against_torch_fp64(ft, dev, shape, HID, glue_mode):
     """Each kernel of csrc/fz_block_glue*.cu through the C ABI against fp64 torch autograd of the same
