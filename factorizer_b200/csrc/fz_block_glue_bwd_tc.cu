@@ -500,8 +500,11 @@ int mlp_bwd_tc_launch(const float* x1, const float* dout, const float* gamma, co
     FZ_CUDA_CHECK(cfg.ensure(mlp_bwd_tc, kSmem));
     const int tps = (int)((voxels + kTV - 1) / kTV);
     const long long tiles = batch * tps;
-    const long long cap = num_sms();
-    const unsigned blocks = (unsigned)(tiles < cap ? tiles : cap);
+    // one persistent CTA per SM; beyond 192 tiles per CTA more CTAs instead: the tensor core accumulates with truncation, so the
+    // error of the weight gradients' TMEM accumulation chains grows with their length (fz_linear_tc.cu)
+    long long nblk = tiles < num_sms() ? tiles : num_sms();
+    if (nblk * 192 < tiles) nblk = (tiles + 191) / 192;
+    const unsigned blocks = (unsigned)nblk;
     for (int h0 = 0; h0 < hidden; h0 += kH) {
         mlp_bwd_tc<<<blocks, kThreads, kSmem, st>>>(x1, dout, gamma, beta, W1 + (size_t)h0 * kC, b1 ? b1 + h0 : nullptr, W2 + h0, dx1,
                                                     dgamma, dbeta, dW1 + (size_t)h0 * kC, db1 ? db1 + h0 : nullptr, dW2 + h0,

@@ -304,8 +304,11 @@ int linear_bwd_tc2_launch(const float* dy, const float* a, const float* gamma, c
     FZ_CUDA_CHECK(cfg_plain.ensure(linear_bwd_tc2<false>, kSmem));
     const int tps = (int)((voxels + kTM - 1) / kTM);
     const long long tiles = batch * tps;
-    const long long cap = 2LL * num_sms();
-    const unsigned blocks = (unsigned)(tiles < cap ? tiles : cap);
+    // two persistent CTAs per SM; beyond 128 tiles per CTA more CTAs instead (length of the TMEM accumulation chain of the
+    // weight gradient: fz_linear_tc.cu)
+    long long nblk = tiles < 2LL * num_sms() ? tiles : 2LL * num_sms();
+    if (nblk * 128 < tiles) nblk = (tiles + 127) / 128;
+    const unsigned blocks = (unsigned)nblk;
     if (layernorm)
         linear_bwd_tc2<true><<<blocks, kThreads, kSmem, st>>>(dy, a, gamma, beta, W, resid, da, dW, db, dgamma, dbeta, voxels, tps, tiles, eps);
     else

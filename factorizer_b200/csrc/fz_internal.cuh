@@ -79,6 +79,11 @@ int linear_bwd_tc2_launch(const float* dy, const float* a, const float* gamma, c
                           float* da, float* dW, float* db, float* dgamma, float* dbeta, long long batch, long long voxels, float eps,
                           int layernorm, cudaStream_t st);
 
+// fz_linear_tc.cu: weight gradient of a pointwise channel map on tcgen05 (any channel counts); the caller zeroes dW / db
+bool linear_wgrad_tc_supported(const float* dy, const float* x, long long batch, int cout, int cin, long long voxels);
+int linear_wgrad_tc_launch(const float* dy, const float* x, float* dW, float* db, long long batch, int cout, int cin, long long voxels,
+                           cudaStream_t st);
+
 // fz_block_glue_bwd_tc.cu: tcgen05 / TMEM version of the MLP + norm2 backward kernel (hidden width a multiple of 64, 3xTF32); the caller
 // zeroes the gradients
 bool mlp_bwd_tc_supported(int hidden);

@@ -361,6 +361,9 @@ int fz_linear_wgrad(const float* dy, const float* x, float* dW, float* db, int64
     if (db) FZ_CUDA_CHECK(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)cout, st));
     if (batch == 0) return FZ_OK;
     if (!dy || !x) return fail(FZ_ERR_INVALID, "linear wgrad: null buffer");
+    // tensor-core path (csrc/fz_linear_tc.cu: TMA-fed K-major operands, 3xTF32) unless the calling thread asked for the FP32 pipe
+    if ((tls().glue_mode & 2) && batch * voxels >= 4096 && linear_wgrad_tc_supported(dy, x, batch, cout, cin, voxels))
+        return linear_wgrad_tc_launch(dy, x, dW, db, batch, cout, cin, voxels, st);
     int dev = 0, sms = 148;
     FZ_CUDA_CHECK(cudaGetDevice(&dev));
     FZ_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
