@@ -505,15 +505,33 @@ def linear_wgrad_supported(x: torch.Tensor, out_channels: int, min_voxels: int =
     return bool(L.lib().fz_linear_wgrad_supported(int(out_channels), x.shape[1] if rows is None else int(rows), vox))
 
 
+def linear_forward(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """y = W x (+ b) for x (B, C_in, voxels): the tcgen05 channel-map kernel (csrc/fz_linear_tc.cu, 3xTF32) where its shape
+    restrictions hold and the GEMM is large enough to pay, else the library's batched GEMM."""
+    B, cin, vox = x.shape
+    cout = weight.shape[0]
+    lib = L.lib()
+    if (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and B * vox >= 4096 and cin >= 32 and cout >= 16
+            and lib.fz_get_glue_mode() & 1 and lib.fz_linear_forward_supported(cout, cin, vox) and x.data_ptr() % 16 == 0):
+        w = weight.contiguous()
+        if w.data_ptr() % 16 == 0:
+            b = None if bias is None else L.require_cuda_f32(bias, "bias")
+            y = torch.empty(B, cout, vox, device=x.device, dtype=torch.float32)
+            with torch.cuda.device(x.device):
+                _call(lib.fz_linear_forward, L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), B, cin, cout, vox, L.stream_ptr(x.device))
+            return y
+    wb = weight.unsqueeze(0).expand(B, -1, -1)
+    return torch.bmm(wb, x) if bias is None else torch.baddbmm(bias[None, :, None], wb, x)
+
+
 class LinearCF(torch.autograd.Function):
     """y = W x (+ b) over the channel axis of a (B, C_in, voxels) tensor (reference factorizer/layers/linear.py:53-58).
-    Forward and input gradient are cuBLAS GEMMs; the weight / bias gradients come from csrc/fz_linear.cu."""
+    Forward and input gradient: the tcgen05 channel-map kernel (linear_forward above; the library GEMM for small shapes);
+    the weight / bias gradients: csrc/fz_linear_tc.cu / fz_linear.cu."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
-        B = x.shape[0]
-        wb = weight.unsqueeze(0).expand(B, -1, -1)
-        y = torch.bmm(wb, x) if bias is None else torch.baddbmm(bias[None, :, None], wb, x)
+        y = linear_forward(x, weight, bias)
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
         return y
@@ -528,7 +546,7 @@ class LinearCF(torch.autograd.Function):
         cout = weight.shape[0]
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = torch.bmm(weight.t().unsqueeze(0).expand(B, -1, -1), gy)
+            gx = linear_forward(gy.contiguous(), weight.t().contiguous(), None)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             gw = torch.empty(weight.shape, device=x.device, dtype=torch.float32)     # row-major whatever the weight's strides
             gb = torch.empty(cout, device=x.device, dtype=torch.float32) if ctx.has_bias else None

@@ -84,6 +84,10 @@ bool linear_wgrad_tc_supported(const float* dy, const float* x, long long batch,
 int linear_wgrad_tc_launch(const float* dy, const float* x, float* dW, float* db, long long batch, int cout, int cin, long long voxels,
                            cudaStream_t st);
 
+bool linear_fwd_tc_supported(const float* x, const float* W, long long batch, int cout, int cin, long long voxels);
+int linear_fwd_tc_launch(const float* x, const float* W, const float* bias, float* y, long long batch, int cout, int cin,
+                         long long voxels, cudaStream_t st);
+
 // fz_block_glue_bwd_tc.cu: tcgen05 / TMEM version of the MLP + norm2 backward kernel (hidden width a multiple of 64, 3xTF32); the caller
 // zeroes the gradients
 bool mlp_bwd_tc_supported(int hidden);

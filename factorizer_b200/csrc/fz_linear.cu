@@ -404,6 +404,22 @@ int fz_linear_wgrad(const float* dy, const float* x, float* dW, float* db, int64
     return FZ_OK;
 }
 
+int fz_linear_forward_supported(int32_t cout, int32_t cin, int64_t voxels) {
+    return cout > 0 && cin > 0 && cin % 4 == 0 && voxels > 0 && voxels % 4 == 0 && voxels < (1LL << 31);
+}
+
+int fz_linear_forward(const float* x, const float* W, const float* bias, float* y, int64_t batch, int32_t cin, int32_t cout,
+                      int64_t voxels, void* stream) {
+    tls().launches = 0;
+    if (batch < 0 || cout <= 0 || cin <= 0 || voxels <= 0) return fail(FZ_ERR_INVALID, "linear forward: bad sizes");
+    if (batch == 0) return FZ_OK;
+    if (!x || !W || !y) return fail(FZ_ERR_INVALID, "linear forward: null buffer");
+    if (!fz_linear_forward_supported(cout, cin, voxels) || !linear_fwd_tc_supported(x, W, batch, cout, cin, voxels))
+        return fail(FZ_ERR_UNSUPPORTED, "linear forward kernel needs voxels and input channels divisible by 4 and 16-byte aligned "
+                                        "buffers (got %d x %d x %lld)", cout, cin, (long long)voxels);
+    return linear_fwd_tc_launch(x, W, bias, y, batch, cout, cin, voxels, (cudaStream_t)stream);
+}
+
 int fz_space_depth2_supported(int32_t D, int32_t H, int32_t W) {
     return D > 0 && H > 0 && W > 0 && D % 2 == 0 && H % 2 == 0 && W % 4 == 0;
 }

@@ -202,6 +202,237 @@ linear_wgrad_tc(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem) : "memory");
 }
 
+// =====================================================================================================================
+// y[b][o][v] = sum_c W[o][c] x[b][c][v] (+ bias[o]): the channel map itself, any channel counts (the wide blocks' linears and
+// MLPs, the patch convolutions on their space-to-depth view; with W^T it is the input gradient).  3xTF32 on tcgen05:
+//   D[128 voxels x 64 outputs] += A[128 x 32 channels] B[64 x 32]^T per K chunk,
+// A = x, voxel-contiguous = MN-major: TMA boxes of (32 channels x 32 voxels) with SWIZZLE_128B_ATOM_32B are exactly the atoms
+// of the one swizzle 32-bit MN-major operands accept; B = W, K-major, SWIZZLE_128B boxes as in the weight-gradient kernel.
+// The fp32 tiles are the hi operands; eight warps write the remainder tiles and later run the epilogue (thread = voxel = TMEM
+// lane: bias, coalesced stores along the voxel axis).  Persistent CTAs walk (voxel tile, output tile) items; K chunks flow
+// through a two-stage TMA -> remainder -> MMA pipeline that runs across items.  The tensor core adds into its accumulator with
+// truncation, so a long accumulation chain loses accuracy (1.4e-5 after the 192 MMAs of 512 input channels): an item is cut
+// into SEGMENTS of 4 K chunks, the a_hi b_hi products (16 MMAs per segment) and the two cross terms go to separate accumulators,
+// and the workers add the segments up in registers (round to nearest).  The accumulator pair is double-buffered in TMEM, so
+// draining a segment overlaps the MMAs of the next one.  Warp 0 = TMA producer, warp 1 = MMA issue, warps 2-9 workers.
+// =====================================================================================================================
+constexpr int kGM = 128, kGN = 64, kGK = 32;         // voxels x outputs per item, channels per K chunk
+constexpr int kGStages = 2;
+constexpr int kGSeg = 4;                              // K chunks per accumulation segment
+constexpr int kGThreads = 320;
+constexpr uint32_t kGA = kGK * kGM * 4;              // x chunk: 4 atoms of (32 channels x 32 voxels) = 16 KiB
+constexpr uint32_t kGB = kGN * kGK * 4;              // W chunk: 64 rows x 128 bytes = 8 KiB
+constexpr uint32_t gA = 0, gAlo = kGA, gB = 2 * kGA, gBlo = 2 * kGA + kGB, kGStage = 2 * kGA + 2 * kGB;   // 48 KiB
+constexpr uint32_t gBarFull = kGStages * kGStage, gBarLo = gBarFull + 8 * kGStages, gBarEmpty = gBarLo + 8 * kGStages,
+                   gBarAccFull = gBarEmpty + 8 * kGStages, gBarAccFree = gBarAccFull + 16, gTmemSlot = gBarAccFree + 16,
+                   kGSmem = gTmemSlot + 8;
+
+// x as (batch, channels, voxels): box (1, 32, 32), the 128-byte rows swizzled in 32-byte atoms
+int make_map_x(CUtensorMap* m, const float* ptr, long long batch, int channels, long long voxels) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return fail(FZ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {(cuuint64_t)voxels, (cuuint64_t)channels, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)voxels * 4, (cuuint64_t)voxels * channels * 4};
+    cuuint32_t box[3] = {32, kGK, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FZ_ERR_CUDA, "cuTensorMapEncodeTiled (x) failed with CUresult %d", (int)r);
+    return FZ_OK;
+}
+// W as (outputs, inputs) row-major: box (64 outputs, 32 inputs)
+int make_map_w(CUtensorMap* m, const float* ptr, int cout, int cin) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return fail(FZ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {(cuuint64_t)cin, (cuuint64_t)cout};
+    cuuint64_t strides[1] = {(cuuint64_t)cin * 4};
+    cuuint32_t box[2] = {kGK, kGN};
+    cuuint32_t es[2] = {1, 1};
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FZ_ERR_CUDA, "cuTensorMapEncodeTiled (W) failed with CUresult %d", (int)r);
+    return FZ_OK;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+
+__global__ void __launch_bounds__(kGThreads, 2)
+linear_fwd_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias,
+              float* __restrict__ y, int cout, int cin, long long vox, int vtiles_per_sample, int otiles, long long total_items) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = (int)uniform_u32((uint32_t)(tid >> 5));
+    const long long my_items = blockIdx.x < total_items ? (total_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int kchunks = (cin + kGK - 1) / kGK;
+
+    if (tid == 0) {
+        for (int s = 0; s < kGStages; ++s) {
+            bar_init(sbase + gBarFull + 8 * s, 1);
+            bar_init(sbase + gBarLo + 8 * s, 8);
+            bar_init(sbase + gBarEmpty + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            bar_init(sbase + gBarAccFull + 8 * a, 1);
+            bar_init(sbase + gBarAccFree + 8 * a, 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" :: "r"(sbase + gTmemSlot) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = uniform_u32(*reinterpret_cast<const uint32_t*>(smem + gTmemSlot));
+
+    if (warp == 0) {
+        // ---- TMA producer: items in the order (voxel tile, output tile): neighbouring CTAs share the x tile in L2 ----
+        if (elect_one()) {
+            long long g = 0;
+            for (long long it = 0; it < my_items; ++it) {
+                const long long item = blockIdx.x + it * gridDim.x;
+                const int ot = (int)(item % otiles);
+                const long long vt_all = item / otiles;
+                const int b = (int)(vt_all / vtiles_per_sample);
+                const int v0 = (int)(vt_all - (long long)b * vtiles_per_sample) * kGM;
+                for (int kc = 0; kc < kchunks; ++kc, ++g) {
+                    const int s = (int)(g % kGStages);
+                    const uint32_t round = (uint32_t)(g / kGStages);
+                    if (round > 0) bar_wait(sbase + gBarEmpty + 8 * s, (round - 1) & 1);
+                    const uint32_t full = sbase + gBarFull + 8 * s, st = sbase + s * kGStage;
+                    bar_expect_tx(full, kGA + kGB);
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) tma_load_3d(st + gA + a * (kGA / 4), &map_x, full, v0 + 32 * a, kc * kGK, b);
+                    tma_load_2d(st + gB, &map_w, full, kc * kGK, ot * kGN);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ---- MMA issue ----
+        const uint32_t idesc = make_idesc(128, kGN, true, false);          // A MN-major, B K-major
+        long long g = 0, seg = 0;
+        for (long long it = 0; it < my_items; ++it) {
+            for (int kc = 0; kc < kchunks; ++kc, ++g) {
+                const int ks = kc % kGSeg;                                 // position inside the segment
+                const uint32_t acc = (uint32_t)(seg & 1), use = (uint32_t)(seg >> 1);
+                if (ks == 0) {
+                    if (use > 0) bar_wait(sbase + gBarAccFree + 8 * acc, (use - 1) & 1);      // the workers have drained this pair
+                    tc_fence_after();
+                }
+                const int s = (int)(g % kGStages);
+                const uint32_t round = (uint32_t)(g / kGStages);
+                bar_wait(sbase + gBarLo + 8 * s, round & 1);
+                tc_fence_after();
+                const bool seg_end = ks + 1 == kGSeg || kc + 1 == kchunks;
+                if (elect_one()) {
+                    const uint32_t st = sbase + s * kGStage;
+                    const uint64_t a_hi = make_desc(st + gA, kGA / 4, 512, 1), a_lo = make_desc(st + gAlo, kGA / 4, 512, 1);
+                    const uint64_t b_hi = make_desc(st + gB, 16, 1024, 2), b_lo = make_desc(st + gBlo, 16, 1024, 2);
+                    const uint32_t d_main = tmem + acc * (2 * kGN), d_cross = d_main + kGN;
+#pragma unroll
+                    for (int k = 0; k < kGK / 8; ++k) {
+                        mma_tf32(d_cross, desc_at(a_lo, k * 1024), desc_at(b_hi, k * 32), idesc, ks > 0 || k > 0);
+                        mma_tf32(d_cross, desc_at(a_hi, k * 1024), desc_at(b_lo, k * 32), idesc, 1);
+                        mma_tf32(d_main, desc_at(a_hi, k * 1024), desc_at(b_hi, k * 32), idesc, ks > 0 || k > 0);
+                    }
+                    commit(sbase + gBarEmpty + 8 * s);
+                    if (seg_end) commit(sbase + gBarAccFull + 8 * acc);
+                }
+                __syncwarp();
+                if (seg_end) ++seg;
+            }
+        }
+    } else {
+        // ---- workers: remainder tiles of every K chunk; a finished segment is drained after the first chunk of the next one ----
+        const int t = tid - 64;                                            // 0 .. 255
+        const int wq = warp & 3, wh = (warp - 2) >> 2;                     // TMEM lane quarter this warp may read; half of the columns
+        const int spi = (kchunks + kGSeg - 1) / kGSeg;                     // segments per item
+        float sum[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sum[i] = 0.f;
+        auto drain = [&](long long seg) {
+            const uint32_t acc = (uint32_t)(seg & 1), use = (uint32_t)(seg >> 1);
+            bar_wait(sbase + gBarAccFull + 8 * acc, use & 1);
+            tc_fence_after();
+            const uint32_t ta = tmem + ((uint32_t)(wq * 32) << 16) + acc * (2 * kGN) + wh * 32;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t dm[16], dc[16];
+                tmem_ld16_nowait(ta + h * 16, dm);
+                tmem_ld16_nowait(ta + kGN + h * 16, dc);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) sum[h * 16 + i] += __uint_as_float(dm[i]) + __uint_as_float(dc[i]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) bar_arrive(sbase + gBarAccFree + 8 * acc);
+            if (seg % spi == spi - 1) {                                    // the item's last segment: bias, store, start over
+                const long long it = seg / spi;
+                const long long item = blockIdx.x + it * gridDim.x;
+                const int ot = (int)(item % otiles);
+                const long long vt_all = item / otiles;
+                const long long b = vt_all / vtiles_per_sample;
+                const long long v = (vt_all - b * vtiles_per_sample) * kGM + wq * 32 + lane;
+                if (v < vox) {
+                    const int o0 = ot * kGN + wh * 32;
+                    float* py = y + (b * cout + o0) * vox + v;
+#pragma unroll
+                    for (int o = 0; o < 32; ++o) {
+                        if (o0 + o < cout) *py = sum[o] + (bias ? __ldg(bias + o0 + o) : 0.f);
+                        py += vox;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sum[i] = 0.f;
+            }
+        };
+        long long g = 0, seg = 0;                                          // seg: the segment the current chunk belongs to
+        for (long long it = 0; it < my_items; ++it) {
+            for (int kc = 0; kc < kchunks; ++kc, ++g) {
+                const int s = (int)(g % kGStages);
+                const uint32_t round = (uint32_t)(g / kGStages);
+                bar_wait(sbase + gBarFull + 8 * s, round & 1);
+                unsigned char* st = smem + s * kGStage;
+                {
+                    const float4* hi = reinterpret_cast<const float4*>(st + gA);
+                    float4* lo = reinterpret_cast<float4*>(st + gAlo);
+#pragma unroll
+                    for (int i = 0; i < (int)(kGA / 16) / 256; ++i) {
+                        const float4 v4 = hi[i * 256 + t];
+                        lo[i * 256 + t] = make_float4(tf32_lo(v4.x), tf32_lo(v4.y), tf32_lo(v4.z), tf32_lo(v4.w));
+                    }
+                }
+                {
+                    const float4* hi = reinterpret_cast<const float4*>(st + gB);
+                    float4* lo = reinterpret_cast<float4*>(st + gBlo);
+#pragma unroll
+                    for (int i = 0; i < (int)(kGB / 16) / 256; ++i) {
+                        const float4 v4 = hi[i * 256 + t];
+                        lo[i * 256 + t] = make_float4(tf32_lo(v4.x), tf32_lo(v4.y), tf32_lo(v4.z), tf32_lo(v4.w));
+                    }
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) bar_arrive(sbase + gBarLo + 8 * s);
+                if (kc % kGSeg == 0 && seg > 0) drain(seg - 1);            // the previous segment, now that this one is under way
+                if (kc % kGSeg == kGSeg - 1 || kc + 1 == kchunks) ++seg;
+            }
+        }
+        if (seg > 0) drain(seg - 1);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem) : "memory");
+}
+
 }  // namespace
 
 bool linear_wgrad_tc_supported(const float* dy, const float* x, long long batch, int cout, int cin, long long voxels) {
@@ -233,4 +464,28 @@ int linear_wgrad_tc_launch(const float* dy, const float* x, float* dW, float* db
     return FZ_OK;
 }
 
+}  // namespace fz
+
+namespace fz {
+bool linear_fwd_tc_supported(const float* x, const float* W, long long batch, int cout, int cin, long long voxels) {
+    return voxels % 4 == 0 && cin % 4 == 0 && voxels < (1LL << 31) && batch < (1LL << 31) && cout > 0 && cin > 0 &&
+           ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(W)) & 15) == 0;
+}
+
+int linear_fwd_tc_launch(const float* x, const float* W, const float* bias, float* y, long long batch, int cout, int cin,
+                         long long voxels, cudaStream_t st) {
+    CUtensorMap map_x, map_w;
+    if (int e = make_map_x(&map_x, x, batch, cin, voxels)) return e;
+    if (int e = make_map_w(&map_w, W, cout, cin)) return e;
+    static SmemConfig cfg;
+    FZ_CUDA_CHECK(cfg.ensure(linear_fwd_tc, kGSmem));
+    const int vtps = (int)((voxels + kGM - 1) / kGM);
+    const int otiles = (cout + kGN - 1) / kGN;
+    const long long items = batch * vtps * otiles;
+    const long long cap = 2LL * num_sms();
+    const unsigned blocks = (unsigned)(items < cap ? items : cap);
+    linear_fwd_tc<<<blocks, kGThreads, kGSmem, st>>>(map_x, map_w, bias, y, cout, cin, voxels, vtps, otiles, items);
+    FZ_LAUNCH_CHECK();
+    return FZ_OK;
+}
 }  // namespace fz

@@ -36,7 +36,10 @@ class Linear(nn.Module):
         if torch.is_grad_enabled() and w.requires_grad and xf.is_contiguous() and _ops.linear_wgrad_supported(xf, w.shape[0]):
             # long contractions over voxels: hand-written weight-gradient kernel (csrc/fz_linear.cu)
             return _ops.LinearCF.apply(xf, w, self.linear.bias).view(shape[0], -1, *shape[2:])
-        if self.linear.bias is not None:
+        if xf.is_cuda and xf.dtype == torch.float32 and not torch.is_autocast_enabled() and not (torch.is_grad_enabled() and (w.requires_grad or xf.requires_grad)):
+            # inference: the same kernel choice as the differentiable path (tcgen05 channel map where it applies)
+            y = _ops.linear_forward(xf.contiguous(), w, self.linear.bias)
+        elif self.linear.bias is not None:
             y = torch.baddbmm(self.linear.bias[None, :, None], w.unsqueeze(0).expand(shape[0], -1, -1), xf)
         else:
             y = torch.bmm(w.unsqueeze(0).expand(shape[0], -1, -1), xf)

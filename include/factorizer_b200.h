@@ -160,6 +160,15 @@ int fz_linear_wgrad_supported(int32_t cout, int32_t cin, int64_t voxels);
 int fz_linear_wgrad(const float* dy, const float* x, float* dW, float* db, int64_t batch, int32_t cout, int32_t cin,
                     int64_t voxels, void* stream);
 
+/* ---- the pointwise channel map itself (reference factorizer/layers/linear.py:53-58) on the tensor cores ----
+ * y[b][o][v] = sum_i W[o][i] x[b][i][v] + bias[o]   (bias may be NULL); x is (batch, cin, voxels), y (batch, cout, voxels),
+ * W (cout, cin) row-major, fp32 contiguous.  With W^T (cin, cout) and dy in place of x it is the input gradient.  3xTF32 on
+ * tcgen05 (fp32 parity), for the wide stages whose library SGEMMs run on the FP32 pipe.  voxels and cin must be multiples of
+ * 4, the pointers 16-byte aligned: fz_linear_forward_supported() tells. */
+int fz_linear_forward_supported(int32_t cout, int32_t cin, int64_t voxels);
+int fz_linear_forward(const float* x, const float* W, const float* bias, float* y, int64_t batch, int32_t cin, int32_t cout,
+                      int64_t voxels, void* stream);
+
 /* (batch, channels, D, H, W) <-> (batch, channels*8, D/2*H/2*W/2) with rows ordered (c, kd, kh, kw): the view on which
  * the reference U-Net's kernel-2 stride-2 down-sampling convolution (factorizer/unet.py:53) and transposed up-sampling
  * convolution (unet.py:97-99) are channel maps.  to_depth != 0: full resolution -> patch rows; 0: the inverse.

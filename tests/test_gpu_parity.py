@@ -520,6 +520,29 @@ def test_linear_weight_gradient_kernel(ft, dev, shape, cout, bias):
     assert not _ops.linear_wgrad_supported(torch.randn(1, 48, 31, 31, 31, device=dev).flatten(2), 40)
 
 
+@pytest.mark.parametrize("B,cin,cout,vox,bias", [(1, 64, 64, 4096, True), (2, 96, 40, 8200, True), (1, 512, 512, 516, False),
+                                                 (3, 40, 200, 1028, True), (1, 32, 3, 32768, True), (2, 256, 128, 4100, False),
+                                                 (1, 4, 16, 64, True), (1, 136, 72, 260, True)])
+def test_channel_map_tensor_core_kernel(ft, dev, B, cin, cout, vox, bias):
+    """fz_linear_forward (csrc/fz_linear_tc.cu: tcgen05, 3xTF32, segmented accumulation) through the C ABI against the
+    reference's formulation (a k=1 Conv1d, layers/linear.py:53-58) in fp64: ragged voxel tiles, channel counts that are not
+    multiples of the K chunk / output tile, several samples, long K (512 channels = 48 accumulation steps per accumulator)."""
+    from factorizer_b200 import _lib as L
+    lib = L.lib()
+    torch.manual_seed(11)
+    x = torch.randn(B, cin, vox, device=dev)
+    W = torch.randn(cout, cin, device=dev) / cin ** 0.5
+    b = torch.randn(cout, device=dev) if bias else None
+    y = torch.full((B, cout, vox), float("nan"), device=dev)
+    assert lib.fz_linear_forward_supported(cout, cin, vox)
+    L.check(lib.fz_linear_forward(x.data_ptr(), W.data_ptr(), b.data_ptr() if bias else None, y.data_ptr(), B, cin, cout, vox,
+                                  torch.cuda.current_stream().cuda_stream))
+    ref = torch.nn.functional.conv1d(x.double(), W.double().unsqueeze(-1), b.double() if bias else None)
+    assert_close(_np(y), _np(ref), what="y")
+    assert not lib.fz_linear_forward_supported(cout, cin, vox + 2)
+    assert not lib.fz_linear_forward_supported(cout, cin + 1, vox)
+
+
 @pytest.mark.parametrize("nd,cin,cout,k,size,bias", [(3, 32, 64, 2, (32, 32, 32), True), (3, 4, 3, 1, (32, 32, 16), True),
                                                      (3, 24, 40, 2, (16, 32, 64), False), (2, 32, 64, 2, (128, 128), True),
                                                      (3, 8, 16, (2, 1, 2), (32, 16, 32), True), (3, 8, 8, 2, (12, 8, 6), True),
