@@ -6,5 +6,6 @@ from .operations import *  # noqa: F401,F403
 from .matrix_factorization import *  # noqa: F401,F403
 from .factorizer import *  # noqa: F401,F403
 from .segmentation import *  # noqa: F401,F403
+from . import distributed  # noqa: F401
 
 __version__ = "0.1.0"
