@@ -61,6 +61,8 @@ _SIGNATURES = {
     "fz_linear_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int64, c_void_p]),
     "fz_linear_forward_supported": (c_int, [c_int32, c_int32, c_int64]),
     "fz_linear_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int64, c_void_p]),
+    "fz_linear_forward_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int64, c_int32, c_void_p,
+                                     c_void_p, c_void_p]),
     "fz_conv3d_stem_supported": (c_int, [c_int32, c_int32, c_int32, c_int32, c_int32]),
     "fz_conv3d_stem_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "fz_space_depth2_supported": (c_int, [c_int32, c_int32, c_int32]),
@@ -69,6 +71,8 @@ _SIGNATURES = {
     "fz_layernorm_cf_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_float, c_void_p]),
     "fz_layernorm_cf_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                                          c_int64, c_float, c_void_p]),
+    "fz_layernorm_cf_backward_add": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
+                                             c_int64, c_float, c_void_p]),
     "fz_set_glue_mode": (None, [c_int32]),
     "fz_get_glue_mode": (c_int, []),
     "fz_glue_supported": (c_int, [c_int32, c_int32, c_int64]),

@@ -407,6 +407,137 @@ class FactorizerBlockFn(_GradModeFunction):
                 None, None, None, None, None, None)
 
 
+# ---- FactorizerBlock of any width: channel-map kernels with fused epilogues around the fused core ------------------
+EPI_NONE, EPI_RESIDUAL, EPI_GELU, EPI_GELU_GRAD = 0, 1, 2, 3
+
+
+def _channel_map(x, w, bias, epi=EPI_NONE, aux=None):
+    """r = W x + bias on (B, C_in, voxels) with the epilogues of fz_linear_forward_ex (csrc/fz_linear_tc.cu); returns y,
+    or (y, gelu(y)) for EPI_GELU.  Shapes the kernel does not take (unaligned views) run the same arithmetic in torch."""
+    lib = L.lib()
+    B, cin, vox = x.shape
+    cout = w.shape[0]
+    w = w.contiguous()
+    if (x.is_contiguous() and lib.fz_linear_forward_supported(cout, cin, vox) and (x.data_ptr() | w.data_ptr()) % 16 == 0
+            and (aux is None or aux.is_contiguous())):
+        y = torch.empty(B, cout, vox, device=x.device, dtype=torch.float32)
+        y2 = torch.empty_like(y) if epi == EPI_GELU else None
+        _call(lib.fz_linear_forward_ex, L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(y), B, cin, cout, vox, epi, L.ptr(aux), L.ptr(y2),
+              L.stream_ptr(x.device))
+        return (y, y2) if epi == EPI_GELU else y
+    wb = w.unsqueeze(0).expand(B, -1, -1)
+    r = torch.bmm(wb, x) if bias is None else torch.baddbmm(bias[None, :, None], wb, x)
+    if epi == EPI_RESIDUAL:
+        return r + aux
+    if epi == EPI_GELU:
+        return r, torch.nn.functional.gelu(r)
+    if epi == EPI_GELU_GRAD:
+        return torch.ops.aten.gelu_backward(r, aux)
+    return r
+
+
+def _channel_map_wgrad(gy, x, want_bias: bool):
+    """dW = sum over (batch, voxels) of gy x^T, db = sum of gy."""
+    lib = L.lib()
+    B, cout, vox = gy.shape
+    cin = x.shape[1]
+    if gy.is_contiguous() and x.is_contiguous() and lib.fz_linear_wgrad_supported(cout, cin, vox):
+        gw = torch.empty(cout, cin, device=x.device, dtype=torch.float32)
+        gb = torch.empty(cout, device=x.device, dtype=torch.float32) if want_bias else None
+        _call(lib.fz_linear_wgrad, L.ptr(gy), L.ptr(x), L.ptr(gw), L.ptr(gb), B, cout, cin, vox, L.stream_ptr(x.device))
+        return gw, gb
+    gw = torch.bmm(gy, x.transpose(1, 2)).sum(0)
+    return gw, (gy.sum((0, 2)) if want_bias else None)
+
+
+def _ln_forward(x3, gamma, beta, eps):
+    B, C, vox = x3.shape
+    y = torch.empty_like(x3)
+    _call(L.lib().fz_layernorm_cf_forward, L.ptr(x3), L.ptr(gamma), L.ptr(beta), L.ptr(y), B, C, vox, float(eps), L.stream_ptr(x3.device))
+    return y
+
+
+def _ln_backward_add(x3, gamma, gy, add, eps):
+    """dx = add + LN'(gy), d(gamma), d(beta)."""
+    B, C, vox = x3.shape
+    dx, dg, db = torch.empty_like(x3), torch.empty_like(gamma), torch.empty_like(gamma)
+    _call(L.lib().fz_layernorm_cf_backward_add, L.ptr(x3), L.ptr(gamma), L.ptr(gy), L.ptr(add), L.ptr(dx), L.ptr(dg), L.ptr(db),
+          B, C, vox, float(eps), L.stream_ptr(x3.device))
+    return dx, dg, db
+
+
+def wide_block_supported(x: torch.Tensor, hidden: int) -> bool:
+    """FactorizerBlockWideFn: any channel count the channel-map and LayerNorm kernels take (multiples of 4 up to 512),
+    voxel counts that are multiples of 4, fp32, no autocast."""
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() >= 3 and x.is_contiguous()):
+        return False
+    if torch.is_autocast_enabled():
+        return False
+    B, C = x.shape[0], x.shape[1]
+    vox = x.numel() // max(B * C, 1)
+    lib = L.lib()
+    return bool(B > 0 and vox > 0 and lib.fz_layernorm_cf_supported(C, vox) and lib.fz_linear_forward_supported(C, C, vox)
+                and lib.fz_linear_forward_supported(int(hidden), C, vox) and lib.fz_linear_forward_supported(C, int(hidden), vox)
+                and x.data_ptr() % 16 == 0)
+
+
+class FactorizerBlockWideFn(_GradModeFunction):
+    """FactorizerBlock.forward (reference factorizer/factorizer.py:74-77 with FactMixer.forward :34-57, MLP
+    layers/mlp.py:54-60) for norm = LayerNorm, act = ReLU, GELU MLP, no dropout, at any width (the 64..512-channel stages
+    of the Swin Factorizer): every step is a kernel of this library, with the residual sums, the bias + GELU and the GELU
+    derivative folded into the epilogues of the tcgen05 channel map and the residual gradients into the LayerNorm backward
+    -- nine launches forward (norm1 | in_proj | core x3 | out_proj + residual | norm2 | fc1 + GELU | fc2 + residual)."""
+
+    @staticmethod
+    def forward(ctx, x, g1, b1n, w_in, w_out, b_out, g2, b2n, w1, bb1, w2, bb2, u0, v0, geom, spec, eps1, eps2):
+        x = _check_vol(x, geom, "x")
+        params = [L.require_cuda_f32(t, "parameter") for t in (g1, b1n, w_in, w_out, b_out, g2, b2n, w1, bb1, w2, bb2)]
+        g1, b1n, w_in, w_out, b_out, g2, b2n, w1, bb1, w2, bb2 = params
+        u0 = L.require_cuda_f32(u0, "u0")
+        v0 = L.require_cuda_f32(v0, "v0")
+        B, C = x.shape[0], x.shape[1]
+        need_grad = _GradModeFunction.wants_grad(ctx, 12)
+        x3 = x.view(B, C, -1)
+        with torch.cuda.device(x.device):
+            n1 = _ln_forward(x3, g1, b1n, eps1)
+            z = _channel_map(n1, w_in, None)
+            m, saved = _swnmf_forward(z.view(x.shape), u0, v0, geom, spec, True, need_grad)
+            m3 = m.view(B, C, -1)
+            x1 = _channel_map(m3, w_out, b_out, EPI_RESIDUAL, x3)
+            n2 = _ln_forward(x1, g2, b2n, eps2)
+            h, g = _channel_map(n2, w1, bb1, EPI_GELU)
+            out = _channel_map(g, w2, bb2, EPI_RESIDUAL, x1)
+        if need_grad:
+            ctx.save_for_backward(x3, n1, z, m3, x1, n2, h, g, saved, g1, w_in, w_out, g2, w1, w2, u0, v0)
+            ctx.geom, ctx.spec, ctx.eps = geom, spec, (float(eps1), float(eps2))
+        return out.view(x.shape)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        x3, n1, z, m3, x1, n2, h, g, saved, g1, w_in, w_out, g2, w1, w2, u0, v0 = ctx.saved_tensors
+        geom = ctx.geom
+        gout = _check_vol(gout, geom, "grad")
+        B, C = x3.shape[0], x3.shape[1]
+        eps1, eps2 = ctx.eps
+        go3 = gout.view(B, C, -1)
+        with torch.cuda.device(x3.device):
+            dh = _channel_map(go3, w2.t(), None, EPI_GELU_GRAD, h)          # (W2^T dOut) * gelu'(h)
+            dw2, dbb2 = _channel_map_wgrad(go3, g, True)
+            dw1, dbb1 = _channel_map_wgrad(dh, n2, True)
+            dn2 = _channel_map(dh, w1.t(), None)
+            dx1, dg2, db2n = _ln_backward_add(x1, g2, dn2, go3, eps2)       # dOut + norm2'(..)
+            dm = _channel_map(dx1, w_out.t(), None)
+            dw_out, db_out = _channel_map_wgrad(dx1, m3, True)
+            vol = (B, C, *geom.size)
+            dz = _swnmf_backward(z.view(vol), dm.view(vol), u0, v0, saved, geom, ctx.spec, True).view(B, C, -1)
+            dw_in, _ = _channel_map_wgrad(dz, n1, False)
+            dn1 = _channel_map(dz, w_in.t(), None)
+            dx, dg1, db1n = _ln_backward_add(x3, g1, dn1, dx1, eps1)        # dx1 + norm1'(..)
+        return (dx.view(vol), dg1, db1n, dw_in, dw_out, db_out, dg2, db2n, dw1, dbb1, dw2, dbb2,
+                None, None, None, None, None, None)
+
+
 # ---- channels-first LayerNorm (glue around the mixer) --------------------------------------------
 def layernorm_cf_supported(x: torch.Tensor) -> bool:
     if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() >= 3):

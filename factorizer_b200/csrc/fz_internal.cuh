@@ -85,8 +85,8 @@ int linear_wgrad_tc_launch(const float* dy, const float* x, float* dW, float* db
                            cudaStream_t st);
 
 bool linear_fwd_tc_supported(const float* x, const float* W, long long batch, int cout, int cin, long long voxels);
-int linear_fwd_tc_launch(const float* x, const float* W, const float* bias, float* y, long long batch, int cout, int cin,
-                         long long voxels, cudaStream_t st);
+int linear_fwd_tc_launch(const float* x, const float* W, const float* bias, float* y, const float* aux, float* y2, int epi,
+                         long long batch, int cout, int cin, long long voxels, cudaStream_t st);
 
 // fz_block_glue_bwd_tc.cu: tcgen05 / TMEM version of the MLP + norm2 backward kernel (hidden width a multiple of 64, 3xTF32); the caller
 // zeroes the gradients

@@ -51,8 +51,8 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_cf_fwd(const float* __re
 
 template <int C>
 __global__ void __launch_bounds__(kLnThreads) layernorm_cf_bwd(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                               const float* __restrict__ dy, float* __restrict__ dx,
-                                                               float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                               const float* __restrict__ dy, const float* __restrict__ add,
+                                                               float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                long long pairs_per_sample, long long total_pairs, float eps) {
     __shared__ float gs[C];
     __shared__ float red[2][C][kLnThreads / 32];
@@ -95,11 +95,13 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_cf_bwd(const float* __re
         }
         m1.x *= (1.f / C); m1.y *= (1.f / C); m2.x *= (1.f / C); m2.y *= (1.f / C);
         float2* op = reinterpret_cast<float2*>(dx + b * C * vox) + v;
+        const float2* ap = add ? reinterpret_cast<const float2*>(add + b * C * vox) + v : nullptr;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             float2 o;
             o.x = rstd.x * (g[c].x - m1.x - xh[c].x * m2.x);
             o.y = rstd.y * (g[c].y - m1.y - xh[c].y * m2.y);
+            if (ap) { const float2 r = __ldcs(ap + (long long)c * pairs_per_sample); o.x += r.x; o.y += r.y; }
             op[(long long)c * pairs_per_sample] = o;
         }
     }
@@ -184,8 +186,8 @@ __device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) 
 }
 
 __global__ void __launch_bounds__(kLnThreads) layernorm_cf_bwd_any(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                                   const float* __restrict__ dy, float* __restrict__ dx,
-                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta, int C,
+                                                                   const float* __restrict__ dy, const float* __restrict__ add,
+                                                                   float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int C,
                                                                    long long pairs_per_sample, long long total_pairs, float eps) {
     extern __shared__ float lsm[];
     const int CP = (C + 31) & ~31;                     // channels rounded up to whole chunks of 32
@@ -240,8 +242,12 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_cf_bwd_any(const float* 
                 const float2 xv = __ldg(xp + (long long)c * pairs_per_sample);
                 const float2 g = __ldg(gp + (long long)c * pairs_per_sample);
                 const float hx = (xv.x - mean.x) * rstd.x, hy = (xv.y - mean.y) * rstd.y;
-                op[(long long)c * pairs_per_sample] = make_float2(rstd.x * (g.x * gs[c] - m1.x - hx * m2.x),
-                                                                  rstd.y * (g.y * gs[c] - m1.y - hy * m2.y));
+                float2 o = make_float2(rstd.x * (g.x * gs[c] - m1.x - hx * m2.x), rstd.y * (g.y * gs[c] - m1.y - hy * m2.y));
+                if (add) {
+                    const float2 r = __ldg(reinterpret_cast<const float2*>(add + b * C * vox) + v + (long long)c * pairs_per_sample);
+                    o.x += r.x; o.y += r.y;
+                }
+                op[(long long)c * pairs_per_sample] = o;
             }
         }
     }
@@ -328,8 +334,8 @@ __global__ void __launch_bounds__(32 * kLnMaxSlices) layernorm_cf_fwd_sliced(con
 }
 
 __global__ void __launch_bounds__(32 * kLnMaxSlices, 2) layernorm_cf_bwd_sliced(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                                             const float* __restrict__ dy, float* __restrict__ dx,
-                                                                             float* __restrict__ dgamma, float* __restrict__ dbeta, int C,
+                                                                             const float* __restrict__ dy, const float* __restrict__ add,
+                                                                             float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int C,
                                                                              long long pairs_per_sample, long long total_pairs, float eps) {
     extern __shared__ float lsm[];
     __shared__ float2 sa[kLnMaxSlices][32], sb[kLnMaxSlices][32];
@@ -393,7 +399,12 @@ __global__ void __launch_bounds__(32 * kLnMaxSlices, 2) layernorm_cf_bwd_sliced(
                 const float2 g = __ldg(gp + (long long)c * pairs_per_sample);
                 const float w = gs[c];
                 const float hx = (xv.x - mean.x) * rstd.x, hy = (xv.y - mean.y) * rstd.y;
-                op[(long long)c * pairs_per_sample] = make_float2(rstd.x * (g.x * w - m1.x - hx * m2.x), rstd.y * (g.y * w - m1.y - hy * m2.y));
+                float2 o = make_float2(rstd.x * (g.x * w - m1.x - hx * m2.x), rstd.y * (g.y * w - m1.y - hy * m2.y));
+                if (add) {
+                    const float2 r = __ldg(reinterpret_cast<const float2*>(add + b * C * vox) + v + (long long)c * pairs_per_sample);
+                    o.x += r.x; o.y += r.y;
+                }
+                op[(long long)c * pairs_per_sample] = o;
             }
         }
         __syncthreads();          // sa / sb are rewritten by the next group
@@ -424,7 +435,7 @@ int launch_fwd(const float* x, const float* gamma, const float* beta, float* y, 
     return FZ_OK;
 }
 template <int C>
-int launch_bwd(const float* x, const float* gamma, const float* dy, float* dx, float* dgamma, float* dbeta, long long batch,
+int launch_bwd(const float* x, const float* gamma, const float* dy, const float* add, float* dx, float* dgamma, float* dbeta, long long batch,
                long long voxels, float eps, cudaStream_t st) {
     const long long pps = voxels / 2, total = batch * pps;
     long long blocks = (total + kLnThreads - 1) / kLnThreads;
@@ -432,7 +443,7 @@ int launch_bwd(const float* x, const float* gamma, const float* dy, float* dx, f
     if (blocks > cap) blocks = cap;
     if (dgamma) FZ_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, C * sizeof(float), st));
     if (dbeta) FZ_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, C * sizeof(float), st));
-    layernorm_cf_bwd<C><<<(unsigned)blocks, kLnThreads, 0, st>>>(x, gamma, dy, dx, dgamma, dbeta, pps, total, eps);
+    layernorm_cf_bwd<C><<<(unsigned)blocks, kLnThreads, 0, st>>>(x, gamma, dy, add, dx, dgamma, dbeta, pps, total, eps);
     FZ_LAUNCH_CHECK();
     return FZ_OK;
 }
@@ -491,6 +502,11 @@ int fz_layernorm_cf_forward(const float* x, const float* gamma, const float* bet
 
 int fz_layernorm_cf_backward(const float* x, const float* gamma, const float* dy, float* dx, float* dgamma,
                              float* dbeta, int64_t batch, int32_t channels, int64_t voxels, float eps, void* stream) {
+    return fz_layernorm_cf_backward_add(x, gamma, dy, nullptr, dx, dgamma, dbeta, batch, channels, voxels, eps, stream);
+}
+
+int fz_layernorm_cf_backward_add(const float* x, const float* gamma, const float* dy, const float* add, float* dx, float* dgamma,
+                                 float* dbeta, int64_t batch, int32_t channels, int64_t voxels, float eps, void* stream) {
     tls().launches = 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (batch == 0 || voxels == 0) {
@@ -501,9 +517,9 @@ int fz_layernorm_cf_backward(const float* x, const float* gamma, const float* dy
     if (int e = check_args(x, dx, batch, channels, voxels)) return e;
     if (!dy) return fail(FZ_ERR_INVALID, "null buffer");
     switch (channels) {
-        case 8: return launch_bwd<8>(x, gamma, dy, dx, dgamma, dbeta, batch, voxels, eps, st);
-        case 16: return launch_bwd<16>(x, gamma, dy, dx, dgamma, dbeta, batch, voxels, eps, st);
-        case 32: return launch_bwd<32>(x, gamma, dy, dx, dgamma, dbeta, batch, voxels, eps, st);
+        case 8: return launch_bwd<8>(x, gamma, dy, add, dx, dgamma, dbeta, batch, voxels, eps, st);
+        case 16: return launch_bwd<16>(x, gamma, dy, add, dx, dgamma, dbeta, batch, voxels, eps, st);
+        case 32: return launch_bwd<32>(x, gamma, dy, add, dx, dgamma, dbeta, batch, voxels, eps, st);
         default: break;
     }
     {
@@ -517,7 +533,7 @@ int fz_layernorm_cf_backward(const float* x, const float* gamma, const float* dy
         if (const int sl = ln_slices(channels, total)) {
             long long groups = (total + 31) / 32;
             if (groups > 4LL * sm_count()) groups = 4LL * sm_count();
-            layernorm_cf_bwd_sliced<<<(unsigned)groups, dim3(32, sl), sizeof(float) * 3 * channels, st>>>(x, gamma, dy, dx, dgamma, dbeta,
+            layernorm_cf_bwd_sliced<<<(unsigned)groups, dim3(32, sl), sizeof(float) * 3 * channels, st>>>(x, gamma, dy, add, dx, dgamma, dbeta,
                                                                                                          channels, pps, total, eps);
             FZ_LAUNCH_CHECK();
             return FZ_OK;
@@ -526,7 +542,7 @@ int fz_layernorm_cf_backward(const float* x, const float* gamma, const float* dy
         const size_t smem = sizeof(float) * (cp + (threads / 32) * 2 * cp);
         static SmemConfig cfg;
         FZ_CUDA_CHECK(cfg.ensure(layernorm_cf_bwd_any, sizeof(float) * (kLnMaxC + (kLnThreads / 32) * 2 * kLnMaxC)));
-        layernorm_cf_bwd_any<<<(unsigned)blocks, threads, smem, st>>>(x, gamma, dy, dx, dgamma, dbeta, channels, pps, total, eps);
+        layernorm_cf_bwd_any<<<(unsigned)blocks, threads, smem, st>>>(x, gamma, dy, add, dx, dgamma, dbeta, channels, pps, total, eps);
         FZ_LAUNCH_CHECK();
         return FZ_OK;
     }

@@ -262,7 +262,8 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
 
 __global__ void __launch_bounds__(kGThreads, 2)
 linear_fwd_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias,
-              float* __restrict__ y, int cout, int cin, long long vox, int vtiles_per_sample, int otiles, long long total_items) {
+              float* __restrict__ y, const float* __restrict__ aux, float* __restrict__ y2, int epi, int cout, int cin, long long vox,
+              int vtiles_per_sample, int otiles, long long total_items) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, lane = tid & 31;
@@ -355,8 +356,37 @@ linear_fwd_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         const int wq = warp & 3, wh = (warp - 2) >> 2;                     // TMEM lane quarter this warp may read; half of the columns
         const int spi = (kchunks + kGSeg - 1) / kGSeg;                     // segments per item
         float sum[32];
+        // where this thread's 32 outputs of item `it` live: y[off + o * vox], o0 + o < cout, voxel inside the sample
+        auto item_pos = [&](long long it, long long& off, int& o0) -> bool {
+            const long long item = blockIdx.x + it * gridDim.x;
+            const int ot = (int)(item % otiles);
+            const long long vt_all = item / otiles;
+            const long long b = vt_all / vtiles_per_sample;
+            const long long v = (vt_all - b * vtiles_per_sample) * kGM + wq * 32 + lane;
+            o0 = ot * kGN + wh * 32;
+            off = (b * cout + o0) * vox + v;
+            return v < vox;
+        };
+        // an item's running sums start from zero -- or from the residual (FZ_EPILOGUE_RESIDUAL): its loads are issued an
+        // item ahead of their first use and cost no registers; FZ_EPILOGUE_GELU_GRAD pulls its aux values into L2 meanwhile
+        auto start_item = [&](long long it) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) sum[i] = 0.f;
+            for (int i = 0; i < 32; ++i) sum[i] = 0.f;
+            if (it >= my_items || epi == FZ_EPILOGUE_NONE || epi == FZ_EPILOGUE_GELU) return;
+            long long off;
+            int o0;
+            if (!item_pos(it, off, o0)) return;
+            if (epi == FZ_EPILOGUE_RESIDUAL) {
+#pragma unroll
+                for (int o = 0; o < 32; ++o)
+                    if (o0 + o < cout) sum[o] = __ldg(aux + off + o * vox);
+            } else {
+#pragma unroll
+                for (int o = 0; o < 32; ++o)
+                    if (o0 + o < cout) asm volatile("prefetch.global.L2 [%0];" :: "l"(aux + off + o * vox));
+            }
+        };
+        start_item(0);
         auto drain = [&](long long seg) {
             const uint32_t acc = (uint32_t)(seg & 1), use = (uint32_t)(seg >> 1);
             bar_wait(sbase + gBarAccFull + 8 * acc, use & 1);
@@ -374,24 +404,45 @@ linear_fwd_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
             tc_fence_before();
             __syncwarp();
             if (lane == 0) bar_arrive(sbase + gBarAccFree + 8 * acc);
-            if (seg % spi == spi - 1) {                                    // the item's last segment: bias, store, start over
+            if (seg % spi == spi - 1) {                                    // the item's last segment: epilogue, store, start over
                 const long long it = seg / spi;
-                const long long item = blockIdx.x + it * gridDim.x;
-                const int ot = (int)(item % otiles);
-                const long long vt_all = item / otiles;
-                const long long b = vt_all / vtiles_per_sample;
-                const long long v = (vt_all - b * vtiles_per_sample) * kGM + wq * 32 + lane;
-                if (v < vox) {
-                    const int o0 = ot * kGN + wh * 32;
-                    float* py = y + (b * cout + o0) * vox + v;
+                long long off;
+                int o0;
+                if (item_pos(it, off, o0)) {
+                    // bias, then FZ_EPILOGUE_*: (+ residual, already in the sums) | y = r, y2 = gelu(r) | y = r * gelu'(aux)
+                    if (bias) {
 #pragma unroll
-                    for (int o = 0; o < 32; ++o) {
-                        if (o0 + o < cout) *py = sum[o] + (bias ? __ldg(bias + o0 + o) : 0.f);
-                        py += vox;
+                        for (int o = 0; o < 32; ++o)
+                            if (o0 + o < cout) sum[o] += __ldg(bias + o0 + o);
+                    }
+                    if (epi == FZ_EPILOGUE_GELU) {
+#pragma unroll
+                        for (int o = 0; o < 32; o += 2) {
+                            float2 e;
+                            const float2 r = make_float2(sum[o], sum[o + 1]);
+                            const float2 gl = __fmul2_rn(r, gauss_cdf2(r, e));
+                            if (o0 + o < cout) { y[off + o * vox] = r.x; y2[off + o * vox] = gl.x; }
+                            if (o0 + o + 1 < cout) { y[off + (o + 1) * vox] = r.y; y2[off + (o + 1) * vox] = gl.y; }
+                        }
+                    } else {
+                        if (epi == FZ_EPILOGUE_GELU_GRAD) {
+                            float h[32];
+#pragma unroll
+                            for (int o = 0; o < 32; ++o) h[o] = o0 + o < cout ? __ldg(aux + off + o * vox) : 0.f;
+#pragma unroll
+                            for (int o = 0; o < 32; o += 2) {
+                                float2 gl, gp;
+                                gelu_grad2(make_float2(h[o], h[o + 1]), gl, gp);
+                                sum[o] *= gp.x;
+                                sum[o + 1] *= gp.y;
+                            }
+                        }
+#pragma unroll
+                        for (int o = 0; o < 32; ++o)
+                            if (o0 + o < cout) y[off + o * vox] = sum[o];
                     }
                 }
-#pragma unroll
-                for (int i = 0; i < 32; ++i) sum[i] = 0.f;
+                start_item(it + 1);
             }
         };
         long long g = 0, seg = 0;                                          // seg: the segment the current chunk belongs to
@@ -472,8 +523,8 @@ bool linear_fwd_tc_supported(const float* x, const float* W, long long batch, in
            ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(W)) & 15) == 0;
 }
 
-int linear_fwd_tc_launch(const float* x, const float* W, const float* bias, float* y, long long batch, int cout, int cin,
-                         long long voxels, cudaStream_t st) {
+int linear_fwd_tc_launch(const float* x, const float* W, const float* bias, float* y, const float* aux, float* y2, int epi,
+                         long long batch, int cout, int cin, long long voxels, cudaStream_t st) {
     CUtensorMap map_x, map_w;
     if (int e = make_map_x(&map_x, x, batch, cin, voxels)) return e;
     if (int e = make_map_w(&map_w, W, cout, cin)) return e;
@@ -484,7 +535,7 @@ int linear_fwd_tc_launch(const float* x, const float* W, const float* bias, floa
     const long long items = batch * vtps * otiles;
     const long long cap = 2LL * num_sms();
     const unsigned blocks = (unsigned)(items < cap ? items : cap);
-    linear_fwd_tc<<<blocks, kGThreads, kGSmem, st>>>(map_x, map_w, bias, y, cout, cin, voxels, vtps, otiles, items);
+    linear_fwd_tc<<<blocks, kGThreads, kGSmem, st>>>(map_x, map_w, bias, y, aux, y2, epi, cout, cin, voxels, vtps, otiles, items);
     FZ_LAUNCH_CHECK();
     return FZ_OK;
 }

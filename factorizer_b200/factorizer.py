@@ -3,11 +3,11 @@ reference's constructor signatures and parameter names (factorizer/factorizer.py
 
 ``FactMixer.forward`` is where the fused kernel plugs in: when the configured
 ``reshape -> act -> factorize -> reshape.inverse_forward`` chain is
-(Matricize | SWMatricize) -> (ReLU | Identity) -> NMF('mu' | 'hals'), the four steps run as one CUDA
-kernel per direction (X read once, Y written once); any other combination runs the same steps through
-the standalone kernels.  A 32-channel FactorizerBlock with LayerNorm / ReLU / GELU and no active dropout runs
-entirely in hand-written kernels (csrc/fz_block_glue.cu around the fused core); other blocks run the glue
-layer by layer.
+(Matricize | SWMatricize) -> (ReLU | Identity) -> NMF('mu' | 'hals'), the four steps run as the fused core (csrc/fz_swnmf_*.cu: three launches per direction on the production path);
+any other combination runs the same steps through the standalone kernels.  A FactorizerBlock with LayerNorm / ReLU / GELU
+and no active dropout runs entirely in hand-written kernels: 32 channels in the fused glue kernels (csrc/fz_block_glue*.cu)
+around the fused core, any other width in the tcgen05 channel-map kernel with fused epilogues (csrc/fz_linear_tc.cu) and the
+channels-first LayerNorm kernels; other blocks run the glue layer by layer.
 """
 from __future__ import annotations
 
@@ -87,18 +87,24 @@ class FactorizerBlock(nn.Module):
                 and fc2.linear.bias is not None and f.in_proj.linear.bias is None and f.out_proj.linear.bias is not None):
             return None
         C = x.shape[1] if x.dim() >= 3 else -1
-        if tuple(n1.normalized_shape) != (C,) or tuple(n2.normalized_shape) != (C,) \
-                or fc2.linear.out_channels != C or not _ops.block_glue_supported(x, fc1.linear.out_channels):
+        if tuple(n1.normalized_shape) != (C,) or tuple(n2.normalized_shape) != (C,) or fc2.linear.out_channels != C:
+            return None
+        if _ops.block_glue_supported(x, fc1.linear.out_channels):
+            fn = _ops.FactorizerBlockFn            # 32 channels: fused glue kernels (csrc/fz_block_glue*.cu)
+        elif _ops.wide_block_supported(x, fc1.linear.out_channels):
+            fn = _ops.FactorizerBlockWideFn        # any other width: channel-map kernels with fused epilogues
+        else:
             return None
         sq = lambda lin: lin.linear.weight.squeeze(-1)
-        return (n1.weight, n1.bias, sq(f.in_proj), sq(f.out_proj), f.out_proj.linear.bias, n2.weight, n2.bias,
-                sq(fc1), fc1.linear.bias, sq(fc2), fc2.linear.bias, f.factorize.init.u0, f.factorize.init.v0,
-                f.reshape._geom, f.factorize.solver_spec(), n1.eps, n2.eps)
+        return fn, (n1.weight, n1.bias, sq(f.in_proj), sq(f.out_proj), f.out_proj.linear.bias, n2.weight, n2.bias,
+                    sq(fc1), fc1.linear.bias, sq(fc2), fc2.linear.bias, f.factorize.init.u0, f.factorize.init.v0,
+                    f.reshape._geom, f.factorize.solver_spec(), n1.eps, n2.eps)
 
     def forward(self, x):
-        args = self._fused_args(x)
-        if args is not None:
-            return _ops.FactorizerBlockFn.apply(x, *args)
+        fused = self._fused_args(x)
+        if fused is not None:
+            fn, args = fused
+            return fn.apply(x, *args)
         x = x + self.fact(self.norm1(x))
         x = x + self.mlp(self.norm2(x))
         return x

@@ -149,6 +149,12 @@ int fz_layernorm_cf_forward(const float* x, const float* gamma, const float* bet
 /* dx, and d(gamma), d(beta) (each `channels` floats, overwritten; either may be NULL) of <dy, y>. */
 int fz_layernorm_cf_backward(const float* x, const float* gamma, const float* dy, float* dx, float* dgamma,
                              float* dbeta, int64_t batch, int32_t channels, int64_t voxels, float eps, void* stream);
+/* the same with a residual gradient: dx = add + LN'(dy)  (the block's x + f(norm(x)) pattern, reference
+ * factorizer/factorizer.py:74-77: one pass instead of LayerNorm backward + an elementwise sum); add may be NULL, must not
+ * alias dx. */
+int fz_layernorm_cf_backward_add(const float* x, const float* gamma, const float* dy, const float* add, float* dx,
+                                 float* dgamma, float* dbeta, int64_t batch, int32_t channels, int64_t voxels, float eps,
+                                 void* stream);
 
 /* ---- weight gradient of the pointwise channel map (reference factorizer/layers/linear.py:53-58, a k=1 Conv1d) ----
  * dW[o][i] = sum over batch and voxels of dy[b][o][v] x[b][i][v]   (cout x cin floats, OVERWRITTEN)
@@ -168,6 +174,14 @@ int fz_linear_wgrad(const float* dy, const float* x, float* dW, float* db, int64
 int fz_linear_forward_supported(int32_t cout, int32_t cin, int64_t voxels);
 int fz_linear_forward(const float* x, const float* W, const float* bias, float* y, int64_t batch, int32_t cin, int32_t cout,
                       int64_t voxels, void* stream);
+/* the same with a fused epilogue on r = W x + bias (same shapes as y for aux / y2):
+ *   FZ_EPILOGUE_RESIDUAL   y = r + aux                      (x + out_proj(..), x1 + fc2(..): reference factorizer.py:74-77)
+ *   FZ_EPILOGUE_GELU       y = r, y2 = gelu(r)  (exact erf)  (fc1 -> GELU, reference layers/mlp.py:54-60; r is kept for the backward)
+ *   FZ_EPILOGUE_GELU_GRAD  y = r * gelu'(aux)               (the input gradient of fc2 through the GELU; aux = the saved r of fc1)
+ * so that no elementwise pass is left between the channel maps of a block. */
+enum { FZ_EPILOGUE_NONE = 0, FZ_EPILOGUE_RESIDUAL = 1, FZ_EPILOGUE_GELU = 2, FZ_EPILOGUE_GELU_GRAD = 3 };
+int fz_linear_forward_ex(const float* x, const float* W, const float* bias, float* y, int64_t batch, int32_t cin, int32_t cout,
+                         int64_t voxels, int32_t epilogue, const float* aux, float* y2, void* stream);
 
 /* (batch, channels, D, H, W) <-> (batch, channels*8, D/2*H/2*W/2) with rows ordered (c, kd, kh, kw): the view on which
  * the reference U-Net's kernel-2 stride-2 down-sampling convolution (factorizer/unet.py:53) and transposed up-sampling

@@ -143,3 +143,42 @@ def test_block_full_size_vs_oracle(ft, dev, n):
         # a parameter gradient is a sum over n^3 voxels of fp32 products: bound relative to its largest entry
         scale = max(1.0, float(np.abs(ref).max()))
         assert tol_ratio(_np(gp) / scale, ref / scale, rtol=1e-4, atol=1e-4) <= 1.0, k
+
+
+@pytest.mark.parametrize("C,n,B,ratio", [(64, 32, 1, 2), (128, 16, 2, 2), (512, 8, 1, 2), (72, 16, 1, 4), (16, 16, 2, 1.5)])
+def test_wide_block_vs_oracle(ft, dev, C, n, B, ratio):
+    """FactorizerBlock at the widths of the Swin Factorizer's deeper stages (and odd ones): the channel-map kernels with fused
+    epilogues (FZ_EPILOGUE_*) + LayerNorm backward with the residual gradient around the production core
+    (_ops.FactorizerBlockWideFn): output, input gradient and every parameter gradient against oracle/block_reference.py."""
+    torch.manual_seed(13 + C)
+    blk = ft.FactorizerBlock(channels=C, spatial_size=(n, n, n), norm=ft.LayerNorm,
+                             reshape=(ft.SWMatricize, {"head_dim": 8, "patch_size": 8}), act=nn.ReLU,
+                             factorize=ft.NMF, rank=1, num_iters=5, init="uniform", solver="hals", mlp_ratio=ratio,
+                             dropout=0.0).to(dev)
+    with torch.no_grad():
+        for nm in ("norm1", "norm2"):
+            getattr(blk, nm).norm.weight.add_(0.2 * torch.randn(C, device=dev))
+            getattr(blk, nm).norm.bias.add_(0.2 * torch.randn(C, device=dev))
+    x = torch.randn(B, C, n, n, n, device=dev).requires_grad_(True)
+    gy = torch.randn(B, C, n, n, n, device=dev)
+    assert blk._fused_args(x) is not None
+    y = blk(x)
+    assert type(y.grad_fn).__name__ == "FactorizerBlockWideFnBackward"
+    params = dict(blk.named_parameters())
+    grads = torch.autograd.grad((y * gy).sum(), [x] + list(params.values()))
+    with torch.no_grad():
+        assert torch.equal(blk(x.detach()), y.detach())            # inference path: same kernels, nothing saved
+        # the product's own z, through the same kernels the block calls (LayerNorm kernel + channel-map kernel)
+        from factorizer_b200 import _ops
+        n1 = blk.norm1.norm
+        z = _ops._channel_map(_ops._ln_forward(x.detach().view(B, C, -1), n1.weight, n1.bias, n1.eps),
+                              blk.fact.in_proj.linear.weight.squeeze(-1), None).view(x.shape)
+    torch.cuda.synchronize()
+    y_ref, gx_ref, gp_ref, _ = block_reference(blk.state_dict(), x, gy, z,
+                                               lambda got, ref: assert_close(_np(got), _np(ref), what="block z = in_proj(norm1(x))"))
+    assert_close(_np(y), _np(y_ref), what="block y")
+    assert_close(_np(grads[0]), _np(gx_ref), what="block gx")
+    for (k, _), gp in zip(params.items(), grads[1:]):
+        ref = _np(gp_ref[k]).reshape(_np(gp).shape)
+        scale = max(1.0, float(np.abs(ref).max()))
+        assert tol_ratio(_np(gp) / scale, ref / scale, rtol=1e-4, atol=1e-4) <= 1.0, k

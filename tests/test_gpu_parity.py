@@ -190,9 +190,8 @@ def test_unfused_chain_equals_fused(ft, dev, golden, name):
 def test_factorizer_block_matches_reference(ft, dev, golden, name):
     c = cases.BLOCK_CASES[name]
     g = golden["block"]
-    # the layer-by-layer path (blocks that are not 32 channels wide) runs its Linear layers as library GEMMs,
-    # which may default to TF32 on CUDA; parity against the reference's fp32 CPU run needs true fp32 there
-    # (our own kernels never use TF32)
+    # shapes the channel-map kernel does not take fall back to library GEMMs, which may default to TF32 on CUDA;
+    # parity against the reference's fp32 CPU run needs true fp32 there (our own kernels never use one TF32 pass)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     blk = ft.FactorizerBlock(channels=c["channels"], spatial_size=c["spatial"], norm=ft.LayerNorm,
@@ -204,9 +203,9 @@ def test_factorizer_block_matches_reference(ft, dev, golden, name):
     xs = (c["batch"], c["channels"], *c["spatial"])
     x = torch.from_numpy(cases.make_array(name, xs, "randn")).to(dev).requires_grad_(True)
     gy = torch.from_numpy(cases.make_array(name, xs, "randn", tag="gy")).to(dev)
-    assert (blk._fused_args(x) is not None) == (c["channels"] == 32)
+    assert blk._fused_args(x) is not None
     y = blk(x)
-    assert (type(y.grad_fn).__name__ == "FactorizerBlockFnBackward") == (c["channels"] == 32)
+    assert type(y.grad_fn).__name__ == ("FactorizerBlockFnBackward" if c["channels"] == 32 else "FactorizerBlockWideFnBackward")
     params = dict(blk.named_parameters())
     grads = torch.autograd.grad((y * gy).sum(), [x] + list(params.values()))
     assert_close(_np(y), g[f"{name}/y"], what="y")
@@ -539,6 +538,23 @@ def test_channel_map_tensor_core_kernel(ft, dev, B, cin, cout, vox, bias):
                                   torch.cuda.current_stream().cuda_stream))
     ref = torch.nn.functional.conv1d(x.double(), W.double().unsqueeze(-1), b.double() if bias else None)
     assert_close(_np(y), _np(ref), what="y")
+    # fused epilogues (fz_linear_forward_ex): + residual | r and gelu(r) | r * gelu'(aux)
+    aux = torch.randn(B, cout, vox, device=dev)
+    y2 = torch.full_like(y, float("nan"))
+    st = torch.cuda.current_stream().cuda_stream
+    run = lambda epi: L.check(lib.fz_linear_forward_ex(x.data_ptr(), W.data_ptr(), b.data_ptr() if bias else None, y.data_ptr(), B, cin,
+                                                       cout, vox, epi, aux.data_ptr(), y2.data_ptr(), st))
+    run(1)
+    assert_close(_np(y), _np(ref + aux.double()), what="residual epilogue")
+    run(2)
+    assert_close(_np(y), _np(ref), what="GELU epilogue, pre-activation")
+    assert_close(_np(y2), _np(torch.nn.functional.gelu(ref)), what="GELU epilogue, activation")
+    run(3)
+    a64 = aux.double().requires_grad_(True)
+    (gp,) = torch.autograd.grad(torch.nn.functional.gelu(a64).sum(), a64)
+    assert_close(_np(y), _np(ref * gp), what="GELU-gradient epilogue")
+    with pytest.raises(ValueError):
+        L.check(lib.fz_linear_forward_ex(x.data_ptr(), W.data_ptr(), None, y.data_ptr(), B, cin, cout, vox, 1, None, None, st))
     assert not lib.fz_linear_forward_supported(cout, cin, vox + 2)
     assert not lib.fz_linear_forward_supported(cout, cin + 1, vox)
 
