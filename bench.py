@@ -275,7 +275,7 @@ def model_leg(dev, world, rank, n=128, steps=3):
             try:
                 side = torch.cuda.Stream(dev)
                 side.wait_stream(torch.cuda.current_stream(dev))
-                gopt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-5, capturable=True)
+                gopt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-5, capturable=True, fused=True)
                 for q in params:
                     q.grad = None
                 # N > 1: this package's bucketed gradient all-reduce (factorizer_b200/distributed.py) -- launched from
@@ -329,7 +329,7 @@ def model_leg(dev, world, rank, n=128, steps=3):
             q.grad = None
         ddp = nn.parallel.DistributedDataParallel(net, device_ids=[dev.index], bucket_cap_mb=4,
                                                   gradient_as_bucket_view=True) if world > 1 else net
-        opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-5)
+        opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-5, fused=True)
 
         def train_step():
             opt.zero_grad(set_to_none=True)
@@ -363,10 +363,10 @@ def model_leg(dev, world, rank, n=128, steps=3):
             out["allreduce_bytes"] = 4 * nparams
             out["train_step"] = (f"forward, sigmoid-BCE + soft-Dice, backward with the NCCL all-reduce (average) of {4 * nparams / 1e6:.1f} MB "
                                  f"of gradients in 4 MB buckets launched from post-accumulate hooks (factorizer_b200/distributed.py) "
-                                 f"under the rest of the backward, AdamW -- all inside one CUDA graph; `eager` = the same step under "
+                                 f"under the rest of the backward, fused AdamW -- all inside one CUDA graph; `eager` = the same step under "
                                  f"torch DistributedDataParallel (bucket_cap_mb=4) with eager launches; world {world}")
         else:
-            out["train_step"] = "forward, sigmoid-BCE + soft-Dice, backward, AdamW; single rank: no gradient all-reduce"
+            out["train_step"] = "forward, sigmoid-BCE + soft-Dice, backward, fused AdamW; single rank: no gradient all-reduce"
         del net, ddp, opt, x, target
         torch.cuda.empty_cache()
         return out

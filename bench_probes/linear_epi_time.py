@@ -29,7 +29,7 @@ for cout, cin, vox in shapes:
     x, W, b = torch.randn(B, cin, vox, device=dev), torch.randn(cout, cin, device=dev) / cin ** 0.5, torch.randn(cout, device=dev)
     y, y2, aux = (torch.empty(B, cout, vox, device=dev) for _ in range(3))
     aux.normal_()
-    run = lambda epi: L.check(lib.fz_linear_forward_ex(x.data_ptr(), W.data_ptr(), b.data_ptr(), y.data_ptr(), B, cin, cout, vox, epi,
+    run = lambda epi: L.check(lib.fz_linear_forward_ex(x.data_ptr(), W.data_ptr(), b.data_ptr(), y.data_ptr(), B, cin, cout, vox, epi, 0,
                                                        aux.data_ptr(), y2.data_ptr(), st))
     t = [timed(lambda e=e: run(e)) for e in range(4)]
     t_add = timed(lambda: torch.add(y, aux, out=y2))

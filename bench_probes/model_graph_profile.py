@@ -22,7 +22,7 @@ def build():
     net = ft.Factorizer(in_channels=4, out_channels=3, spatial_size=(n, n, n), norm=ft.LayerNorm,
                         reshape=(ft.SWMatricize, {"head_dim": 8, "patch_size": 8}), act=nn.ReLU, factorize=ft.NMF, rank=1,
                         num_iters=5, init="uniform", solver="hals", mlp_ratio=2, dropout=0.1).to(dev)
-    opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-5, capturable=True)
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-5, capturable=True, fused=True)
 
     def body():
         opt.zero_grad(set_to_none=True)

@@ -61,8 +61,8 @@ _SIGNATURES = {
     "fz_linear_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int64, c_void_p]),
     "fz_linear_forward_supported": (c_int, [c_int32, c_int32, c_int64]),
     "fz_linear_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int64, c_void_p]),
-    "fz_linear_forward_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int64, c_int32, c_void_p,
-                                     c_void_p, c_void_p]),
+    "fz_linear_forward_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int64, c_int32, c_int32,
+                                     c_void_p, c_void_p, c_void_p]),
     "fz_conv3d_stem_supported": (c_int, [c_int32, c_int32, c_int32, c_int32, c_int32]),
     "fz_conv3d_stem_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "fz_space_depth2_supported": (c_int, [c_int32, c_int32, c_int32]),

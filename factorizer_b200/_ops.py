@@ -411,21 +411,22 @@ class FactorizerBlockFn(_GradModeFunction):
 EPI_NONE, EPI_RESIDUAL, EPI_GELU, EPI_GELU_GRAD = 0, 1, 2, 3
 
 
-def _channel_map(x, w, bias, epi=EPI_NONE, aux=None):
+def _channel_map(x, w, bias, epi=EPI_NONE, aux=None, transposed=False):
     """r = W x + bias on (B, C_in, voxels) with the epilogues of fz_linear_forward_ex (csrc/fz_linear_tc.cu); returns y,
-    or (y, gelu(y)) for EPI_GELU.  Shapes the kernel does not take (unaligned views) run the same arithmetic in torch."""
+    or (y, gelu(y)) for EPI_GELU.  transposed: w is the (C_in, C_out) matrix of the layer whose input gradient this is,
+    read as it lies.  Shapes the kernel does not take (unaligned views) run the same arithmetic in torch."""
     lib = L.lib()
     B, cin, vox = x.shape
-    cout = w.shape[0]
     w = w.contiguous()
+    cout = w.shape[1] if transposed else w.shape[0]
     if (x.is_contiguous() and lib.fz_linear_forward_supported(cout, cin, vox) and (x.data_ptr() | w.data_ptr()) % 16 == 0
-            and (aux is None or aux.is_contiguous())):
+            and (aux is None or aux.is_contiguous()) and not (transposed and cout % 4)):
         y = torch.empty(B, cout, vox, device=x.device, dtype=torch.float32)
         y2 = torch.empty_like(y) if epi == EPI_GELU else None
-        _call(lib.fz_linear_forward_ex, L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(y), B, cin, cout, vox, epi, L.ptr(aux), L.ptr(y2),
-              L.stream_ptr(x.device))
+        _call(lib.fz_linear_forward_ex, L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(y), B, cin, cout, vox, epi, int(transposed),
+              L.ptr(aux), L.ptr(y2), L.stream_ptr(x.device))
         return (y, y2) if epi == EPI_GELU else y
-    wb = w.unsqueeze(0).expand(B, -1, -1)
+    wb = (w.t() if transposed else w).unsqueeze(0).expand(B, -1, -1)
     r = torch.bmm(wb, x) if bias is None else torch.baddbmm(bias[None, :, None], wb, x)
     if epi == EPI_RESIDUAL:
         return r + aux
@@ -522,17 +523,17 @@ class FactorizerBlockWideFn(_GradModeFunction):
         eps1, eps2 = ctx.eps
         go3 = gout.view(B, C, -1)
         with torch.cuda.device(x3.device):
-            dh = _channel_map(go3, w2.t(), None, EPI_GELU_GRAD, h)          # (W2^T dOut) * gelu'(h)
+            dh = _channel_map(go3, w2, None, EPI_GELU_GRAD, h, True)        # (W2^T dOut) * gelu'(h)
             dw2, dbb2 = _channel_map_wgrad(go3, g, True)
             dw1, dbb1 = _channel_map_wgrad(dh, n2, True)
-            dn2 = _channel_map(dh, w1.t(), None)
+            dn2 = _channel_map(dh, w1, None, transposed=True)
             dx1, dg2, db2n = _ln_backward_add(x1, g2, dn2, go3, eps2)       # dOut + norm2'(..)
-            dm = _channel_map(dx1, w_out.t(), None)
+            dm = _channel_map(dx1, w_out, None, transposed=True)
             dw_out, db_out = _channel_map_wgrad(dx1, m3, True)
             vol = (B, C, *geom.size)
             dz = _swnmf_backward(z.view(vol), dm.view(vol), u0, v0, saved, geom, ctx.spec, True).view(B, C, -1)
             dw_in, _ = _channel_map_wgrad(dz, n1, False)
-            dn1 = _channel_map(dz, w_in.t(), None)
+            dn1 = _channel_map(dz, w_in, None, transposed=True)
             dx, dg1, db1n = _ln_backward_add(x3, g1, dn1, dx1, eps1)        # dx1 + norm1'(..)
         return (dx.view(vol), dg1, db1n, dw_in, dw_out, db_out, dg2, db2n, dw1, dbb1, dw2, dbb2,
                 None, None, None, None, None, None)
@@ -636,22 +637,25 @@ def linear_wgrad_supported(x: torch.Tensor, out_channels: int, min_voxels: int =
     return bool(L.lib().fz_linear_wgrad_supported(int(out_channels), x.shape[1] if rows is None else int(rows), vox))
 
 
-def linear_forward(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
-    """y = W x (+ b) for x (B, C_in, voxels): the tcgen05 channel-map kernel (csrc/fz_linear_tc.cu, 3xTF32) where its shape
-    restrictions hold and the GEMM is large enough to pay, else the library's batched GEMM."""
+def linear_forward(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], transposed: bool = False) -> torch.Tensor:
+    """y = W x (+ b) for x (B, C_in, voxels) -- or W^T x with `transposed` (the input gradient, from the weight as stored): the
+    tcgen05 channel-map kernel (csrc/fz_linear_tc.cu, 3xTF32) where its shape restrictions hold and the GEMM is large enough
+    to pay, else the library's batched GEMM."""
     B, cin, vox = x.shape
-    cout = weight.shape[0]
+    cout = weight.shape[1] if transposed else weight.shape[0]
     lib = L.lib()
-    if (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and B * vox >= 4096 and cin >= 32 and cout >= 16
-            and lib.fz_get_glue_mode() & 1 and lib.fz_linear_forward_supported(cout, cin, vox) and x.data_ptr() % 16 == 0):
+    if (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and B * vox >= 512 and cin >= 32 and cout >= 16
+            and lib.fz_get_glue_mode() & 1 and lib.fz_linear_forward_supported(cout, cin, vox) and x.data_ptr() % 16 == 0
+            and not (transposed and cout % 4)):
         w = weight.contiguous()
         if w.data_ptr() % 16 == 0:
             b = None if bias is None else L.require_cuda_f32(bias, "bias")
             y = torch.empty(B, cout, vox, device=x.device, dtype=torch.float32)
             with torch.cuda.device(x.device):
-                _call(lib.fz_linear_forward, L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), B, cin, cout, vox, L.stream_ptr(x.device))
+                _call(lib.fz_linear_forward_ex, L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), B, cin, cout, vox, EPI_NONE, int(transposed),
+                      None, None, L.stream_ptr(x.device))
             return y
-    wb = weight.unsqueeze(0).expand(B, -1, -1)
+    wb = (weight.t() if transposed else weight).unsqueeze(0).expand(B, -1, -1)
     return torch.bmm(wb, x) if bias is None else torch.baddbmm(bias[None, :, None], wb, x)
 
 
@@ -662,8 +666,9 @@ class LinearCF(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias):
-        y = linear_forward(x, weight, bias)
-        ctx.save_for_backward(x, weight)
+        wc = weight.contiguous()                    # a copy only for transposed views (the up-samplers' weights)
+        y = linear_forward(x, wc, bias)
+        ctx.save_for_backward(x, wc)
         ctx.has_bias = bias is not None
         return y
 
@@ -677,7 +682,7 @@ class LinearCF(torch.autograd.Function):
         cout = weight.shape[0]
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = linear_forward(gy.contiguous(), weight.t().contiguous(), None)
+            gx = linear_forward(gy.contiguous(), weight, None, transposed=True)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             gw = torch.empty(weight.shape, device=x.device, dtype=torch.float32)     # row-major whatever the weight's strides
             gb = torch.empty(cout, device=x.device, dtype=torch.float32) if ctx.has_bias else None

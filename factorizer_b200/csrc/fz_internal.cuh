@@ -86,7 +86,7 @@ int linear_wgrad_tc_launch(const float* dy, const float* x, float* dW, float* db
 
 bool linear_fwd_tc_supported(const float* x, const float* W, long long batch, int cout, int cin, long long voxels);
 int linear_fwd_tc_launch(const float* x, const float* W, const float* bias, float* y, const float* aux, float* y2, int epi,
-                         long long batch, int cout, int cin, long long voxels, cudaStream_t st);
+                         int wt, long long batch, int cout, int cin, long long voxels, cudaStream_t st);
 
 // fz_block_glue_bwd_tc.cu: tcgen05 / TMEM version of the MLP + norm2 backward kernel (hidden width a multiple of 64, 3xTF32); the caller
 // zeroes the gradients

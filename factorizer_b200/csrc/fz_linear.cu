@@ -410,11 +410,11 @@ int fz_linear_forward_supported(int32_t cout, int32_t cin, int64_t voxels) {
 
 int fz_linear_forward(const float* x, const float* W, const float* bias, float* y, int64_t batch, int32_t cin, int32_t cout,
                       int64_t voxels, void* stream) {
-    return fz_linear_forward_ex(x, W, bias, y, batch, cin, cout, voxels, FZ_EPILOGUE_NONE, nullptr, nullptr, stream);
+    return fz_linear_forward_ex(x, W, bias, y, batch, cin, cout, voxels, FZ_EPILOGUE_NONE, 0, nullptr, nullptr, stream);
 }
 
 int fz_linear_forward_ex(const float* x, const float* W, const float* bias, float* y, int64_t batch, int32_t cin, int32_t cout,
-                         int64_t voxels, int32_t epilogue, const float* aux, float* y2, void* stream) {
+                         int64_t voxels, int32_t epilogue, int32_t w_transposed, const float* aux, float* y2, void* stream) {
     tls().launches = 0;
     if (batch < 0 || cout <= 0 || cin <= 0 || voxels <= 0) return fail(FZ_ERR_INVALID, "linear forward: bad sizes");
     if (epilogue < FZ_EPILOGUE_NONE || epilogue > FZ_EPILOGUE_GELU_GRAD) return fail(FZ_ERR_INVALID, "linear forward: unknown epilogue %d", epilogue);
@@ -423,10 +423,12 @@ int fz_linear_forward_ex(const float* x, const float* W, const float* bias, floa
     if ((epilogue == FZ_EPILOGUE_RESIDUAL || epilogue == FZ_EPILOGUE_GELU_GRAD) && !aux)
         return fail(FZ_ERR_INVALID, "linear forward: this epilogue reads `aux`");
     if (epilogue == FZ_EPILOGUE_GELU && !y2) return fail(FZ_ERR_INVALID, "linear forward: the GELU epilogue writes `y2`");
-    if (!fz_linear_forward_supported(cout, cin, voxels) || !linear_fwd_tc_supported(x, W, batch, cout, cin, voxels))
-        return fail(FZ_ERR_UNSUPPORTED, "linear forward kernel needs voxels and input channels divisible by 4 and 16-byte aligned "
-                                        "buffers (got %d x %d x %lld)", cout, cin, (long long)voxels);
-    return linear_fwd_tc_launch(x, W, bias, y, aux, y2, epilogue, batch, cout, cin, voxels, (cudaStream_t)stream);
+    if (!fz_linear_forward_supported(cout, cin, voxels) || !linear_fwd_tc_supported(x, W, batch, cout, cin, voxels) ||
+        (w_transposed && cout % 4))
+        return fail(FZ_ERR_UNSUPPORTED, "linear forward kernel needs voxels and input channels (with a transposed weight: output "
+                                        "channels too) divisible by 4 and 16-byte aligned buffers (got %d x %d x %lld)", cout, cin,
+                    (long long)voxels);
+    return linear_fwd_tc_launch(x, W, bias, y, aux, y2, epilogue, w_transposed != 0, batch, cout, cin, voxels, (cudaStream_t)stream);
 }
 
 int fz_space_depth2_supported(int32_t D, int32_t H, int32_t W) {

@@ -255,6 +255,22 @@ int make_map_w(CUtensorMap* m, const float* ptr, int cout, int cin) {
     if (r != CUDA_SUCCESS) return fail(FZ_ERR_CUDA, "cuTensorMapEncodeTiled (W) failed with CUresult %d", (int)r);
     return FZ_OK;
 }
+// W stored as (inputs, outputs) row-major, used transposed (the input gradient reads the layer's weight as it lies): the
+// outputs are contiguous, i.e. the B operand is MN-major like x: boxes of (32 outputs x 32 inputs), 128-byte rows swizzled in
+// 32-byte atoms
+int make_map_wt(CUtensorMap* m, const float* ptr, int cout, int cin) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return fail(FZ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {(cuuint64_t)cout, (cuuint64_t)cin};
+    cuuint64_t strides[1] = {(cuuint64_t)cout * 4};
+    cuuint32_t box[2] = {32, kGK};
+    cuuint32_t es[2] = {1, 1};
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FZ_ERR_CUDA, "cuTensorMapEncodeTiled (W^T) failed with CUresult %d", (int)r);
+    return FZ_OK;
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  :: "r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1) : "memory");
@@ -262,7 +278,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
 
 __global__ void __launch_bounds__(kGThreads, 2)
 linear_fwd_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias,
-              float* __restrict__ y, const float* __restrict__ aux, float* __restrict__ y2, int epi, int cout, int cin, long long vox,
+              float* __restrict__ y, const float* __restrict__ aux, float* __restrict__ y2, int epi, int wt, int cout, int cin, long long vox,
               int vtiles_per_sample, int otiles, long long total_items) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
@@ -310,14 +326,20 @@ linear_fwd_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                     bar_expect_tx(full, kGA + kGB);
 #pragma unroll
                     for (int a = 0; a < 4; ++a) tma_load_3d(st + gA + a * (kGA / 4), &map_x, full, v0 + 32 * a, kc * kGK, b);
-                    tma_load_2d(st + gB, &map_w, full, kc * kGK, ot * kGN);
+                    if (wt) {
+                        tma_load_2d(st + gB, &map_w, full, ot * kGN, kc * kGK);
+                        tma_load_2d(st + gB + kGB / 2, &map_w, full, ot * kGN + 32, kc * kGK);
+                    } else {
+                        tma_load_2d(st + gB, &map_w, full, kc * kGK, ot * kGN);
+                    }
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         // ---- MMA issue ----
-        const uint32_t idesc = make_idesc(128, kGN, true, false);          // A MN-major, B K-major
+        const uint32_t idesc = make_idesc(128, kGN, true, wt != 0);        // A MN-major; B K-major, or MN-major for W^T
+        const uint32_t b_lbo = wt ? kGB / 2 : 16, b_sbo = wt ? 512 : 1024, b_type = wt ? 1 : 2, b_kstep = wt ? 1024 : 32;
         long long g = 0, seg = 0;
         for (long long it = 0; it < my_items; ++it) {
             for (int kc = 0; kc < kchunks; ++kc, ++g) {
@@ -335,13 +357,13 @@ linear_fwd_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                 if (elect_one()) {
                     const uint32_t st = sbase + s * kGStage;
                     const uint64_t a_hi = make_desc(st + gA, kGA / 4, 512, 1), a_lo = make_desc(st + gAlo, kGA / 4, 512, 1);
-                    const uint64_t b_hi = make_desc(st + gB, 16, 1024, 2), b_lo = make_desc(st + gBlo, 16, 1024, 2);
+                    const uint64_t b_hi = make_desc(st + gB, b_lbo, b_sbo, b_type), b_lo = make_desc(st + gBlo, b_lbo, b_sbo, b_type);
                     const uint32_t d_main = tmem + acc * (2 * kGN), d_cross = d_main + kGN;
 #pragma unroll
                     for (int k = 0; k < kGK / 8; ++k) {
-                        mma_tf32(d_cross, desc_at(a_lo, k * 1024), desc_at(b_hi, k * 32), idesc, ks > 0 || k > 0);
-                        mma_tf32(d_cross, desc_at(a_hi, k * 1024), desc_at(b_lo, k * 32), idesc, 1);
-                        mma_tf32(d_main, desc_at(a_hi, k * 1024), desc_at(b_hi, k * 32), idesc, ks > 0 || k > 0);
+                        mma_tf32(d_cross, desc_at(a_lo, k * 1024), desc_at(b_hi, k * b_kstep), idesc, ks > 0 || k > 0);
+                        mma_tf32(d_cross, desc_at(a_hi, k * 1024), desc_at(b_lo, k * b_kstep), idesc, 1);
+                        mma_tf32(d_main, desc_at(a_hi, k * 1024), desc_at(b_hi, k * b_kstep), idesc, ks > 0 || k > 0);
                     }
                     commit(sbase + gBarEmpty + 8 * s);
                     if (seg_end) commit(sbase + gBarAccFull + 8 * acc);
@@ -524,10 +546,10 @@ bool linear_fwd_tc_supported(const float* x, const float* W, long long batch, in
 }
 
 int linear_fwd_tc_launch(const float* x, const float* W, const float* bias, float* y, const float* aux, float* y2, int epi,
-                         long long batch, int cout, int cin, long long voxels, cudaStream_t st) {
+                         int wt, long long batch, int cout, int cin, long long voxels, cudaStream_t st) {
     CUtensorMap map_x, map_w;
     if (int e = make_map_x(&map_x, x, batch, cin, voxels)) return e;
-    if (int e = make_map_w(&map_w, W, cout, cin)) return e;
+    if (int e = wt ? make_map_wt(&map_w, W, cout, cin) : make_map_w(&map_w, W, cout, cin)) return e;
     static SmemConfig cfg;
     FZ_CUDA_CHECK(cfg.ensure(linear_fwd_tc, kGSmem));
     const int vtps = (int)((voxels + kGM - 1) / kGM);
@@ -535,7 +557,7 @@ int linear_fwd_tc_launch(const float* x, const float* W, const float* bias, floa
     const long long items = batch * vtps * otiles;
     const long long cap = 2LL * num_sms();
     const unsigned blocks = (unsigned)(items < cap ? items : cap);
-    linear_fwd_tc<<<blocks, kGThreads, kGSmem, st>>>(map_x, map_w, bias, y, aux, y2, epi, cout, cin, voxels, vtps, otiles, items);
+    linear_fwd_tc<<<blocks, kGThreads, kGSmem, st>>>(map_x, map_w, bias, y, aux, y2, epi, wt, cout, cin, voxels, vtps, otiles, items);
     FZ_LAUNCH_CHECK();
     return FZ_OK;
 }

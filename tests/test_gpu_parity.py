@@ -543,7 +543,7 @@ def test_channel_map_tensor_core_kernel(ft, dev, B, cin, cout, vox, bias):
     y2 = torch.full_like(y, float("nan"))
     st = torch.cuda.current_stream().cuda_stream
     run = lambda epi: L.check(lib.fz_linear_forward_ex(x.data_ptr(), W.data_ptr(), b.data_ptr() if bias else None, y.data_ptr(), B, cin,
-                                                       cout, vox, epi, aux.data_ptr(), y2.data_ptr(), st))
+                                                       cout, vox, epi, 0, aux.data_ptr(), y2.data_ptr(), st))
     run(1)
     assert_close(_np(y), _np(ref + aux.double()), what="residual epilogue")
     run(2)
@@ -553,8 +553,18 @@ def test_channel_map_tensor_core_kernel(ft, dev, B, cin, cout, vox, bias):
     a64 = aux.double().requires_grad_(True)
     (gp,) = torch.autograd.grad(torch.nn.functional.gelu(a64).sum(), a64)
     assert_close(_np(y), _np(ref * gp), what="GELU-gradient epilogue")
+    # the weight read transposed (the input gradient from the layer's weight as stored): Wt is (cin, cout) row-major
+    if cout % 4 == 0:
+        Wt = W.t().contiguous()
+        y.fill_(float("nan"))
+        L.check(lib.fz_linear_forward_ex(x.data_ptr(), Wt.data_ptr(), b.data_ptr() if bias else None, y.data_ptr(), B, cin, cout, vox,
+                                         0, 1, None, None, st))
+        assert_close(_np(y), _np(ref), what="transposed weight")
+    else:
+        with pytest.raises(NotImplementedError):
+            L.check(lib.fz_linear_forward_ex(x.data_ptr(), W.data_ptr(), None, y.data_ptr(), B, cin, cout, vox, 0, 1, None, None, st))
     with pytest.raises(ValueError):
-        L.check(lib.fz_linear_forward_ex(x.data_ptr(), W.data_ptr(), None, y.data_ptr(), B, cin, cout, vox, 1, None, None, st))
+        L.check(lib.fz_linear_forward_ex(x.data_ptr(), W.data_ptr(), None, y.data_ptr(), B, cin, cout, vox, 1, 0, None, None, st))
     assert not lib.fz_linear_forward_supported(cout, cin, vox + 2)
     assert not lib.fz_linear_forward_supported(cout, cin + 1, vox)
 
