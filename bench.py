@@ -20,8 +20,10 @@ core       BASELINE config 2 (the fused SWMatricize+ReLU+NMF+inverse op inside t
 parity_checked
            max error / tolerance (rtol 1e-4, atol 1e-5) of the TIMED buffers against the oracle, after the timing: the core's
            y and dx against oracle/nmf_oracle.c, the block's out and dx against oracle/block_reference.py
-model      configs 4-5: the README Swin Factorizer, inference pass and training step; under torchrun the training step
-           runs under DistributedDataParallel (NCCL gradient all-reduce, 4 MB buckets) and reports the all-reduce alone too
+model      configs 4-5: the README Swin Factorizer, inference pass and training step (each also as ONE CUDA graph); under
+           torchrun the graphed training step carries the NCCL gradient all-reduce (factorizer_b200/distributed.py: 4 MB
+           buckets launched from post-accumulate hooks under the backward), `eager` is the same step under torch
+           DistributedDataParallel, and the all-reduce is timed alone too
 cpu_baseline / --impl reference
            oracle/torch_port.py -- the reference's PyTorch eager path restated in plain torch (the reference itself is
            pure Python and absent on the GPU box) -- on the SAME workload (the whole block at (1,32,128^3), all host
@@ -342,8 +344,10 @@ def model_leg(dev, world, rank, n=128, steps=3):
 
         train_ms = timed(train_step)
         out = {"workload": f"Swin Factorizer (README 78-96) 4->3 ch, {n}^3, widths (32,64,128,256,512), HALS r1, B=1/GPU, fp32, "
-                           "cudnn.benchmark; wide-stage GEMMs and the patch (down / up / head) convolutions' forward are cuBLAS, the "
-                           "stem's forward and every weight gradient of those layers are csrc/fz_linear.cu",
+                           "cudnn.benchmark; all nine blocks run as one autograd node each in this library's kernels (32 channels: "
+                           "csrc/fz_block_glue*.cu; 64..512: the tcgen05 channel map with fused epilogues, csrc/fz_linear_tc.cu), so do the "
+                           "adapters and the patch (down / up) convolutions as channel maps, the stem's forward and every weight gradient; "
+                           "the 3-channel head and the stem backward's pad / unfold are library kernels",
                "params": nparams, "infer_ms": infer_ms, "train_step_ms": train_ms}
         if graph_ms is not None:
             out["eager"] = {"infer_ms": infer_ms, "train_step_ms": train_ms}
