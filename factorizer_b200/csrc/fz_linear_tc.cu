@@ -379,33 +379,47 @@ linear_fwd_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         const int spi = (kchunks + kGSeg - 1) / kGSeg;                     // segments per item
         float sum[32];
         // where this thread's 32 outputs of item `it` live: y[off + o * vox], o0 + o < cout, voxel inside the sample
+        // (32-bit index arithmetic: the launcher keeps the item count below 2^31)
         auto item_pos = [&](long long it, long long& off, int& o0) -> bool {
-            const long long item = blockIdx.x + it * gridDim.x;
-            const int ot = (int)(item % otiles);
-            const long long vt_all = item / otiles;
-            const long long b = vt_all / vtiles_per_sample;
-            const long long v = (vt_all - b * vtiles_per_sample) * kGM + wq * 32 + lane;
-            o0 = ot * kGN + wh * 32;
-            off = (b * cout + o0) * vox + v;
+            const unsigned item = blockIdx.x + (unsigned)it * gridDim.x;
+            const unsigned vt_all = item / (unsigned)otiles, ot = item - vt_all * (unsigned)otiles;
+            const unsigned b = vt_all / (unsigned)vtiles_per_sample;
+            const long long v = (long long)(vt_all - b * (unsigned)vtiles_per_sample) * kGM + wq * 32 + lane;
+            o0 = (int)ot * kGN + wh * 32;
+            off = ((long long)b * cout + o0) * vox + v;
             return v < vox;
         };
-        // an item's running sums start from zero -- or from the residual (FZ_EPILOGUE_RESIDUAL): its loads are issued an
-        // item ahead of their first use and cost no registers; FZ_EPILOGUE_GELU_GRAD pulls its aux values into L2 meanwhile
+        // an item's running sums start from the bias -- or from the residual (FZ_EPILOGUE_RESIDUAL; the bias is added at the
+        // end then): the loads are issued an item ahead of their first use and cost no registers; FZ_EPILOGUE_GELU_GRAD pulls
+        // its aux values into L2 meanwhile
         auto start_item = [&](long long it) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) sum[i] = 0.f;
-            if (it >= my_items || epi == FZ_EPILOGUE_NONE || epi == FZ_EPILOGUE_GELU) return;
+            if (it >= my_items) return;
             long long off;
             int o0;
-            if (!item_pos(it, off, o0)) return;
-            if (epi == FZ_EPILOGUE_RESIDUAL) {
+            const bool live = item_pos(it, off, o0);
+            if (epi != FZ_EPILOGUE_RESIDUAL) {
+                if (bias) {
 #pragma unroll
-                for (int o = 0; o < 32; ++o)
-                    if (o0 + o < cout) sum[o] = __ldg(aux + off + o * vox);
-            } else {
+                    for (int o = 0; o < 32; ++o)
+                        if (o0 + o < cout) sum[o] = __ldg(bias + o0 + o);
+                }
+                if (epi == FZ_EPILOGUE_GELU_GRAD && live) {
+                    const float* pa = aux + off;
 #pragma unroll
-                for (int o = 0; o < 32; ++o)
-                    if (o0 + o < cout) asm volatile("prefetch.global.L2 [%0];" :: "l"(aux + off + o * vox));
+                    for (int o = 0; o < 32; ++o) {
+                        if (o0 + o < cout) asm volatile("prefetch.global.L2 [%0];" :: "l"(pa));
+                        pa += vox;
+                    }
+                }
+            } else if (live) {
+                const float* pa = aux + off;
+#pragma unroll
+                for (int o = 0; o < 32; ++o) {
+                    if (o0 + o < cout) sum[o] = __ldg(pa);
+                    pa += vox;
+                }
             }
         };
         start_item(0);
@@ -431,26 +445,35 @@ linear_fwd_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                 long long off;
                 int o0;
                 if (item_pos(it, off, o0)) {
-                    // bias, then FZ_EPILOGUE_*: (+ residual, already in the sums) | y = r, y2 = gelu(r) | y = r * gelu'(aux)
-                    if (bias) {
+                    // FZ_EPILOGUE_*: (bias / residual already in the sums) | y = r, y2 = gelu(r) | y = r * gelu'(aux)
+                    const bool full = o0 + 32 <= cout;                     // no channel predicates on whole groups of 32
+                    if (epi == FZ_EPILOGUE_RESIDUAL && bias) {
 #pragma unroll
                         for (int o = 0; o < 32; ++o)
-                            if (o0 + o < cout) sum[o] += __ldg(bias + o0 + o);
+                            if (full || o0 + o < cout) sum[o] += __ldg(bias + o0 + o);
                     }
+                    float* py = y + off;
                     if (epi == FZ_EPILOGUE_GELU) {
+                        float* pg = y2 + off;
 #pragma unroll
                         for (int o = 0; o < 32; o += 2) {
                             float2 e;
                             const float2 r = make_float2(sum[o], sum[o + 1]);
                             const float2 gl = __fmul2_rn(r, gauss_cdf2(r, e));
-                            if (o0 + o < cout) { y[off + o * vox] = r.x; y2[off + o * vox] = gl.x; }
-                            if (o0 + o + 1 < cout) { y[off + (o + 1) * vox] = r.y; y2[off + (o + 1) * vox] = gl.y; }
+                            if (full || o0 + o < cout) { *py = r.x; *pg = gl.x; }
+                            py += vox; pg += vox;
+                            if (full || o0 + o + 1 < cout) { *py = r.y; *pg = gl.y; }
+                            py += vox; pg += vox;
                         }
                     } else {
                         if (epi == FZ_EPILOGUE_GELU_GRAD) {
                             float h[32];
+                            const float* pa = aux + off;
 #pragma unroll
-                            for (int o = 0; o < 32; ++o) h[o] = o0 + o < cout ? __ldg(aux + off + o * vox) : 0.f;
+                            for (int o = 0; o < 32; ++o) {
+                                h[o] = (full || o0 + o < cout) ? __ldg(pa) : 0.f;
+                                pa += vox;
+                            }
 #pragma unroll
                             for (int o = 0; o < 32; o += 2) {
                                 float2 gl, gp;
@@ -459,9 +482,16 @@ linear_fwd_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                                 sum[o + 1] *= gp.y;
                             }
                         }
+                        if (full) {
 #pragma unroll
-                        for (int o = 0; o < 32; ++o)
-                            if (o0 + o < cout) y[off + o * vox] = sum[o];
+                            for (int o = 0; o < 32; ++o) { *py = sum[o]; py += vox; }
+                        } else {
+#pragma unroll
+                            for (int o = 0; o < 32; ++o) {
+                                if (o0 + o < cout) *py = sum[o];
+                                py += vox;
+                            }
+                        }
                     }
                 }
                 start_item(it + 1);
@@ -555,6 +585,7 @@ int linear_fwd_tc_launch(const float* x, const float* W, const float* bias, floa
     const int vtps = (int)((voxels + kGM - 1) / kGM);
     const int otiles = (cout + kGN - 1) / kGN;
     const long long items = batch * vtps * otiles;
+    if (items >= (1LL << 31)) return fail(FZ_ERR_UNSUPPORTED, "linear forward: more than 2^31 (voxel tile, output tile) items");
     const long long cap = 2LL * num_sms();
     const unsigned blocks = (unsigned)(items < cap ? items : cap);
     linear_fwd_tc<<<blocks, kGThreads, kGSmem, st>>>(map_x, map_w, bias, y, aux, y2, epi, wt, cout, cin, voxels, vtps, otiles, items);
