@@ -12,7 +12,7 @@ import torch
 from ._build import LIB_PATH
 
 FZ_MAX_SHIFTS = 8
-FZ_MAX_RANK = 4
+FZ_MAX_RANK = 8
 FZ_SOLVER_MU, FZ_SOLVER_HALS = 0, 1
 FZ_OK, FZ_ERR_INVALID, FZ_ERR_UNSUPPORTED, FZ_ERR_CUDA = 0, 1, 2, 3
 FZ_DTYPE_F32, FZ_DTYPE_BF16 = 0, 1

@@ -493,6 +493,10 @@ static int dispatch_rank(const NmfArgs& a, int R, bool bwd, cudaStream_t st) {
         case 2: return launch_generic<2, WINDOW>(a, bwd, st);
         case 3: return launch_generic<3, WINDOW>(a, bwd, st);
         case 4: return launch_generic<4, WINDOW>(a, bwd, st);
+        case 5: return launch_generic<5, WINDOW>(a, bwd, st);
+        case 6: return launch_generic<6, WINDOW>(a, bwd, st);
+        case 7: return launch_generic<7, WINDOW>(a, bwd, st);
+        case 8: return launch_generic<8, WINDOW>(a, bwd, st);
         default: return fail(FZ_ERR_UNSUPPORTED, "rank %d not supported (1..%d)", R, FZ_MAX_RANK);
     }
 }

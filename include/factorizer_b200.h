@@ -30,7 +30,7 @@ extern "C" {
 
 #define FZ_VERSION 100          /* 0.1.0 */
 #define FZ_MAX_SHIFTS 8
-#define FZ_MAX_RANK 4
+#define FZ_MAX_RANK 8
 
 enum {
     FZ_OK = 0,

@@ -136,8 +136,9 @@ def test_out_of_scope_names_raise(ft):
         ft.NMF(size=(8, 16), init="svd")
     with pytest.raises(NotImplementedError):
         ft.MatrixFactorization(size=(8, 16))                # reference default solver 'cd'
+    assert ft.NMF(size=(64, 512)).rank == 6                 # the default compression on a 64 x 512 matrix: within FZ_MAX_RANK = 8
     with pytest.raises(NotImplementedError):
-        ft.NMF(size=(8, 16), rank=5)
+        ft.NMF(size=(16, 32), rank=9)
 
 
 def test_no_cpu_fallback(ft):
