@@ -500,6 +500,31 @@ def test_layernorm_channels_first(ft, dev, shape):
     assert_close(_np(gb) / scale, _np(rb) / scale, what="gb")
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 8, 8, 8), (1, 64, 6, 10, 4), (3, 200, 50), (1, 512, 8, 8, 8), (2, 8, 4098)])
+def test_layernorm_backward_with_residual_gradient(ft, dev, shape):
+    """fz_layernorm_cf_backward_add: dx = add + LN'(dy) in one pass (every kernel family: register kernels for 8 / 16 / 32
+    channels, the chunked one, the sliced one for few voxels) against torch fp64; d(gamma), d(beta) as without the addend."""
+    from factorizer_b200 import _lib as L
+    lib = L.lib()
+    torch.manual_seed(21)
+    B, C = shape[0], shape[1]
+    x = torch.randn(shape, device=dev)
+    vox = x.numel() // (B * C)
+    gamma, beta = torch.randn(C, device=dev), torch.randn(C, device=dev)
+    gy, add = torch.randn(shape, device=dev), torch.randn(shape, device=dev)
+    dx, dg, db = torch.full_like(x, float("nan")), torch.empty(C, device=dev), torch.empty(C, device=dev)
+    L.check(lib.fz_layernorm_cf_backward_add(x.data_ptr(), gamma.data_ptr(), gy.data_ptr(), add.data_ptr(), dx.data_ptr(), dg.data_ptr(),
+                                             db.data_ptr(), B, C, vox, 1e-5, torch.cuda.current_stream().cuda_stream))
+    x64 = x.double().requires_grad_(True)
+    g64, b64 = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    y64 = torch.nn.functional.layer_norm(x64.movedim(1, -1), (C,), g64, b64, 1e-5).movedim(-1, 1)
+    rx, rg, rb = torch.autograd.grad((y64 * gy.double()).sum(), [x64, g64, b64])
+    assert_close(_np(dx), _np(rx + add.double()), what="dx")
+    scale = max(1.0, float(rg.abs().max()), float(rb.abs().max()))
+    assert_close(_np(dg) / scale, _np(rg) / scale, what="d gamma")
+    assert_close(_np(db) / scale, _np(rb) / scale, what="d beta")
+
+
 @pytest.mark.parametrize("shape,cout,bias", [((1, 64, 32, 32, 32), 128, True), ((2, 96, 8200), 64, True),
                                              ((1, 32, 40, 40, 12), 32, False), ((3, 128, 24, 24, 24), 256, True),
                                              ((1, 96, 32, 32, 32), 40, True), ((2, 200, 32, 32, 16), 32, True)])
