@@ -102,6 +102,9 @@ class BucketedGradAllReduce:
 
     def _hook(self, p: torch.nn.Parameter) -> None:
         b = self._bucket_of[p]
+        if self._ready[b] or self._missing[b] <= 0:
+            raise RuntimeError("BucketedGradAllReduce: a gradient arrived for a bucket that was already reduced -- call zero_grad() "
+                               "before every backward pass (gradient accumulation over several backward passes is not supported)")
         self._missing[b] -= 1
         if self._missing[b] == 0:
             self._pack(b)
