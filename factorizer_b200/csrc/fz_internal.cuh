@@ -24,6 +24,9 @@ struct NmfArgs {
     DevGeom G;
     int shift;  // which window set this launch handles
     int relu;
+    // direct mode only: X (and the gradient accumulator) stay in global memory -- matrices whose working set exceeds one CTA's
+    // shared memory (set by the launcher)
+    int spill;
 };
 
 // fz_nmf_generic.cu

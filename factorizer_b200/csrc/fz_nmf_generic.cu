@@ -196,17 +196,19 @@ __device__ __forceinline__ void load_tile(float* dst, const float* src, long lon
     }
 }
 
-__device__ __forceinline__ Smem carve(float* smem, int M, int N, int R, int T, bool bwd, bool window) {
+__device__ __forceinline__ Smem carve(float* smem, int M, int N, int R, int T, bool bwd, bool window, bool spill) {
     Smem s;
     float* p = smem;
-    s.X = p; p += M * N;
+    s.X = p;
+    if (!spill) p += M * N;
     s.V = p; p += R * N;
     s.U = p; p += M * R;
     s.A = p; p += M * R;
     s.Bm = p; p += R * R;
     s.GX = s.VH = s.UH = s.GV = s.GC = s.GU = s.GA = s.GB = s.red = s.rowpart = nullptr;
     if (bwd) {
-        s.GX = p; p += M * N;
+        s.GX = p;
+        if (!spill) p += M * N;
         s.VH = p; p += (T + 1) * R * N;
         s.UH = p; p += (T + 1) * M * R;
         s.GV = p; p += R * N;
@@ -221,10 +223,11 @@ __device__ __forceinline__ Smem carve(float* smem, int M, int N, int R, int T, b
     return s;
 }
 
-size_t generic_smem_bytes(int M, int N, int R, int T, bool bwd, bool window) {
-    size_t f = (size_t)M * N + (size_t)R * N + 2 * (size_t)M * R + (size_t)R * R;
+size_t generic_smem_bytes(int M, int N, int R, int T, bool bwd, bool window, bool spill = false) {
+    const size_t mn = spill ? 0 : (size_t)M * N;
+    size_t f = mn + (size_t)R * N + 2 * (size_t)M * R + (size_t)R * R;
     if (bwd)
-        f += (size_t)M * N + (size_t)(T + 1) * R * N + (size_t)(T + 1) * M * R + 2 * (size_t)R * N +
+        f += mn + (size_t)(T + 1) * R * N + (size_t)(T + 1) * M * R + 2 * (size_t)R * N +
              2 * (size_t)M * R + (size_t)R * R + (size_t)(kThreads / 32) * R * R + (size_t)M * R * R;
     if (window) f += (size_t)N;
     return f * sizeof(float);
@@ -235,12 +238,14 @@ template <int R, bool WINDOW>
 __global__ void __launch_bounds__(kThreads) nmf_fwd_generic(NmfArgs a) {
     extern __shared__ __align__(16) float smem_f[];
     const int M = a.M, N = a.N;
-    Smem s = carve(smem_f, M, N, R, a.T, false, WINDOW);
+    const bool spill = !WINDOW && a.spill;
+    Smem s = carve(smem_f, M, N, R, a.T, false, WINDOW, spill);
     for (long long mid = blockIdx.x; mid < a.n; mid += gridDim.x) {
         long long base;
         locate<WINDOW>(a, mid, s.coloff, &base);
         if (WINDOW) __syncthreads();
-        load_tile<WINDOW>(s.X, a.x, base, s.coloff, M, N, a.G.vox, WINDOW && a.relu, 1.f);
+        if (spill) s.X = const_cast<float*>(a.x) + base;        // read in place (generic addressing; L2-resident across the sweeps)
+        else load_tile<WINDOW>(s.X, a.x, base, s.coloff, M, N, a.G.vox, WINDOW && a.relu, 1.f);
         for (int e = threadIdx.x; e < M * R; e += blockDim.x) s.U[e] = a.u0[e];
         for (int e = threadIdx.x; e < N * R; e += blockDim.x) s.V[(e % R) * N + e / R] = a.v0[e];
         __syncthreads();
@@ -278,12 +283,18 @@ __global__ void __launch_bounds__(kThreads) nmf_bwd_generic(NmfArgs a) {
     extern __shared__ __align__(16) float smem_f[];
     const int M = a.M, N = a.N, T = a.T;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    Smem s = carve(smem_f, M, N, R, T, true, WINDOW);
+    const bool spill = !WINDOW && a.spill;
+    Smem s = carve(smem_f, M, N, R, T, true, WINDOW, spill);
     for (long long mid = blockIdx.x; mid < a.n; mid += gridDim.x) {
         long long base;
         locate<WINDOW>(a, mid, s.coloff, &base);
         if (WINDOW) __syncthreads();
-        load_tile<WINDOW>(s.X, a.x, base, s.coloff, M, N, a.G.vox, WINDOW && a.relu, 1.f);
+        if (spill) {                                             // X read in place, the gradient accumulated in its output buffer
+            s.X = const_cast<float*>(a.x) + base;
+            s.GX = a.gx + base;
+        } else {
+            load_tile<WINDOW>(s.X, a.x, base, s.coloff, M, N, a.G.vox, WINDOW && a.relu, 1.f);
+        }
         // upstream gradient staged in GX for the two initial products
         if (a.gy) {
             load_tile<WINDOW>(s.GX, a.gy, base, s.coloff, M, N, a.G.vox, false,
@@ -463,8 +474,14 @@ __global__ void __launch_bounds__(kThreads) nmf_bwd_generic(NmfArgs a) {
 
 // ---- host launchers -------------------------------------------------------------------------------
 template <int R, bool WINDOW>
-static int launch_generic(const NmfArgs& a, bool bwd, cudaStream_t st) {
-    const size_t smem = generic_smem_bytes(a.M, a.N, R, a.T, bwd, WINDOW);
+static int launch_generic(const NmfArgs& a_in, bool bwd, cudaStream_t st) {
+    NmfArgs a = a_in;
+    a.spill = 0;
+    size_t smem = generic_smem_bytes(a.M, a.N, R, a.T, bwd, WINDOW);
+    if (smem > 227 * 1024 && !WINDOW) {        // standalone matrices: leave X (and dX) in global memory
+        a.spill = 1;
+        smem = generic_smem_bytes(a.M, a.N, R, a.T, bwd, WINDOW, true);
+    }
     if (smem > 227 * 1024)
         return fail(FZ_ERR_UNSUPPORTED,
                     "matrix %dx%d (rank %d, %d iters) needs %zu B of shared memory in the generic "

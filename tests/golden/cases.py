@@ -26,16 +26,14 @@ NMF_CASES = {
     "hals_r1_32x64": dict(shape=(2, 3, 32, 64), rank=1, solver="hals", num_iters=5, num_grad_steps=None, dist="uniform"),
     # ranks above 4: ft.NMF((64, 512)) with the reference's default compression=10 resolves to rank 6
     # (matrix_factorization.py:480-487); rank 8 is FZ_MAX_RANK
-    # (at 64 x 512 the backward's working set exceeds one CTA's shared memory: forward / decompose only, see FORWARD_ONLY)
-    "mu_r6_64x512": dict(shape=(2, 64, 512), rank=6, solver="mu", num_iters=5, num_grad_steps=None, dist="uniform"),
+    # (at 64 x 512 the backward's working set exceeds one CTA's shared memory, at 128 x 1024 the forward's too: X and dX stay in
+    # global memory there, csrc/fz_nmf_generic.cu `spill`)
+    "mu_r6_64x512": dict(shape=(1, 64, 512), rank=6, solver="mu", num_iters=5, num_grad_steps=None, dist="uniform"),
+    "mu_r2_128x1024": dict(shape=(1, 128, 1024), rank=2, solver="mu", num_iters=4, num_grad_steps=None, dist="uniform"),
     "mu_r6_32x256": dict(shape=(2, 32, 256), rank=6, solver="mu", num_iters=5, num_grad_steps=None, dist="uniform"),
     "hals_r5_16x64": dict(shape=(3, 16, 64), rank=5, solver="hals", num_iters=5, num_grad_steps=None, dist="uniform"),
     "mu_r8_32x128_k3": dict(shape=(2, 2, 32, 128), rank=8, solver="mu", num_iters=5, num_grad_steps=3, dist="uniform"),
 }
-
-# cases whose backward does not fit the generic kernel (the product raises NotImplementedError there): GPU tests check the
-# forward and the factors only
-FORWARD_ONLY = {"mu_r6_64x512"}
 
 # --- SWMatricize / Matricize forward + inverse (bit-exact) ---------------------------------------
 # name -> dict(input_size, kwargs for ft.SWMatricize, cls)
