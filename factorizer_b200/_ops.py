@@ -408,7 +408,7 @@ class FactorizerBlockFn(_GradModeFunction):
 
 
 # ---- FactorizerBlock of any width: channel-map kernels with fused epilogues around the fused core ------------------
-EPI_NONE, EPI_RESIDUAL, EPI_GELU, EPI_GELU_GRAD = 0, 1, 2, 3
+EPI_NONE, EPI_RESIDUAL, EPI_GELU, EPI_GELU_GRAD, EPI_GELU_ONLY = 0, 1, 2, 3, 4
 
 
 def _channel_map(x, w, bias, epi=EPI_NONE, aux=None, transposed=False):
@@ -434,6 +434,8 @@ def _channel_map(x, w, bias, epi=EPI_NONE, aux=None, transposed=False):
         return r, torch.nn.functional.gelu(r)
     if epi == EPI_GELU_GRAD:
         return torch.ops.aten.gelu_backward(r, aux)
+    if epi == EPI_GELU_ONLY:
+        return torch.nn.functional.gelu(r)
     return r
 
 
@@ -506,7 +508,10 @@ class FactorizerBlockWideFn(_GradModeFunction):
             m3 = m.view(B, C, -1)
             x1 = _channel_map(m3, w_out, b_out, EPI_RESIDUAL, x3)
             n2 = _ln_forward(x1, g2, b2n, eps2)
-            h, g = _channel_map(n2, w1, bb1, EPI_GELU)
+            if need_grad:
+                h, g = _channel_map(n2, w1, bb1, EPI_GELU)
+            else:                                                       # inference: the pre-activation is not kept
+                h, g = None, _channel_map(n2, w1, bb1, EPI_GELU_ONLY)
             out = _channel_map(g, w2, bb2, EPI_RESIDUAL, x1)
         if need_grad:
             ctx.save_for_backward(x3, n1, z, m3, x1, n2, h, g, saved, g1, w_in, w_out, g2, w1, w2, u0, v0)

@@ -417,7 +417,7 @@ int fz_linear_forward_ex(const float* x, const float* W, const float* bias, floa
                          int64_t voxels, int32_t epilogue, int32_t w_transposed, const float* aux, float* y2, void* stream) {
     tls().launches = 0;
     if (batch < 0 || cout <= 0 || cin <= 0 || voxels <= 0) return fail(FZ_ERR_INVALID, "linear forward: bad sizes");
-    if (epilogue < FZ_EPILOGUE_NONE || epilogue > FZ_EPILOGUE_GELU_GRAD) return fail(FZ_ERR_INVALID, "linear forward: unknown epilogue %d", epilogue);
+    if (epilogue < FZ_EPILOGUE_NONE || epilogue > FZ_EPILOGUE_GELU_ONLY) return fail(FZ_ERR_INVALID, "linear forward: unknown epilogue %d", epilogue);
     if (batch == 0) return FZ_OK;
     if (!x || !W || !y) return fail(FZ_ERR_INVALID, "linear forward: null buffer");
     if ((epilogue == FZ_EPILOGUE_RESIDUAL || epilogue == FZ_EPILOGUE_GELU_GRAD) && !aux)

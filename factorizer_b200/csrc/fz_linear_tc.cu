@@ -466,6 +466,16 @@ linear_fwd_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                             py += vox; pg += vox;
                         }
                     } else {
+                        if (epi == FZ_EPILOGUE_GELU_ONLY) {
+#pragma unroll
+                            for (int o = 0; o < 32; o += 2) {
+                                float2 e;
+                                const float2 r = make_float2(sum[o], sum[o + 1]);
+                                const float2 gl = __fmul2_rn(r, gauss_cdf2(r, e));
+                                sum[o] = gl.x;
+                                sum[o + 1] = gl.y;
+                            }
+                        }
                         if (epi == FZ_EPILOGUE_GELU_GRAD) {
                             float h[32];
                             const float* pa = aux + off;

@@ -178,10 +178,11 @@ int fz_linear_forward(const float* x, const float* W, const float* bias, float* 
  *   FZ_EPILOGUE_RESIDUAL   y = r + aux                      (x + out_proj(..), x1 + fc2(..): reference factorizer.py:74-77)
  *   FZ_EPILOGUE_GELU       y = r, y2 = gelu(r)  (exact erf)  (fc1 -> GELU, reference layers/mlp.py:54-60; r is kept for the backward)
  *   FZ_EPILOGUE_GELU_GRAD  y = r * gelu'(aux)               (the input gradient of fc2 through the GELU; aux = the saved r of fc1)
+ *   FZ_EPILOGUE_GELU_ONLY  y = gelu(r)                      (inference: the pre-activation is not kept)
  * so that no elementwise pass is left between the channel maps of a block.  w_transposed != 0: W points to a (cin, cout)
  * row-major matrix and r = W^T x + bias -- the input gradient of a layer straight from its weight as stored (cout must be a
  * multiple of 4 then). */
-enum { FZ_EPILOGUE_NONE = 0, FZ_EPILOGUE_RESIDUAL = 1, FZ_EPILOGUE_GELU = 2, FZ_EPILOGUE_GELU_GRAD = 3 };
+enum { FZ_EPILOGUE_NONE = 0, FZ_EPILOGUE_RESIDUAL = 1, FZ_EPILOGUE_GELU = 2, FZ_EPILOGUE_GELU_GRAD = 3, FZ_EPILOGUE_GELU_ONLY = 4 };
 int fz_linear_forward_ex(const float* x, const float* W, const float* bias, float* y, int64_t batch, int32_t cin, int32_t cout,
                          int64_t voxels, int32_t epilogue, int32_t w_transposed, const float* aux, float* y2, void* stream);
 

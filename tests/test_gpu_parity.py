@@ -574,6 +574,8 @@ def test_channel_map_tensor_core_kernel(ft, dev, B, cin, cout, vox, bias):
     run(2)
     assert_close(_np(y), _np(ref), what="GELU epilogue, pre-activation")
     assert_close(_np(y2), _np(torch.nn.functional.gelu(ref)), what="GELU epilogue, activation")
+    run(4)
+    assert_close(_np(y), _np(torch.nn.functional.gelu(ref)), what="GELU-only epilogue")
     run(3)
     a64 = aux.double().requires_grad_(True)
     (gp,) = torch.autograd.grad(torch.nn.functional.gelu(a64).sum(), a64)
