@@ -98,6 +98,10 @@ BLOCK_CASES = {
                          kw=dict(head_dim=8, patch_size=8), nmf=dict(rank=1, num_iters=5, init="uniform", solver="hals")),
     "block_c32_p4": dict(channels=32, spatial=(4, 8, 12), batch=2, mlp_ratio=1.5,
                          kw=dict(head_dim=8, patch_size=4), nmf=dict(rank=1, num_iters=5, init="uniform", solver="hals")),
+    # a width the 32-channel glue kernels do not take, ragged everywhere: 24 channels (not a multiple of the channel map's K chunk),
+    # hidden width 36, 320 voxels per sample (2.5 voxel tiles), two samples: _ops.FactorizerBlockWideFn
+    "block_c24_p4": dict(channels=24, spatial=(4, 4, 20), batch=2, mlp_ratio=1.5,
+                         kw=dict(head_dim=8, patch_size=4), nmf=dict(rank=1, num_iters=5, init="uniform", solver="hals")),
 }
 
 
