@@ -217,15 +217,13 @@ linear_wgrad_tc(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
 // draining a segment overlaps the MMAs of the next one.  Warp 0 = TMA producer, warp 1 = MMA issue, warps 2-9 workers.
 // =====================================================================================================================
 constexpr int kGM = 128, kGN = 64, kGK = 32;         // voxels x outputs per item, channels per K chunk
-constexpr int kGStages = 2;
 constexpr int kGSeg = 4;                              // K chunks per accumulation segment
 constexpr int kGThreads = 320;
 constexpr uint32_t kGA = kGK * kGM * 4;              // x chunk: 4 atoms of (32 channels x 32 voxels) = 16 KiB
 constexpr uint32_t kGB = kGN * kGK * 4;              // W chunk: 64 rows x 128 bytes = 8 KiB
 constexpr uint32_t gA = 0, gAlo = kGA, gB = 2 * kGA, gBlo = 2 * kGA + kGB, kGStage = 2 * kGA + 2 * kGB;   // 48 KiB
-constexpr uint32_t gBarFull = kGStages * kGStage, gBarLo = gBarFull + 8 * kGStages, gBarEmpty = gBarLo + 8 * kGStages,
-                   gBarAccFull = gBarEmpty + 8 * kGStages, gBarAccFree = gBarAccFull + 16, gTmemSlot = gBarAccFree + 16,
-                   kGSmem = gTmemSlot + 8;
+// barriers behind the stages: full / remainder-ready / empty per stage, accumulator full / free per accumulator pair, the TMEM slot
+__host__ __device__ constexpr uint32_t g_smem_bytes(int stages) { return stages * kGStage + 3 * 8 * stages + 16 + 16 + 8; }
 
 // x as (batch, channels, voxels): box (1, 32, 32), the 128-byte rows swizzled in 32-byte atoms
 int make_map_x(CUtensorMap* m, const float* ptr, long long batch, int channels, long long voxels) {
@@ -276,10 +274,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
                  :: "r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 
-__global__ void __launch_bounds__(kGThreads, 2)
+// STAGES = 2: two CTAs per SM (the streaming shapes); STAGES = 4: one CTA per SM with four K chunks in flight, for launches with
+// fewer items than SMs (the 8^3 / 16^3 stages: few voxel tiles, long K), which are bound by the chunk hand-over latency
+template <int STAGES>
+__global__ void __launch_bounds__(kGThreads, STAGES <= 2 ? 2 : 1)
 linear_fwd_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias,
               float* __restrict__ y, const float* __restrict__ aux, float* __restrict__ y2, int epi, int wt, int cout, int cin, long long vox,
               int vtiles_per_sample, int otiles, long long total_items) {
+    constexpr int kGStages = STAGES;
+    constexpr uint32_t gBarFull = kGStages * kGStage, gBarLo = gBarFull + 8 * kGStages, gBarEmpty = gBarLo + 8 * kGStages,
+                       gBarAccFull = gBarEmpty + 8 * kGStages, gBarAccFree = gBarAccFull + 16, gTmemSlot = gBarAccFree + 16;
+    static_assert(gTmemSlot + 8 == g_smem_bytes(STAGES), "shared-memory map");
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, lane = tid & 31;
@@ -590,15 +595,23 @@ int linear_fwd_tc_launch(const float* x, const float* W, const float* bias, floa
     CUtensorMap map_x, map_w;
     if (int e = make_map_x(&map_x, x, batch, cin, voxels)) return e;
     if (int e = wt ? make_map_wt(&map_w, W, cout, cin) : make_map_w(&map_w, W, cout, cin)) return e;
-    static SmemConfig cfg;
-    FZ_CUDA_CHECK(cfg.ensure(linear_fwd_tc, kGSmem));
     const int vtps = (int)((voxels + kGM - 1) / kGM);
     const int otiles = (cout + kGN - 1) / kGN;
     const long long items = batch * vtps * otiles;
     if (items >= (1LL << 31)) return fail(FZ_ERR_UNSUPPORTED, "linear forward: more than 2^31 (voxel tile, output tile) items");
-    const long long cap = 2LL * num_sms();
-    const unsigned blocks = (unsigned)(items < cap ? items : cap);
-    linear_fwd_tc<<<blocks, kGThreads, kGSmem, st>>>(map_x, map_w, bias, y, aux, y2, epi, wt, cout, cin, voxels, vtps, otiles, items);
+    if (items <= num_sms() && cin > 2 * kGK) {            // fewer items than SMs and more than two K chunks: deeper pipeline, one CTA per SM
+        static SmemConfig cfg4;
+        FZ_CUDA_CHECK(cfg4.ensure(linear_fwd_tc<4>, g_smem_bytes(4)));
+        linear_fwd_tc<4><<<(unsigned)items, kGThreads, g_smem_bytes(4), st>>>(map_x, map_w, bias, y, aux, y2, epi, wt, cout, cin, voxels, vtps,
+                                                                             otiles, items);
+    } else {
+        static SmemConfig cfg2;
+        FZ_CUDA_CHECK(cfg2.ensure(linear_fwd_tc<2>, g_smem_bytes(2)));
+        const long long cap = 2LL * num_sms();
+        const unsigned blocks = (unsigned)(items < cap ? items : cap);
+        linear_fwd_tc<2><<<blocks, kGThreads, g_smem_bytes(2), st>>>(map_x, map_w, bias, y, aux, y2, epi, wt, cout, cin, voxels, vtps, otiles,
+                                                                    items);
+    }
     FZ_LAUNCH_CHECK();
     return FZ_OK;
 }
