@@ -209,8 +209,9 @@ linear_wgrad_tc(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
 // A = x, voxel-contiguous = MN-major: TMA boxes of (32 channels x 32 voxels) with SWIZZLE_128B_ATOM_32B are exactly the atoms
 // of the one swizzle 32-bit MN-major operands accept; B = W, K-major, SWIZZLE_128B boxes as in the weight-gradient kernel.
 // The fp32 tiles are the hi operands; eight warps write the remainder tiles and later run the epilogue (thread = voxel = TMEM
-// lane: bias, coalesced stores along the voxel axis).  Persistent CTAs walk (voxel tile, output tile) items; K chunks flow
-// through a two-stage TMA -> remainder -> MMA pipeline that runs across items.  The tensor core adds into its accumulator with
+// lane; bias / residual loaded into the running sums an item ahead; FZ_EPILOGUE_*: + residual, GELU, GELU derivative;
+// coalesced stores along the voxel axis).  Persistent CTAs walk (voxel tile, output tile) items; K chunks flow
+// through a two-stage (four-stage for launches with fewer items than SMs) TMA -> remainder -> MMA pipeline that runs across items.  The tensor core adds into its accumulator with
 // truncation, so a long accumulation chain loses accuracy (1.4e-5 after the 192 MMAs of 512 input channels): an item is cut
 // into SEGMENTS of 4 K chunks, the a_hi b_hi products (16 MMAs per segment) and the two cross terms go to separate accumulators,
 // and the workers add the segments up in registers (round to nearest).  The accumulator pair is double-buffered in TMEM, so
